@@ -1,0 +1,279 @@
+"""ctypes binding of libstif_b200.so (see include/stif_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or no B200 is present the
+calls raise.  Nothing in this module imports `oracle/`.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstif_b200.so")
+
+STIF_OK = 0
+STIF_EINVAL = -1
+STIF_ECUDA = -2
+STIF_ENOMEM = -3
+STIF_ESTATE = -4
+STIF_ENONFINITE = -5
+
+VARIO_PEEL = 1
+VARIO_NO_CULL = 2
+KRIG_F32_STORAGE = 1
+
+ST_MODELS = {"sum": 0, "product": 1, "product_sum": 2, "metric": 3, "sum_metric": 4}
+MARGINAL_MODELS = {"spherical": 0, "gaussian": 1}
+ST_NPARAMS = {"sum": 6, "product": 6, "product_sum": 7, "metric": 4, "sum_metric": 10}
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_u64_p = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol include/stif_b200.h declares
+SIGNATURES = {
+    "stif_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "stif_ctx_destroy": (ctypes.c_int, [_vp]),
+    "stif_last_error": (ctypes.c_char_p, []),
+    "stif_version": (ctypes.c_int, []),
+    "stif_sm_count": (ctypes.c_int, [_vp]),
+    "stif_variogram_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_double,
+                                          ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          _vp, _vp, _vp]),
+    "stif_variogram_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_double,
+                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           _vp, _vp]),
+    "stif_variogram_stats": (ctypes.c_int, [_vp, _c_u64_p]),
+    "stif_kriging_set_obs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int]),
+    "stif_kriging_set_model": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, _vp, ctypes.c_int]),
+    "stif_variogram_model_eval": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
+    "stif_kriging_predict_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                 ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stif_kriging_predict_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stif_kriging_stats": (ctypes.c_int, [_vp, _c_u64_p]),
+    "stif_last_phase_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "stif_bench_dfma": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_float)]),
+}
+
+_lib = None
+
+
+class StifNativeError(RuntimeError):
+    """CUDA/runtime failure inside libstif_b200."""
+
+
+def load_library():
+    """dlopen libstif_b200.so and declare every prototype. Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StifNativeError(
+            f"{LIB_PATH} is not built (run `python -m stif_b200.build`); "
+            "stif_b200 has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _raise(code, where):
+    msg = load_library().stif_last_error().decode("utf-8", "replace")
+    text = f"{where}: {msg} (code {code})"
+    if code in (STIF_EINVAL, STIF_ESTATE):
+        raise ValueError(text)
+    if code == STIF_ENOMEM:
+        raise MemoryError(text)
+    if code == STIF_ENONFINITE:
+        raise np.linalg.LinAlgError(text)
+    raise StifNativeError(text)
+
+
+def _check(code, where):
+    if code != STIF_OK:
+        _raise(code, where)
+
+
+def _f64(a):
+    """Contiguous float64 copy/view; int64 and bool convert exactly (|t| < 2^53)."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def split_space(space):
+    """(n,2) C- or F-ordered array -> two contiguous float64 columns."""
+    space = np.asarray(space)
+    if space.ndim != 2 or space.shape[1] != 2:
+        raise ValueError(f"space must have shape (n, 2), got {space.shape}")
+    return _f64(space[:, 0]), _f64(space[:, 1])
+
+
+class Context:
+    """One libstif_b200 context = one CUDA device. Not thread-safe."""
+
+    def __init__(self, device=-1):
+        self._lib = load_library()
+        h = _vp()
+        _check(self._lib.stif_ctx_create(int(device), ctypes.byref(h)), "stif_ctx_create")
+        self._h = h
+        self._obs_id = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.stif_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return self._lib.stif_sm_count(self._h)
+
+    # ---- variogram ---------------------------------------------------------------
+    def variogram_host(self, x, y, t, v, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
+                       mode=0, mean=0.0, flags=VARIO_PEEL, part=0, nparts=1):
+        x, y, t, v = _f64(x), _f64(y), _f64(t), _f64(v)
+        n = len(x)
+        if not (len(y) == n and len(t) == n and len(v) == n):
+            raise ValueError("x, y, t, v must have the same length")
+        nb = int(n_space_bins) * int(n_time_bins)
+        counts = np.zeros(max(nb, 0), dtype=np.uint64)
+        sums = np.zeros(max(nb, 0), dtype=np.float64)
+        _check(self._lib.stif_variogram_host(
+            self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(v), n, float(space_dist_max),
+            float(time_dist_max), int(n_space_bins), int(n_time_bins), int(mode), float(mean),
+            int(flags), int(part), int(nparts), _ptr(counts), _ptr(sums)), "stif_variogram_host")
+        shape = (int(n_space_bins), int(n_time_bins))
+        return counts.reshape(shape), sums.reshape(shape)
+
+    def variogram_dev(self, x_ptr, y_ptr, t_ptr, v_ptr, n, space_dist_max, time_dist_max,
+                      n_space_bins, n_time_bins, counts_ptr, sums_ptr, mode=0, mean=0.0,
+                      flags=VARIO_PEEL, part=0, nparts=1, stream=0):
+        """Device pointers (ints, e.g. torch tensor.data_ptr()); asynchronous on `stream`."""
+        _check(self._lib.stif_variogram_dev(
+            self._h, x_ptr, y_ptr, t_ptr, v_ptr, int(n), float(space_dist_max),
+            float(time_dist_max), int(n_space_bins), int(n_time_bins), int(mode), float(mean),
+            int(flags), int(part), int(nparts), counts_ptr, sums_ptr, stream or None),
+            "stif_variogram_dev")
+
+    def variogram_stats(self):
+        out = (ctypes.c_uint64 * 4)()
+        _check(self._lib.stif_variogram_stats(self._h, out), "stif_variogram_stats")
+        return {"pairs": int(out[0]), "pairs_evaluated": int(out[1]), "pairs_in_window": int(out[2]),
+                "items": int(out[3])}
+
+    # ---- kriging -----------------------------------------------------------------
+    def kriging_set_obs(self, x, y, t, resid):
+        x, y, t, resid = _f64(x), _f64(y), _f64(t), _f64(resid)
+        n = len(x)
+        if not (len(y) == n and len(t) == n and len(resid) == n):
+            raise ValueError("x, y, t, resid must have the same length")
+        _check(self._lib.stif_kriging_set_obs(self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(resid), n, 0),
+               "stif_kriging_set_obs")
+
+    def kriging_set_obs_dev(self, x_ptr, y_ptr, t_ptr, r_ptr, n):
+        _check(self._lib.stif_kriging_set_obs(self._h, x_ptr, y_ptr, t_ptr, r_ptr, int(n), 1),
+               "stif_kriging_set_obs")
+
+    def kriging_set_model(self, st_model, space_model, time_model, metric_model, params):
+        if st_model not in ST_MODELS:
+            raise KeyError(st_model)
+        for m in (space_model, time_model, metric_model):
+            if m not in MARGINAL_MODELS:
+                raise KeyError(m)
+        p = _f64(params)
+        _check(self._lib.stif_kriging_set_model(
+            self._h, ST_MODELS[st_model], MARGINAL_MODELS[space_model], MARGINAL_MODELS[time_model],
+            MARGINAL_MODELS[metric_model], _ptr(p), len(p)), "stif_kriging_set_model")
+
+    def variogram_model_eval(self, h, t):
+        h_b, t_b = np.broadcast_arrays(np.asarray(h, dtype=np.float64), np.asarray(t, dtype=np.float64))
+        shape = h_b.shape
+        h_c, t_c = _f64(h_b).ravel(), _f64(t_b).ravel()
+        out = np.empty(h_c.shape, dtype=np.float64)
+        _check(self._lib.stif_variogram_model_eval(self._h, _ptr(h_c), _ptr(t_c), h_c.size, _ptr(out)),
+               "stif_variogram_model_eval")
+        return out.reshape(shape)
+
+    def kriging_predict_host(self, tx, ty, tt, min_pts, max_pts, space_dist_max, time_dist_max,
+                             leave_out=None, flags=KRIG_F32_STORAGE, want_weights=False):
+        tx, ty, tt = _f64(tx), _f64(ty), _f64(tt)
+        n = len(tx)
+        if not (len(ty) == n and len(tt) == n):
+            raise ValueError("tx, ty, tt must have the same length")
+        lo = None
+        if leave_out is not None:
+            lo = np.ascontiguousarray(leave_out, dtype=np.int64)
+            if len(lo) != n:
+                raise ValueError("leave_out_idxs must have one entry per target")
+        mean = np.zeros(n, dtype=np.float64)
+        std = np.zeros(n, dtype=np.float64)
+        w = g = idx = nused = None
+        if want_weights:
+            w = np.zeros((n, int(max_pts)), dtype=np.float32)
+            g = np.zeros((n, int(max_pts)), dtype=np.float32)
+            idx = np.zeros((n, int(max_pts)), dtype=np.uint32)
+            nused = np.zeros(n, dtype=np.int32)
+        _check(self._lib.stif_kriging_predict_host(
+            self._h, _ptr(tx), _ptr(ty), _ptr(tt), _ptr(lo), n, int(min_pts), int(max_pts),
+            float(space_dist_max), float(time_dist_max), int(flags), _ptr(mean), _ptr(std),
+            _ptr(w), _ptr(g), _ptr(idx), _ptr(nused)), "stif_kriging_predict_host")
+        if want_weights:
+            return mean, std, w, g, idx, nused
+        return mean, std
+
+    def kriging_predict_dev(self, tx_ptr, ty_ptr, tt_ptr, n, min_pts, max_pts, space_dist_max,
+                            time_dist_max, mean_ptr, std_ptr, leave_out_ptr=None,
+                            flags=KRIG_F32_STORAGE, w_ptr=None, g_ptr=None, idx_ptr=None,
+                            nused_ptr=None, stream=0):
+        _check(self._lib.stif_kriging_predict_dev(
+            self._h, tx_ptr, ty_ptr, tt_ptr, leave_out_ptr, int(n), int(min_pts), int(max_pts),
+            float(space_dist_max), float(time_dist_max), int(flags), mean_ptr, std_ptr, w_ptr, g_ptr,
+            idx_ptr, nused_ptr, stream or None), "stif_kriging_predict_dev")
+
+    def kriging_stats(self):
+        out = (ctypes.c_uint64 * 4)()
+        _check(self._lib.stif_kriging_stats(self._h, out), "stif_kriging_stats")
+        return {"candidates_examined": int(out[0]), "candidates_in_window": int(out[1]),
+                "targets_below_min": int(out[2]), "targets_singular": int(out[3])}
+
+    # ---- measurement -------------------------------------------------------------
+    def last_phase_ms(self):
+        out = (ctypes.c_float * 4)()
+        _check(self._lib.stif_last_phase_ms(self._h, out), "stif_last_phase_ms")
+        return [float(v) for v in out]
+
+    def bench_dfma(self, iters=4096):
+        rate = ctypes.c_double()
+        ms = ctypes.c_float()
+        _check(self._lib.stif_bench_dfma(self._h, int(iters), ctypes.byref(rate), ctypes.byref(ms)),
+               "stif_bench_dfma")
+        return rate.value, ms.value
+
+
+_default_ctx = None
+
+
+def default_context():
+    """Process-wide context on the current CUDA device (LOCAL_RANK if set)."""
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("STIF_B200_DEVICE", os.environ.get("LOCAL_RANK", "-1")))
+        _default_ctx = Context(dev)
+    return _default_ctx

@@ -1,0 +1,98 @@
+// common.cuh -- context, error handling and scratch management shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/stif_b200.h"
+
+namespace stif {
+
+void set_error(const char *fmt, ...);
+
+#define STIF_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            stif::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                \
+                            cudaGetErrorString(e__));                                    \
+            return (e__ == cudaErrorMemoryAllocation) ? STIF_ENOMEM : STIF_ECUDA;        \
+        }                                                                                \
+    } while (0)
+
+#define STIF_TRY(call)                                                                   \
+    do {                                                                                 \
+        int r__ = (call);                                                                \
+        if (r__ != STIF_OK) return r__;                                                  \
+    } while (0)
+
+// A grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return STIF_OK;
+        if (p) {
+            STIF_CUDA(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            return STIF_ENOMEM;
+        }
+        cap = want;
+        return STIF_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct KrigModel {
+    int st_model = -1, space_model = 0, time_model = 0, metric_model = 0;
+    int nparams = 0;
+    double x[10] = {0};
+};
+
+}  // namespace stif
+
+struct stif_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;      // the context's own stream
+    cudaEvent_t ev[6] = {nullptr};      // phase timing events
+    int n_phase = 0;                    // number of valid phases recorded in the last call
+    cudaStream_t last_stream = nullptr; // stream the last call was enqueued on
+
+    // ---- variogram scratch ----
+    stif::DevBuf v_keys, v_keys_out, v_idx, v_idx_out, v_cubtmp;  // time sort
+    stif::DevBuf v_pts;                                            // sorted AoS double4
+    stif::DevBuf v_tileinfo;   // per i-tile j-range + prefix (work list)
+    stif::DevBuf v_partial;    // per-block partial histograms
+    stif::DevBuf v_stats;      // device counters
+    stif::DevBuf v_stage;      // staging for host entry point
+    uint64_t v_stats_host[4] = {0, 0, 0, 0};
+
+    // ---- kriging state ----
+    int64_t n_obs = 0;
+    stif::DevBuf k_obs;        // obs SoA (x, y, t, resid) as given
+    stif::KrigModel model;
+    stif::DevBuf k_scratch[16];
+    stif::DevBuf k_stats;
+    uint64_t k_stats_host[4] = {0, 0, 0, 0};
+    // grid cache key
+    double grid_smax = -1, grid_tmax = -1;
+    int64_t grid_nobs = -1;
+};

@@ -1,0 +1,151 @@
+// context.cu -- context lifetime, error strings, phase timers, FP64 peak microbenchmark.
+#include "common.cuh"
+
+namespace stif {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// 8 independent DFMA chains per thread, all operands in registers.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3;
+    double r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            r0 = __fma_rn(r0, a, b);
+            r1 = __fma_rn(r1, a, b);
+            r2 = __fma_rn(r2, a, b);
+            r3 = __fma_rn(r3, a, b);
+            r4 = __fma_rn(r4, a, b);
+            r5 = __fma_rn(r5, a, b);
+            r6 = __fma_rn(r6, a, b);
+            r7 = __fma_rn(r7, a, b);
+        }
+    }
+    double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    if (s == 123.456) out[0] = s;  // never true for the chosen a, b; keeps the chains live
+}
+
+}  // namespace stif
+
+extern "C" {
+
+const char *stif_last_error(void) { return stif::g_err; }
+
+int stif_version(void) { return 100; }
+
+int stif_ctx_create(int device, stif_ctx **out)
+{
+    if (!out) {
+        stif::set_error("stif_ctx_create: out is NULL");
+        return STIF_EINVAL;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        stif::set_error("no CUDA device available (%s); libstif_b200 has no CPU fallback",
+                        cudaGetErrorString(e));
+        cudaGetLastError();
+        return STIF_ECUDA;
+    }
+    if (device < 0) STIF_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) {
+        stif::set_error("device %d out of range (%d devices)", device, ndev);
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    STIF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        stif::set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                        device, prop.major, prop.minor);
+        return STIF_ECUDA;
+    }
+    stif_ctx *c = new stif_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    STIF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) STIF_CUDA(cudaEventCreate(&c->ev[i]));
+    *out = c;
+    return STIF_OK;
+}
+
+int stif_ctx_destroy(stif_ctx *c)
+{
+    if (!c) return STIF_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->v_keys.release();
+    c->v_keys_out.release();
+    c->v_idx.release();
+    c->v_idx_out.release();
+    c->v_cubtmp.release();
+    c->v_pts.release();
+    c->v_tileinfo.release();
+    c->v_partial.release();
+    c->v_stats.release();
+    c->v_stage.release();
+    c->k_obs.release();
+    c->k_stats.release();
+    for (auto &b : c->k_scratch) b.release();
+    for (int i = 0; i < 6; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return STIF_OK;
+}
+
+int stif_sm_count(stif_ctx *c) { return c ? c->sm_count : 0; }
+
+int stif_last_phase_ms(stif_ctx *c, float out[4])
+{
+    if (!c || !out) {
+        stif::set_error("stif_last_phase_ms: NULL argument");
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < 4; ++i) out[i] = 0.f;
+    if (c->n_phase == 0) return STIF_OK;
+    STIF_CUDA(cudaEventSynchronize(c->ev[c->n_phase]));
+    for (int i = 0; i < c->n_phase && i < 4; ++i)
+        STIF_CUDA(cudaEventElapsedTime(&out[i], c->ev[i], c->ev[i + 1]));
+    return STIF_OK;
+}
+
+int stif_bench_dfma(stif_ctx *c, int iters, double *lane_instr_per_s, float *ms_out)
+{
+    if (!c || iters <= 0) {
+        stif::set_error("stif_bench_dfma: bad argument");
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    double *d = nullptr;
+    STIF_CUDA(cudaMalloc(&d, 8));
+    const int blocks = c->sm_count * 8, threads = 256;
+    // warm-up
+    stif::dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(d, iters / 4 + 1, 1.0000001, 1e-9);
+    STIF_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    stif::dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(d, iters, 1.0000001, 1e-9);
+    STIF_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    STIF_CUDA(cudaEventSynchronize(c->ev[1]));
+    float ms = 0.f;
+    STIF_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->n_phase = 0;
+    STIF_CUDA(cudaFree(d));
+    const double n_instr = (double)blocks * threads * (double)iters * 64.0;
+    if (lane_instr_per_s) *lane_instr_per_s = n_instr / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return STIF_OK;
+}
+
+}  // extern "C"

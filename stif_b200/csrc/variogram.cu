@@ -1,0 +1,592 @@
+// variogram.cu -- all-pairs empirical space-time variogram / covariogram on sm_100a.
+//
+// Replaces the numba loop of stif/utils.py:104-190 (get_variogram) and :193-279
+// (get_covariogram), all-pairs branch of _pair_index_generator (stif/utils.py:87-92).
+//
+// Executed arithmetic (bit-exact with the reference's LLVM fast-math code, see
+// oracle/oracle_variogram.c): d2 = fma(dy,dy,rn(dx*dx)); the cut-off sqrt_rn(d2) > smax
+// is evaluated as d2 > T where T is the largest double with sqrt_rn(T) <= smax (exact,
+// monotone; found on the host); bins are trunc(sqrt_rn(d2)*(1/ws)), trunc(|dt|*(1/wt)).
+//
+// Pipeline (all on one stream, no host synchronisation):
+//   1. pack time keys, radix-sort observation indices by time (CUB; plumbing)
+//   2. gather into a time-sorted AoS double4 {x,y,t,v} array, NaN-padded to a tile multiple
+//   3. per i-tile (1024 obs) find the last j-sub-tile (256 obs) that can still be inside
+//      the time window -> work list of (i-tile, j-sub-tile) items; every other tile pair
+//      is provably outside |dt| <= tmax and is never visited ("culling")
+//   4. persistent pair kernel: grid = SMs x resident CTAs; block b takes items
+//      b, b+grid, ... of its partition (static, deterministic).  Per item each thread
+//      keeps 4 i-points in registers and sweeps the 256 j-points broadcast from shared
+//      memory: 7 FP64-pipe instructions per pair.  Pairs inside the window are pushed to
+//      a per-thread shared-memory queue (2 predicated instructions, no branch) and binned
+//      later in a dense drain loop with shared-memory histogram atomics.
+//   5. deterministic fixed-order reduction of the per-block partial histograms.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+
+namespace stif {
+namespace vario {
+
+constexpr int VT = 256;        // threads per block
+constexpr int VR = 4;          // i-points per thread (registers)
+constexpr int TI = VT * VR;    // i-tile: 1024 observations
+constexpr int TJ = 256;        // j-sub-tile: 256 observations (8-bit index in the queue)
+constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
+constexpr int QCAP = 32;       // queue slots per thread (uint16 each)
+constexpr int VG = 4;          // j-iterations between queue-overflow checks
+constexpr int MAX_BINS = 8192; // shared-memory histogram limit (12 B per bin)
+constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x 2^18 pairs < 2^32: u32 counts are safe
+
+struct Params {
+    const double4 *pts;   // sorted, padded observations
+    const int *item_prefix;  // [nI+1] exclusive prefix of items per i-tile
+    const int *item_jbeg;    // [nI]  (= I*JPI)
+    int nI;
+    int n_bins, n_time_bins, n_space_bins;
+    int mode;
+    int part, nparts;
+    double tcut;     // largest d2 with sqrt_rn(d2) <= space_dist_max
+    double tmax;     // time_dist_max
+    double inv_ws, inv_wt;
+    double mean;
+    double *partial_sum;           // [grid][n_bins]
+    unsigned long long *partial_cnt;  // [grid][n_bins]
+    unsigned long long *stats;     // [4]
+};
+
+__global__ void pack_keys_kernel(const double *t, int64_t n, double *keys, unsigned *idx)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = t[i];
+        idx[i] = (unsigned)i;
+    }
+}
+
+__global__ void iota_kernel(int64_t n, unsigned *idx)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (unsigned)i;
+}
+
+__global__ void gather_kernel(const double *x, const double *y, const double *t, const double *v,
+                              const unsigned *idx, int64_t n, int64_t n_pad, double4 *pts)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pad) return;
+    double4 p;
+    if (k < n) {
+        unsigned i = idx[k];
+        p = make_double4(x[i], y[i], t[i], v[i]);
+    } else {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        p = make_double4(qnan, qnan, qnan, 0.0);  // NaN never passes d2 <= tcut
+    }
+    pts[k] = p;
+}
+
+// One thread per i-tile: last j-sub-tile that may hold a pair with rn(tj - ti) <= tmax.
+// Sorted ascending by t, so the smallest lag between i-tile I and sub-tile J (beyond the
+// diagonal) is rn(t[J*TJ] - t_last(I)), and rounding is monotone.
+__global__ void tile_range_kernel(const double4 *pts, int64_t n, int nI, int nJ, double tmax,
+                                  int cull, int *count, int *jbeg)
+{
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nI) return;
+    const int jb = I * JPI;
+    int jend = nJ - 1;
+    if (cull) {
+        int64_t last = (int64_t)I * TI + TI - 1;
+        if (last > n - 1) last = n - 1;
+        const double ti_max = pts[last].z;
+        // first J in (jb+JPI-1, nJ) with lag > tmax; all later ones are also outside
+        int lo = jb + JPI, hi = nJ;  // search in [lo, hi)
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            double lag = __dsub_rn(pts[(int64_t)mid * TJ].z, ti_max);
+            if (lag > tmax) hi = mid; else lo = mid + 1;
+        }
+        jend = lo - 1;
+    }
+    if (jend > nJ - 1) jend = nJ - 1;
+    int c = jend - jb + 1;
+    if (c < 0) c = 0;
+    count[I] = c;
+    jbeg[I] = jb;
+}
+
+// Single-block exclusive scan (nI is small: n/1024).
+__global__ void scan_kernel(const int *count, int nI, int *prefix)
+{
+    __shared__ int s_part[1024];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nI; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = (i < nI) ? count[i] : 0;
+        s_part[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            int a = (threadIdx.x >= off) ? s_part[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_part[threadIdx.x] += a;
+            __syncthreads();
+        }
+        int incl = s_part[threadIdx.x];
+        if (i < nI) prefix[i] = s_carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[nI] = s_carry;
+}
+
+struct Smem {
+    double4 *s_i;          // [TI]
+    double4 *s_j;          // [TJ]
+    unsigned short *q;     // [QCAP][VT]
+    double *s_sum;         // [n_bins]
+    unsigned *s_cnt;       // [n_bins]
+};
+
+__device__ __forceinline__ void st_shared_u16(unsigned addr, unsigned short v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+__device__ __forceinline__ void drain(const Smem &S, const Params &P, int tid, int cnt)
+{
+    for (int s = 0; s < cnt; ++s) {
+        const unsigned e = S.q[s * VT + tid];
+        const int j = e & 0xff, r = e >> 8;
+        const double4 pi = S.s_i[r * VT + tid];
+        const double4 pj = S.s_j[j];
+        const double dx = __dsub_rn(pi.x, pj.x);
+        const double dy = __dsub_rn(pi.y, pj.y);
+        const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
+        const double lag_s = __dsqrt_rn(d2);
+        const double lag_t = fabs(__dsub_rn(pi.z, pj.z));
+        const long long bs = __double2ll_rz(__dmul_rn(lag_s, P.inv_ws));
+        const long long bt = __double2ll_rz(__dmul_rn(lag_t, P.inv_wt));
+        if (bs >= 0 && bs < P.n_space_bins && bt >= 0 && bt < P.n_time_bins) {
+            double a, b;
+            if (P.mode == 0) {
+                a = __dsub_rn(pi.w, pj.w);
+                b = a;
+            } else {
+                a = __dsub_rn(pi.w, P.mean);
+                b = __dsub_rn(pj.w, P.mean);
+            }
+            const int bin = (int)bs * P.n_time_bins + (int)bt;
+            atomicAdd(&S.s_sum[bin], __dmul_rn(a, b));
+            atomicAdd(&S.s_cnt[bin], 1u);
+        }
+    }
+}
+
+template <bool DIAG>
+__device__ __forceinline__ unsigned scan_item(const Smem &S, const Params &P, int tid, int ioff0)
+{
+    double xi[VR], yi[VR], ti[VR];
+    int ioff[VR];
+#pragma unroll
+    for (int r = 0; r < VR; ++r) {
+        const double4 p = S.s_i[r * VT + tid];
+        xi[r] = p.x;
+        yi[r] = p.y;
+        ti[r] = p.z;
+        ioff[r] = ioff0 + r * VT;  // (global i) - (global j of sub-tile start)
+    }
+    const double tcut = P.tcut, tmax = P.tmax;
+    unsigned npass = 0;
+    // 32-bit shared-window address of this thread's next free queue slot
+    const unsigned qbase = (unsigned)__cvta_generic_to_shared(S.q + tid);
+    unsigned qa = qbase;
+    const unsigned qhigh = qbase + (QCAP - VG * VR) * VT * 2;
+    for (int jb = 0; jb < TJ; jb += VG) {
+        if (__any_sync(0xffffffffu, qa > qhigh)) {
+            const int cnt = (int)((qa - qbase) / (2 * VT));
+            drain(S, P, tid, cnt);
+            npass += cnt;
+            qa = qbase;
+        }
+#pragma unroll
+        for (int g = 0; g < VG; ++g) {
+            const int j = jb + g;
+            const double4 pj = S.s_j[j];
+#pragma unroll
+            for (int r = 0; r < VR; ++r) {
+                const double dx = __dsub_rn(xi[r], pj.x);
+                const double dy = __dsub_rn(yi[r], pj.y);
+                const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
+                const double dt = fabs(__dsub_rn(ti[r], pj.z));
+                bool pass = (d2 <= tcut) && (dt <= tmax);
+                if (DIAG) pass = pass && (j > ioff[r]);
+                if (pass) {
+                    st_shared_u16(qa, (unsigned short)(j | (r << 8)));
+                    qa += 2 * VT;
+                }
+            }
+        }
+    }
+    const int cnt = (int)((qa - qbase) / (2 * VT));
+    drain(S, P, tid, cnt);
+    npass += cnt;
+    return npass;
+}
+
+__global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem S;
+    S.s_i = reinterpret_cast<double4 *>(smem_raw);
+    S.s_j = S.s_i + TI;
+    S.q = reinterpret_cast<unsigned short *>(S.s_j + TJ);
+    S.s_sum = reinterpret_cast<double *>(S.q + QCAP * VT);
+    S.s_cnt = reinterpret_cast<unsigned *>(S.s_sum + P.n_bins);
+
+    const int tid = threadIdx.x;
+    for (int b = tid; b < P.n_bins; b += VT) {
+        S.s_sum[b] = 0.0;
+        S.s_cnt[b] = 0u;
+    }
+    unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
+    double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
+    for (int b = tid; b < P.n_bins; b += VT) my_cnt[b] = 0ull;
+
+    const long long M = P.item_prefix[P.nI];  // total items
+    unsigned long long npass = 0;
+    unsigned items_done = 0, items_total = 0;
+    // this partition owns items w with w % nparts == part; block b takes every grid-th
+    for (long long k = blockIdx.x;; k += gridDim.x) {
+        const long long w = k * P.nparts + P.part;
+        if (w >= M) break;
+        // item -> (I, J): largest I with prefix[I] <= w
+        int lo = 0, hi = P.nI - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (P.item_prefix[mid] <= w) lo = mid; else hi = mid - 1;
+        }
+        const int I = lo;
+        const int J = P.item_jbeg[I] + (int)(w - P.item_prefix[I]);
+
+        __syncthreads();  // previous item finished with the tiles
+        const double4 *gi = P.pts + (size_t)I * TI;
+        const double4 *gj = P.pts + (size_t)J * TJ;
+#pragma unroll
+        for (int r = 0; r < VR; ++r) S.s_i[r * VT + tid] = gi[r * VT + tid];
+        S.s_j[tid] = gj[tid];
+        __syncthreads();
+
+        const int ioff0 = (I * TI + tid) - J * TJ;
+        if (J < I * JPI + JPI)
+            npass += scan_item<true>(S, P, tid, ioff0);
+        else
+            npass += scan_item<false>(S, P, tid, ioff0);
+
+        ++items_total;
+        if (++items_done == FLUSH_ITEMS) {
+            __syncthreads();
+            for (int b = tid; b < P.n_bins; b += VT) {
+                my_cnt[b] += S.s_cnt[b];
+                S.s_cnt[b] = 0u;
+            }
+            items_done = 0;
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < P.n_bins; b += VT) {
+        my_cnt[b] += S.s_cnt[b];
+        my_sum[b] = S.s_sum[b];
+    }
+    // stats: passing pairs (warp reduce, one atomic per warp)
+    for (int off = 16; off > 0; off >>= 1) npass += __shfl_xor_sync(0xffffffffu, npass, off);
+    if ((tid & 31) == 0 && npass) atomicAdd(&P.stats[2], npass);
+    if (tid == 0 && items_total) atomicAdd(&P.stats[3], (unsigned long long)items_total);
+}
+
+// Fixed-order reduction over the per-block partials + the reference's peeled first pair.
+__global__ void reduce_kernel(Params P, int nblocks, const double *x, const double *y,
+                              const double *t, const double *v, int64_t n, double smax,
+                              double ws, double wt, int peel, unsigned long long *counts,
+                              double *sums)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.n_bins) return;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long c = 0;
+    for (int k = 0; k < nblocks; ++k) {
+        acc[k & 7] += P.partial_sum[(size_t)k * P.n_bins + b];
+        c += P.partial_cnt[(size_t)k * P.n_bins + b];
+    }
+    double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    if (peel && n >= 2) {
+        // rows 0 and 1 of the caller's arrays: the pair kernel binned them with the
+        // reciprocal multiply; the reference bins this one pair with a true division.
+        const double dx = __dsub_rn(x[0], x[1]), dy = __dsub_rn(y[0], y[1]);
+        const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
+        const double lag_s = __dsqrt_rn(d2);
+        const double lag_t = fabs(__dsub_rn(t[0], t[1]));
+        if (!(lag_s > smax) && !(lag_t > P.tmax) && d2 == d2 && lag_t == lag_t) {
+            const long long bs_m = __double2ll_rz(__dmul_rn(lag_s, P.inv_ws));
+            const long long bt_m = __double2ll_rz(__dmul_rn(lag_t, P.inv_wt));
+            const long long bs_d = __double2ll_rz(__ddiv_rn(lag_s, ws));
+            const long long bt_d = __double2ll_rz(__ddiv_rn(lag_t, wt));
+            const bool in_m = bs_m >= 0 && bs_m < P.n_space_bins && bt_m >= 0 && bt_m < P.n_time_bins;
+            const bool in_d = bs_d >= 0 && bs_d < P.n_space_bins && bt_d >= 0 && bt_d < P.n_time_bins;
+            const long long bin_m = in_m ? bs_m * P.n_time_bins + bt_m : -1;
+            const long long bin_d = in_d ? bs_d * P.n_time_bins + bt_d : -1;
+            if (bin_m != bin_d) {
+                double a, bb;
+                if (P.mode == 0) {
+                    a = __dsub_rn(v[0], v[1]);
+                    bb = a;
+                } else {
+                    a = __dsub_rn(v[0], P.mean);
+                    bb = __dsub_rn(v[1], P.mean);
+                }
+                const double val = __dmul_rn(a, bb);
+                if (bin_m == b) {
+                    c -= 1;
+                    s -= val;
+                }
+                if (bin_d == b) {
+                    c += 1;
+                    s += val;
+                }
+            }
+        }
+    }
+    counts[b] = c;
+    sums[b] = s;
+}
+
+// Largest double T with sqrt_rn(T) <= smax (host; IEEE sqrt is correctly rounded and
+// monotone, so sqrt_rn(d2) > smax  <=>  d2 > T).
+static double sqrt_cut_threshold(double smax)
+{
+    if (isnan(smax)) return -1.0;                 // "lag > NaN" is never true in IEEE, but
+                                                  // fast-math makes it UB; treat as empty
+    if (smax < 0.0) return -1.0;                  // sqrt >= 0 > smax for every pair
+    if (isinf(smax)) return INFINITY;
+    double c = smax * smax;
+    if (isinf(c)) c = 1.79769313486231570815e308;
+    while (sqrt(c) > smax) c = nextafter(c, -INFINITY);
+    for (;;) {
+        double up = nextafter(c, INFINITY);
+        if (isinf(up) || sqrt(up) > smax) break;
+        c = up;
+    }
+    return c;
+}
+
+}  // namespace vario
+}  // namespace stif
+
+using namespace stif;
+using namespace stif::vario;
+
+extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y, const double *t,
+                                  const double *v, int64_t n, double smax, double tmax, int ns,
+                                  int nt, int mode, double mean, int flags, int part, int nparts,
+                                  uint64_t *counts_dev, double *sums_dev, void *stream_v)
+{
+    if (!c) {
+        set_error("stif_variogram: ctx is NULL");
+        return STIF_EINVAL;
+    }
+    if (ns <= 0 || nt <= 0 || (int64_t)ns * nt > MAX_BINS) {
+        set_error("stif_variogram: n_space_bins*n_time_bins must be in [1, %d] (got %d x %d)",
+                  MAX_BINS, ns, nt);
+        return STIF_EINVAL;
+    }
+    if (n < 0 || n > 0x7fffffff - 2 * TI) {
+        set_error("stif_variogram: n = %lld out of range", (long long)n);
+        return STIF_EINVAL;
+    }
+    if (mode != 0 && mode != 1) {
+        set_error("stif_variogram: mode must be 0 (variogram) or 1 (covariogram)");
+        return STIF_EINVAL;
+    }
+    if (nparts < 1 || part < 0 || part >= nparts) {
+        set_error("stif_variogram: bad partition %d of %d", part, nparts);
+        return STIF_EINVAL;
+    }
+    if (!counts_dev || !sums_dev || (n > 0 && (!x || !y || !t || !v))) {
+        set_error("stif_variogram: NULL pointer argument");
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    c->last_stream = st;
+    const int n_bins = ns * nt;
+    const bool cull = !(flags & STIF_VARIO_NO_CULL);
+
+    STIF_TRY(c->v_stats.reserve(4 * sizeof(unsigned long long)));
+    STIF_CUDA(cudaMemsetAsync(c->v_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    STIF_CUDA(cudaEventRecord(c->ev[0], st));
+    c->n_phase = 3;
+
+    if (n < 2) {
+        STIF_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * n_bins, st));
+        STIF_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * n_bins, st));
+        for (int i = 1; i <= 3; ++i) STIF_CUDA(cudaEventRecord(c->ev[i], st));
+        c->v_stats_host[0] = c->v_stats_host[1] = c->v_stats_host[3] = 0;
+        return STIF_OK;
+    }
+
+    const int64_t n_pad = (n + TI - 1) / TI * TI;
+    const int nI = (int)(n_pad / TI), nJ = (int)(n_pad / TJ);
+
+    // 1. sort indices by time
+    STIF_TRY(c->v_idx.reserve(sizeof(unsigned) * n));
+    STIF_TRY(c->v_idx_out.reserve(sizeof(unsigned) * n));
+    const int tb = 256;
+    const unsigned nb_n = (unsigned)((n + tb - 1) / tb);
+    const unsigned *order = nullptr;
+    if (cull) {
+        STIF_TRY(c->v_keys.reserve(sizeof(double) * n));
+        STIF_TRY(c->v_keys_out.reserve(sizeof(double) * n));
+        pack_keys_kernel<<<nb_n, tb, 0, st>>>(t, n, c->v_keys.as<double>(), c->v_idx.as<unsigned>());
+        size_t tmp_bytes = 0;
+        STIF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->v_keys.as<double>(),
+                                                  c->v_keys_out.as<double>(),
+                                                  c->v_idx.as<unsigned>(),
+                                                  c->v_idx_out.as<unsigned>(), (int)n, 0, 64, st));
+        STIF_TRY(c->v_cubtmp.reserve(tmp_bytes));
+        STIF_CUDA(cub::DeviceRadixSort::SortPairs(c->v_cubtmp.p, tmp_bytes, c->v_keys.as<double>(),
+                                                  c->v_keys_out.as<double>(),
+                                                  c->v_idx.as<unsigned>(),
+                                                  c->v_idx_out.as<unsigned>(), (int)n, 0, 64, st));
+        order = c->v_idx_out.as<unsigned>();
+    } else {
+        iota_kernel<<<nb_n, tb, 0, st>>>(n, c->v_idx.as<unsigned>());
+        order = c->v_idx.as<unsigned>();
+    }
+    // 2. gather into sorted, padded AoS
+    STIF_TRY(c->v_pts.reserve(sizeof(double4) * n_pad));
+    gather_kernel<<<(unsigned)((n_pad + tb - 1) / tb), tb, 0, st>>>(x, y, t, v, order, n, n_pad,
+                                                                    c->v_pts.as<double4>());
+    // 3. work list
+    STIF_TRY(c->v_tileinfo.reserve(sizeof(int) * (3 * (size_t)nI + 1)));
+    int *count = c->v_tileinfo.as<int>();
+    int *jbeg = count + nI;
+    int *prefix = jbeg + nI;
+    tile_range_kernel<<<(nI + 127) / 128, 128, 0, st>>>(c->v_pts.as<double4>(), n, nI, nJ, tmax,
+                                                        cull ? 1 : 0, count, jbeg);
+    scan_kernel<<<1, 1024, 0, st>>>(count, nI, prefix);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaEventRecord(c->ev[1], st));
+
+    // 4. pair kernel
+    Params P;
+    P.pts = c->v_pts.as<double4>();
+    P.item_prefix = prefix;
+    P.item_jbeg = jbeg;
+    P.nI = nI;
+    P.n_bins = n_bins;
+    P.n_time_bins = nt;
+    P.n_space_bins = ns;
+    P.mode = mode;
+    P.part = part;
+    P.nparts = nparts;
+    P.tcut = sqrt_cut_threshold(smax);
+    P.tmax = tmax;
+    const double ws = smax / (double)ns, wt = tmax / (double)nt;  // utils.py:146-147
+    P.inv_ws = 1.0 / ws;
+    P.inv_wt = 1.0 / wt;
+    P.mean = mean;
+    P.stats = c->v_stats.as<unsigned long long>();
+
+    const size_t smem = sizeof(double4) * (TI + TJ) + sizeof(unsigned short) * QCAP * VT +
+                        (sizeof(double) + sizeof(unsigned)) * (size_t)n_bins;
+    STIF_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    int occ = 0;
+    STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel, VT, smem));
+    if (occ < 1) {
+        set_error("stif_variogram: pair kernel does not fit (smem %zu B)", smem);
+        return STIF_ECUDA;
+    }
+    const int grid = c->sm_count * occ;
+    STIF_TRY(c->v_partial.reserve((sizeof(double) + sizeof(unsigned long long)) * (size_t)grid *
+                                  n_bins));
+    P.partial_sum = c->v_partial.as<double>();
+    P.partial_cnt = reinterpret_cast<unsigned long long *>(P.partial_sum + (size_t)grid * n_bins);
+    pair_kernel<<<grid, VT, smem, st>>>(P);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaEventRecord(c->ev[2], st));
+
+    // 5. reduce (+ peel fix-up on partition 0)
+    const int peel = ((flags & STIF_VARIO_PEEL) && part == 0) ? 1 : 0;
+    reduce_kernel<<<(n_bins + 127) / 128, 128, 0, st>>>(
+        P, grid, x, y, t, v, n, smax, ws, wt, peel,
+        reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaEventRecord(c->ev[3], st));
+
+    const uint64_t all_pairs = (uint64_t)n * (uint64_t)(n - 1) / 2;
+    c->v_stats_host[0] = all_pairs / (uint64_t)nparts;
+    return STIF_OK;
+}
+
+extern "C" int stif_variogram_stats(stif_ctx *c, uint64_t out[4])
+{
+    if (!c || !out) {
+        set_error("stif_variogram_stats: NULL argument");
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    out[0] = c->v_stats_host[0];
+    out[1] = out[2] = out[3] = 0;
+    if (!c->v_stats.p || !c->v_tileinfo.p) return STIF_OK;
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    STIF_CUDA(cudaStreamSynchronize(st));
+    unsigned long long h[4];
+    STIF_CUDA(cudaMemcpy(h, c->v_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    out[2] = h[2];
+    out[3] = h[3];
+    out[1] = h[3] * (uint64_t)TI * TJ;
+    return STIF_OK;
+}
+
+extern "C" int stif_variogram_host(stif_ctx *c, const double *x, const double *y, const double *t,
+                                   const double *v, int64_t n, double smax, double tmax, int ns,
+                                   int nt, int mode, double mean, int flags, int part, int nparts,
+                                   uint64_t *counts_host, double *sums_host)
+{
+    if (!c) {
+        set_error("stif_variogram: ctx is NULL");
+        return STIF_EINVAL;
+    }
+    if (ns <= 0 || nt <= 0 || (int64_t)ns * nt > MAX_BINS || n < 0) {
+        set_error("stif_variogram: bad sizes (n=%lld, bins %d x %d, limit %d bins)", (long long)n,
+                  ns, nt, MAX_BINS);
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    const size_t nb = (size_t)ns * nt;
+    const size_t in_bytes = sizeof(double) * (size_t)n;
+    const size_t out_off = (4 * in_bytes + 255) / 256 * 256;
+    STIF_TRY(c->v_stage.reserve(out_off + nb * 16));
+    char *base = c->v_stage.as<char>();
+    double *dx = (double *)base, *dy = dx + n, *dt = dy + n, *dv = dt + n;
+    uint64_t *dc = (uint64_t *)(base + out_off);
+    double *ds = (double *)(base + out_off + nb * 8);
+    cudaStream_t st = c->stream;
+    if (n > 0) {
+        STIF_CUDA(cudaMemcpyAsync(dx, x, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dy, y, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dt, t, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dv, v, in_bytes, cudaMemcpyHostToDevice, st));
+    }
+    STIF_TRY(stif_variogram_dev(c, dx, dy, dt, dv, n, smax, tmax, ns, nt, mode, mean, flags, part,
+                                nparts, dc, ds, st));
+    STIF_CUDA(cudaMemcpyAsync(counts_host, dc, nb * 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaMemcpyAsync(sums_host, ds, nb * 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
+    return STIF_OK;
+}

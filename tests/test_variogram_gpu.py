@@ -1,0 +1,132 @@
+"""GPU parity: libstif_b200 variogram kernels vs the CPU oracle (bit-exact counts,
+sums within 1e-12 relative) -- through the C ABI (stif_variogram_host)."""
+import numpy as np
+import pytest
+
+from oracle import variogram as ov
+from stif_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+RTOL_SUMS = 1e-12  # north-star tolerance for the binned semivariance sums
+
+
+def synth(n, seed=20261019, int_time=True):
+    rng = np.random.default_rng(seed)
+    space = rng.uniform(0, 100, (n, 2))
+    t = rng.integers(0, 365, n) if int_time else rng.uniform(0, 365, n)
+    v = rng.normal(size=n)
+    return space, t, v
+
+
+def check(ctx, space, t, v, smax, tmax, ns, nt, mode=0, flags=_native.VARIO_PEEL):
+    x, y = _native.split_space(space)
+    mean = float(np.mean(np.asarray(v, dtype=np.float64))) if mode == 1 else 0.0
+    counts, sums = ctx.variogram_host(x, y, t, v, smax, tmax, ns, nt, mode=mode, mean=mean, flags=flags)
+    h, c = ov.raw(space, t, v, smax, tmax, ns, nt, mode=mode)
+    assert np.array_equal(counts.astype(np.float64), c), "bin pair counts must be bit-exact"
+    scale = np.maximum(np.abs(h), 1e-300)
+    if mode == 0:
+        assert np.all(np.abs(sums - h) <= RTOL_SUMS * scale)
+    else:
+        # covariogram sums cancel; bound by the sum of |terms| ~ counts * var
+        bound = RTOL_SUMS * np.maximum(c * np.var(v), 1e-300)
+        assert np.all(np.abs(sums - h) <= bound)
+    return counts, sums
+
+
+@pytest.mark.parametrize("n", [2, 3, 255, 256, 257, 1023, 1024, 1025, 2500, 5000])
+def test_sizes(ctx, n):
+    space, t, v = synth(n, seed=n)
+    check(ctx, space, t, v, 30.0, 30, 30, 30)
+
+
+def test_empty_and_single(ctx):
+    for n in (0, 1):
+        counts, sums = ctx.variogram_host(np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n), 1.0, 1.0, 3, 4)
+        assert counts.shape == (3, 4) and counts.sum() == 0 and np.all(sums == 0)
+
+
+@pytest.mark.parametrize("int_time", [True, False])
+@pytest.mark.parametrize("flags", [_native.VARIO_PEEL, _native.VARIO_PEEL | _native.VARIO_NO_CULL])
+def test_synth_20k(ctx, int_time, flags):
+    space, t, v = synth(20000, int_time=int_time)
+    check(ctx, space, t, v, 30.0, 30, 30, 30, flags=flags)
+
+
+def test_covariogram(ctx):
+    space, t, v = synth(12000, seed=5)
+    check(ctx, space, t, v + 3.0, 25.0, 20.0, 12, 9, mode=1)
+
+
+def test_all_pairs_in_one_bin(ctx):
+    space, t, v = synth(4000, seed=9)
+    counts, _ = check(ctx, space, t, v, 1e3, 1e3, 1, 1)
+    assert counts.sum() == 4000 * 3999 // 2
+
+
+def test_duplicates_and_edges(ctx):
+    # integer lattice: many exact ties on bin edges and on the cut-offs (lag == max)
+    g = np.arange(40, dtype=np.float64)
+    xx, yy = np.meshgrid(g, g)
+    space = np.column_stack([xx.ravel(), yy.ravel()])
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 12, len(space))
+    v = rng.normal(size=len(space))
+    check(ctx, space, t, v, 10.0, 5, 10, 5)
+    check(ctx, space, t, v, 10.0, 5, 7, 3)
+
+
+def test_unsorted_negative_times(ctx):
+    rng = np.random.default_rng(11)
+    n = 6000
+    space = rng.uniform(-50, 50, (n, 2))
+    t = rng.uniform(-1e3, 1e3, n)
+    v = rng.normal(size=n) * 100
+    check(ctx, space, t, v, 40.0, 150.0, 16, 16)
+
+
+def test_bool_values_f_order(ctx):
+    rng = np.random.default_rng(12)
+    n = 5000
+    space = np.asfortranarray(rng.uniform(0, 10, (n, 2)))
+    t = rng.integers(0, 50, n)
+    v = rng.uniform(size=n) > 0.5
+    check(ctx, space, t, v, 3.0, 10, 10, 10)
+
+
+def test_partitions_sum_to_whole(ctx):
+    space, t, v = synth(9000, seed=21)
+    x, y = _native.split_space(space)
+    whole_c, whole_s = ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30)
+    acc_c = np.zeros_like(whole_c)
+    acc_s = np.zeros_like(whole_s)
+    for p in range(3):
+        c, s = ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30, part=p, nparts=3)
+        acc_c += c
+        acc_s += s
+    assert np.array_equal(acc_c, whole_c)
+    assert np.allclose(acc_s, whole_s, rtol=1e-13, atol=0)
+
+
+def test_stats_and_culling(ctx):
+    space, t, v = synth(30000)
+    x, y = _native.split_space(space)
+    c1, _ = ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30)
+    st_cull = ctx.variogram_stats()
+    c2, _ = ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30, flags=_native.VARIO_PEEL | _native.VARIO_NO_CULL)
+    st_all = ctx.variogram_stats()
+    assert np.array_equal(c1, c2)
+    assert st_cull["pairs"] == 30000 * 29999 // 2
+    assert st_cull["pairs_in_window"] == st_all["pairs_in_window"]
+    assert st_cull["pairs_evaluated"] < st_all["pairs_evaluated"]
+
+
+def test_bad_arguments(ctx):
+    z = np.zeros(4)
+    with pytest.raises(ValueError):
+        ctx.variogram_host(z, z, z, z, 1.0, 1.0, 0, 3)
+    with pytest.raises(ValueError):
+        ctx.variogram_host(z, z, z, z, 1.0, 1.0, 200, 200)
+    with pytest.raises(ValueError):
+        ctx.variogram_host(z, z, z, z, 1.0, 1.0, 3, 3, part=2, nparts=2)

@@ -1,11 +1,1165 @@
-// TEMPORARY stub -- replaced by the real implementation.
+// kriging.cu -- space-time ordinary kriging on sm_100a.
+//
+// Replaces (reference file:line):
+//   stif/data.py:170-212        Data.get_kriging_idxs  (dense n_obs x batch pre-filter)
+//   stif/predictor.py:602-660   nd_kriging             (candidate gamma-vector, top-k)
+//   stif/predictor.py:566-593   calc_kriging_weights   (bordered system + lstsq)
+//   stif/predictor.py:547-556   variogram_model        (+ stif/variogram_models.py:7-218)
+//   stif/predictor.py:882-906   mean / std epilogue
+//
+// Pipeline per call (one stream, no host synchronisation inside):
+//   grid   : observations binned into a uniform space-time grid whose cells are at least
+//            one search radius wide; (cell, obs-index) radix-sorted (CUB, plumbing), so each
+//            cell is a contiguous run in ascending observation index.  Cached per
+//            (obs set, radii).
+//   search : one warp per target (targets visited in grid-cell order for L2 locality).  The
+//            3x3x2 (causal) cell stencil is 6 contiguous runs; lanes stream the runs
+//            coalesced, apply the reference's exact filter
+//              rn(dx*dx)+rn(dy*dy) < smax^2  &  |dt| < tmax  &  t_obs <= t_tgt  &  not left out
+//            (stif/data.py:195-211; unfused like scipy cdist), compact survivors with a
+//            ballot, evaluate gamma(h,t) densely, and keep the k lowest (gamma, index) with a
+//            warp-wide bisection select; bounded shared memory for any candidate count.
+//   solve  : one warp per target assembles the (k+1)x(k+2) augmented ordinary-kriging system
+//            in shared memory, factorises with partially pivoted LU, back-substitutes, and
+//            runs the fused epilogue (float32 storage emulation + numpy pairwise order, or
+//            all-float64).
 #include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+
+namespace stif {
+namespace krig {
+
+constexpr int KMAX = 128;        // max_kriging_points limit
+constexpr int SEARCH_WARPS = 4;  // warps per block in the search kernel
+constexpr int PEND_CAP = 256;    // pending candidate positions per warp
+constexpr int BUF_CAP = 512;     // (gamma, idx) buffer per warp; >= KMAX + PEND_CAP
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Model {
+    int st;                 // STIF_ST_*
+    int ks, kt, km;         // marginal kinds
+    double rs, c0s, bs, is; // space marginal: range, sill, nugget, inverse (1/r or 1/(r/2)^2)
+    double rt, c0t, bt, it; // time marginal
+    double rm, c0m, bm, im; // metric marginal
+    double ani2;            // ani*ani
+    double k;               // product_sum weighting coefficient
+};
+
+struct Grid {
+    const double4 *obs;     // cell-sorted {x, y, t, bits(idx)}
+    const unsigned *cell_start;  // [ncells + 1]
+    double x0, y0, t0;
+    double inv_cx, inv_cy, inv_ct;
+    int nx, ny, nt;
+};
+
+// ---- variogram model (stif/variogram_models.py) -----------------------------------
+// Formulas are evaluated verbatim (no validity assumption: Nelder-Mead parameters are
+// unconstrained); h/a is evaluated as h*(1/a) like the reference's fast-math code.
+__device__ __forceinline__ double marginal(int kind, double h, double r, double c0, double b,
+                                           double inv)
+{
+    if (kind == STIF_M_SPHERICAL) {  // variogram_models.py:40-44
+        if (h <= r) {
+            const double u = h * inv;
+            return b + c0 * ((1.5 * u) - (0.5 * ((u * u) * u)));
+        }
+        return b + c0;
+    }
+    // gaussian, variogram_models.py:70-71: a = r/2; b + c0*(1 - exp(-(h^2/a^2)))
+    return b + c0 * (1.0 - exp(-((h * h) * inv)));
+}
+
+__device__ __forceinline__ double gamma_st(const Model &M, double h, double t)
+{
+    switch (M.st) {
+    case STIF_ST_SUM:  // :98-99
+        return marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) + marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it);
+    case STIF_ST_PRODUCT:  // :126-127
+        return marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) * marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it);
+    case STIF_ST_PRODUCT_SUM: {  // :155-157  k*prod + prod
+        const double p = marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) *
+                         marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it);
+        return M.k * p + p;
+    }
+    case STIF_ST_METRIC: {  // :184-186
+        const double d = sqrt(h * h + (M.ani2 * t) * t);
+        return marginal(M.km, d, M.rm, M.c0m, M.bm, M.im);
+    }
+    default: {  // sum_metric :213-218
+        const double d = sqrt(h * h + (M.ani2 * t) * t);
+        return (marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) +
+                marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it)) +
+               marginal(M.km, d, M.rm, M.c0m, M.bm, M.im);
+    }
+    }
+}
+
+__global__ void model_eval_kernel(Model M, const double *h, const double *t, int64_t n, double *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gamma_st(M, h[i], t[i]);
+}
+
+// ---- grid build --------------------------------------------------------------------
+__global__ void bbox_kernel(const double *x, const double *y, const double *t, int64_t n,
+                            double *bbox /* [6]: min x,y,t, max x,y,t; pre-initialised */)
+{
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double v[3] = {x[i], y[i], t[i]};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (v[d] < mn[d]) mn[d] = v[d];   // NaN never updates
+            if (v[d] > mx[d]) mx[d] = v[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int off = 16; off > 0; off >>= 1) {
+            mn[d] = fmin(mn[d], __shfl_xor_sync(FULL, mn[d], off));
+            mx[d] = fmax(mx[d], __shfl_xor_sync(FULL, mx[d], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // atomic min/max on doubles via ordered integer keys
+        auto enc = [](double v) -> unsigned long long {
+            unsigned long long b = (unsigned long long)__double_as_longlong(v);
+            return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+        };
+        unsigned long long *bb = reinterpret_cast<unsigned long long *>(bbox);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&bb[d], enc(mn[d]));
+            atomicMax(&bb[3 + d], enc(mx[d]));
+        }
+    }
+}
+
+__device__ __forceinline__ double dec_key(unsigned long long k)
+{
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+struct GridDims {
+    double x0, y0, t0, inv_cx, inv_cy, inv_ct;
+    int nx, ny, nt;
+};
+
+// Decide grid geometry on the device (no host round trip): cells are >= radius*(1+1e-9)
+// wide and the total number of cells is capped at max_cells by widening them.
+__global__ void grid_dims_kernel(const double *bbox_enc, double smax, double tmax, int64_t max_cells,
+                                 GridDims *out)
+{
+    const unsigned long long *bb = reinterpret_cast<const unsigned long long *>(bbox_enc);
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = dec_key(bb[d]);
+        hi[d] = dec_key(bb[3 + d]);
+        if (!(hi[d] >= lo[d])) {  // empty or all-NaN
+            lo[d] = 0.0;
+            hi[d] = 0.0;
+        }
+    }
+    double cell[3] = {smax, smax, tmax};
+    double n[3];
+    for (int d = 0; d < 3; ++d) {
+        if (!(cell[d] > 0.0) || isinf(cell[d])) cell[d] = (hi[d] - lo[d]) + 1.0;
+        cell[d] *= (1.0 + 1e-9);
+        n[d] = floor((hi[d] - lo[d]) / cell[d]) + 2.0;  // one spare cell at the upper edge
+        if (!(n[d] >= 2.0)) n[d] = 2.0;
+    }
+    // cap: widen all cells by a common factor until the product fits
+    for (int it = 0; it < 64 && n[0] * n[1] * n[2] > (double)max_cells; ++it) {
+        for (int d = 0; d < 3; ++d) {
+            if (n[d] > 2.0) {
+                cell[d] *= 1.26;
+                n[d] = floor((hi[d] - lo[d]) / cell[d]) + 2.0;
+            }
+        }
+    }
+    out->x0 = lo[0];
+    out->y0 = lo[1];
+    out->t0 = lo[2];
+    out->inv_cx = 1.0 / cell[0];
+    out->inv_cy = 1.0 / cell[1];
+    out->inv_ct = 1.0 / cell[2];
+    out->nx = (int)n[0];
+    out->ny = (int)n[1];
+    out->nt = (int)n[2];
+}
+
+__device__ __forceinline__ int raw_cell(double v, double v0, double inv, int n)
+{
+    double c = floor((v - v0) * inv);
+    if (!(c >= -2.0)) c = -2.0;  // also catches NaN
+    if (c > (double)n + 1.0) c = (double)n + 1.0;
+    return (int)c;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void obs_keys_kernel(const double *x, const double *y, const double *t, int64_t n,
+                                const GridDims *gd, unsigned *keys, unsigned *idx)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridDims g = *gd;
+    const int cx = clampi(raw_cell(x[i], g.x0, g.inv_cx, g.nx), 0, g.nx - 1);
+    const int cy = clampi(raw_cell(y[i], g.y0, g.inv_cy, g.ny), 0, g.ny - 1);
+    const int ct = clampi(raw_cell(t[i], g.t0, g.inv_ct, g.nt), 0, g.nt - 1);
+    keys[i] = (unsigned)((ct * g.ny + cy) * g.nx + cx);
+    idx[i] = (unsigned)i;
+}
+
+__global__ void obs_gather_kernel(const double *x, const double *y, const double *t,
+                                  const unsigned *idx_sorted, int64_t n, double4 *out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned i = idx_sorted[k];
+    out[k] = make_double4(x[i], y[i], t[i], __longlong_as_double((long long)i));
+}
+
+// cell_start[c] = first sorted position with key >= c  (c in [0, ncells]); one thread per cell.
+__global__ void cell_start_kernel(const unsigned *keys_sorted, int64_t n, const GridDims *gd,
+                                  int64_t max_cells, unsigned *cell_start)
+{
+    const GridDims g = *gd;
+    const int64_t ncells = (int64_t)g.nx * g.ny * g.nt;
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncells || c > max_cells) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)keys_sorted[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    cell_start[c] = (unsigned)lo;
+}
+
+__global__ void target_keys_kernel(const double *tx, const double *ty, const double *tt, int64_t n,
+                                   const GridDims *gd, unsigned *keys, unsigned *idx)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridDims g = *gd;
+    const int cx = clampi(raw_cell(tx[i], g.x0, g.inv_cx, g.nx), 0, g.nx - 1);
+    const int cy = clampi(raw_cell(ty[i], g.y0, g.inv_cy, g.ny), 0, g.ny - 1);
+    const int ct = clampi(raw_cell(tt[i], g.t0, g.inv_ct, g.nt), 0, g.nt - 1);
+    keys[i] = (unsigned)((ct * g.ny + cy) * g.nx + cx);
+    idx[i] = (unsigned)i;
+}
+
+// ---- neighbour search + top-k ------------------------------------------------------
+__device__ __forceinline__ unsigned long long gamma_key(double g)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(g);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+struct WarpBuf {
+    unsigned long long *key;  // [BUF_CAP]
+    unsigned *idx;            // [BUF_CAP]
+    unsigned *pend;           // [PEND_CAP]
+};
+
+__device__ __forceinline__ int warp_count_le(const unsigned long long *key, int m, int lane,
+                                             unsigned long long thr)
+{
+    int c = 0;
+    for (int e = lane; e < m; e += 32) c += (key[e] <= thr) ? 1 : 0;
+    return __reduce_add_sync(FULL, c);
+}
+
+// Keep the k smallest (key, idx) of buf[0..m) (unsorted, compacted to the front).
+__device__ void select_k(const WarpBuf &B, int &m, int k, int lane)
+{
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int e = lane; e < m; e += 32) {
+        const unsigned long long v = B.key[e];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(FULL, lo, off);
+        const unsigned long long b = __shfl_xor_sync(FULL, hi, off);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    // bisection for the k-th smallest key; early exit when a threshold splits exactly k
+    unsigned long long thr = hi;
+    bool exact = false;
+    while (lo < hi) {
+        const unsigned long long mid = lo + ((hi - lo) >> 1);
+        const int c = warp_count_le(B.key, m, lane, mid);
+        if (c == k) {
+            thr = mid;
+            exact = true;
+            break;
+        }
+        if (c > k) hi = mid; else lo = mid + 1;
+    }
+    unsigned ithr = 0xffffffffu;
+    if (!exact) {
+        thr = lo;  // k-th smallest key value; ties at thr are broken by lowest index
+        int c_less = 0, c_tie = 0;
+        for (int e = lane; e < m; e += 32) {
+            const unsigned long long v = B.key[e];
+            c_less += (v < thr) ? 1 : 0;
+            c_tie += (v == thr) ? 1 : 0;
+        }
+        c_less = __reduce_add_sync(FULL, c_less);
+        c_tie = __reduce_add_sync(FULL, c_tie);
+        const int need = k - c_less;  // 1 <= need <= c_tie
+        if (need < c_tie) {
+            unsigned ilo = 0u, ihi = 0xffffffffu;  // smallest i with count(tie & idx <= i) >= need
+            while (ilo < ihi) {
+                const unsigned mid = ilo + ((ihi - ilo) >> 1);
+                int c = 0;
+                for (int e = lane; e < m; e += 32) c += (B.key[e] == thr && B.idx[e] <= mid) ? 1 : 0;
+                c = __reduce_add_sync(FULL, c);
+                if (c >= need) ihi = mid; else ilo = mid + 1;
+            }
+            ithr = ilo;
+        }
+    }
+    // in-place compaction (writes never pass the chunk being read)
+    int out = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int e = base + lane;
+        unsigned long long v = 0;
+        unsigned id = 0;
+        bool sel = false;
+        if (e < m) {
+            v = B.key[e];
+            id = B.idx[e];
+            sel = exact ? (v <= thr) : (v < thr || (v == thr && id <= ithr));
+        }
+        const unsigned bal = __ballot_sync(FULL, sel);
+        __syncwarp();
+        if (sel) {
+            const int pos = out + __popc(bal & ((1u << lane) - 1u));
+            B.key[pos] = v;
+            B.idx[pos] = id;
+        }
+        out += __popc(bal);
+        __syncwarp();
+    }
+    m = out;  // == k
+}
+
+// Bitonic sort of buf[0..m) by (use_key ? key : 0, idx) ascending; m <= KMAX.
+// Padding entries carry idx 0xffffffff (never a real observation index) and sort last.
+__device__ void sort_buf(const WarpBuf &B, int m, bool use_key, int lane)
+{
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    for (int e = m + lane; e < p2; e += 32) {
+        B.key[e] = ~0ull;
+        B.idx[e] = 0xffffffffu;
+    }
+    __syncwarp();
+    for (int size = 2; size <= p2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int tsk = lane; tsk < (p2 >> 1); tsk += 32) {
+                const int i = ((tsk / stride) * (stride << 1)) + (tsk % stride);
+                const int j = i + stride;
+                const bool up = ((i & size) == 0);
+                const unsigned long long ki = B.key[i], kj = B.key[j];
+                const unsigned ii = B.idx[i], ij = B.idx[j];
+                const unsigned long long pi = use_key ? ki : (ii == 0xffffffffu ? ~0ull : 0ull);
+                const unsigned long long pj = use_key ? kj : (ij == 0xffffffffu ? ~0ull : 0ull);
+                const bool gt = (pi > pj) || (pi == pj && ii > ij);
+                if (gt == up) {
+                    B.key[i] = kj;
+                    B.key[j] = ki;
+                    B.idx[i] = ij;
+                    B.idx[j] = ii;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+
+struct SearchParams {
+    const double4 *obs;
+    const unsigned *cell_start;
+    const GridDims *gd;
+    const double *tx, *ty, *tt;     // full target arrays
+    const long long *leave_out;     // nullable
+    const unsigned *order;          // chunk-local visit order
+    int64_t c0;                     // first target of the chunk
+    int n;                          // targets in the chunk
+    double smax2, tmax;
+    int k, min_pts;
+    Model M;
+    int *sel_n;            // [n]   -1: below min_pts (or no candidate), else neighbours kept
+    unsigned *sel_idx;     // [n][k]
+    double *sel_gamma;     // [n][k]
+    unsigned *cand_n;      // [n] candidates inside the window
+    unsigned *exam_n;      // [n] candidates examined
+};
+
+__device__ __forceinline__ void flush_pending(const WarpBuf &B, const SearchParams &P, int &pend_n,
+                                              int &m, bool &truncated, double x, double y, double t,
+                                              int lane)
+{
+    __syncwarp();
+    if (m + pend_n > BUF_CAP) {
+        select_k(B, m, P.k, lane);
+        truncated = true;
+    }
+    for (int e = lane; e < pend_n; e += 32) {
+        const double4 o = P.obs[B.pend[e]];
+        const double dx = o.x - x, dy = o.y - y;
+        const double h = sqrt(dx * dx + dy * dy);     // predictor.py:627-634
+        const double lag_t = fabs(o.z - t);           // predictor.py:635
+        B.key[m + e] = gamma_key(gamma_st(P.M, h, lag_t));
+        B.idx[m + e] = (unsigned)__double_as_longlong(o.w);
+    }
+    m += pend_n;
+    pend_n = 0;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams P)
+{
+    __shared__ unsigned long long s_key[SEARCH_WARPS][BUF_CAP];
+    __shared__ unsigned s_idx[SEARCH_WARPS][BUF_CAP];
+    __shared__ unsigned s_pend[SEARCH_WARPS][PEND_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * SEARCH_WARPS + warp;
+    if (slot >= P.n) return;
+    WarpBuf B{s_key[warp], s_idx[warp], s_pend[warp]};
+    const unsigned tl = P.order[slot];
+    const int64_t tg = P.c0 + tl;
+    const double x = P.tx[tg], y = P.ty[tg], t = P.tt[tg];
+    const long long leave = P.leave_out ? P.leave_out[tg] : -1;
+    const GridDims g = *P.gd;
+
+    const int cxr = raw_cell(x, g.x0, g.inv_cx, g.nx);
+    const int cyr = raw_cell(y, g.y0, g.inv_cy, g.ny);
+    const int ctr = raw_cell(t, g.t0, g.inv_ct, g.nt);
+    const int cx_lo = max(cxr - 1, 0), cx_hi = min(cxr + 1, g.nx - 1);
+    const int cy_lo = max(cyr - 1, 0), cy_hi = min(cyr + 1, g.ny - 1);
+    const int ct_lo = max(ctr - 1, 0), ct_hi = min(ctr, g.nt - 1);  // causal: t_obs <= t_tgt
+
+    int pend_n = 0, m = 0;
+    bool truncated = false;
+    unsigned examined = 0, in_window = 0;
+    if (cx_lo <= cx_hi) {
+        for (int ct = ct_lo; ct <= ct_hi; ++ct) {
+            for (int cy = cy_lo; cy <= cy_hi; ++cy) {
+                const int row = (ct * g.ny + cy) * g.nx;
+                const unsigned beg = P.cell_start[row + cx_lo];
+                const unsigned end = P.cell_start[row + cx_hi + 1];
+                examined += end - beg;
+                for (unsigned p0 = beg; p0 < end; p0 += 32) {
+                    const unsigned p = p0 + lane;
+                    bool pass = false;
+                    if (p < end) {
+                        const double4 o = P.obs[p];
+                        const double dx = o.x - x, dy = o.y - y;
+                        const double d2 = dx * dx + dy * dy;      // cdist sqeuclidean, data.py:195-199
+                        const double dt = o.z - t;
+                        pass = (d2 < P.smax2) && (fabs(dt) < P.tmax) && (o.z <= t) &&   // data.py:206-211
+                               ((long long)(unsigned)__double_as_longlong(o.w) != leave);
+                    }
+                    const unsigned bal = __ballot_sync(FULL, pass);
+                    if (bal) {
+                        if (pass) B.pend[pend_n + __popc(bal & ((1u << lane) - 1u))] = p;
+                        pend_n += __popc(bal);
+                        if (pend_n > PEND_CAP - 32) {
+                            in_window += pend_n;
+                            flush_pending(B, P, pend_n, m, truncated, x, y, t, lane);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    in_window += pend_n;
+    flush_pending(B, P, pend_n, m, truncated, x, y, t, lane);
+    if (m > P.k) {
+        select_k(B, m, P.k, lane);
+        truncated = true;
+    }
+    if (lane == 0) {
+        P.cand_n[tl] = in_window;
+        P.exam_n[tl] = examined;
+    }
+    if ((int)in_window < P.min_pts || in_window == 0) {  // predictor.py:624-626
+        if (lane == 0) P.sel_n[tl] = ((int)in_window < P.min_pts) ? -1 : 0;
+        return;
+    }
+    // reference order: ascending gamma when truncated (predictor.py:637-642), else the
+    // pre-filter's ascending observation index (data.py:212)
+    sort_buf(B, m, truncated, lane);
+    for (int e = lane; e < m; e += 32) {
+        P.sel_idx[(size_t)tl * P.k + e] = B.idx[e];
+        unsigned long long kb = B.key[e];
+        kb = (kb & 0x8000000000000000ull) ? (kb & 0x7fffffffffffffffull) : ~kb;
+        P.sel_gamma[(size_t)tl * P.k + e] = __longlong_as_double((long long)kb);
+    }
+    if (lane == 0) P.sel_n[tl] = m;
+}
+
+// ---- assemble + solve + epilogue ---------------------------------------------------
+struct SolveParams {
+    const double *ox, *oy, *ot, *oresid;   // observations, original order
+    const unsigned *order;
+    int64_t c0;
+    int n;
+    int k, ld;
+    int flags;
+    Model M;
+    const int *sel_n;
+    const unsigned *sel_idx;
+    const double *sel_gamma;
+    double *mean, *std;          // [n_targets] (global target index)
+    float *w_out, *g_out;        // nullable, [n_targets][k]
+    unsigned *idx_out;           // nullable
+    int *nused_out;              // nullable
+    unsigned *singular;          // [n] chunk-local flag
+};
+
+// numpy's pairwise sum of a row of length n <= 128 (numpy/_core/src/umath/loops_utils.h.src),
+// preceded by the reduction's initial 0: bit-compatible with np.sum(row) -- checked against
+// numpy 2.3 in tests/test_oracle_cpu.py.
+template <typename T>
+__device__ T numpy_row_sum(const T *a, int n)
+{
+    T res;
+    if (n < 8) {
+        res = (T)0;
+        for (int i = 0; i < n; ++i) res = res + a[i];
+    } else {
+        T r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = r[j] + a[i + j];
+        }
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res = res + a[i];
+    }
+    return (T)0 + res;
+}
+
+__global__ void solve_kernel(SolveParams P, int warps_per_block, int warp_doubles)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * warps_per_block + warp;
+    if (slot >= P.n) return;
+    const unsigned tl = P.order[slot];
+    const int64_t tg = P.c0 + tl;
+    const int k = P.k, ld = P.ld;
+    double *A = smem_d + (size_t)warp * warp_doubles;  // (k+1) x ld, row-major; column n = rhs
+    double *xs = A + (size_t)(k + 1) * ld;             // [k+1]
+    double *ys = xs + (k + 1);
+    double *ts = ys + (k + 1);
+    double *sol = ts + (k + 1);                        // [k+1]
+    double *g0 = sol + (k + 1);                        // [k+1]
+    unsigned *ids = reinterpret_cast<unsigned *>(g0 + (k + 1));  // [k+1]
+
+    const int m = P.sel_n[tl];
+    if (m <= 0) {
+        if (lane == 0) {
+            P.mean[tg] = 0.0;
+            P.std[tg] = 0.0;
+            if (P.nused_out) P.nused_out[tg] = m < 0 ? -1 : 0;
+        }
+        for (int e = lane; e < k; e += 32) {
+            if (P.w_out) P.w_out[(size_t)tg * k + e] = 0.f;
+            if (P.g_out) P.g_out[(size_t)tg * k + e] = 0.f;
+            if (P.idx_out) P.idx_out[(size_t)tg * k + e] = 0u;
+        }
+        return;
+    }
+    const int n = m + 1;
+    for (int e = lane; e < m; e += 32) {
+        const unsigned id = P.sel_idx[(size_t)tl * k + e];
+        ids[e] = id;
+        xs[e] = P.ox[id];
+        ys[e] = P.oy[id];
+        ts[e] = P.ot[id];
+        const double g = P.sel_gamma[(size_t)tl * k + e];
+        g0[e] = g;
+        A[e * ld + n] = g;        // rhs = [gamma_vector; 1]   predictor.py:582-585
+        A[e * ld + m] = 1.0;      // Lagrange column            predictor.py:578
+        A[m * ld + e] = 1.0;      // Lagrange row
+    }
+    if (lane == 0) {
+        A[m * ld + m] = 0.0;      // predictor.py:580
+        A[m * ld + n] = 1.0;
+    }
+    __syncwarp();
+    // gamma matrix, predictor.py:573-575 (diagonal = gamma(0,0), no special case)
+    const double gdiag = gamma_st(P.M, 0.0, 0.0);
+    for (int e = lane; e < m; e += 32) A[e * ld + e] = gdiag;
+    {
+        const int npairs = m * (m - 1) / 2;
+        int a = 0, off = lane;  // pair (a, a+1+off)
+        for (int e = lane; e < npairs; e += 32) {
+            while (off >= m - 1 - a) {
+                off -= (m - 1 - a);
+                ++a;
+            }
+            const int b = a + 1 + off;
+            const double dx = xs[a] - xs[b], dy = ys[a] - ys[b];
+            const double h = sqrt(dx * dx + dy * dy);          // utils.py:40-44
+            const double lt = fabs(ts[a] - ts[b]);             // utils.py:19-22
+            const double g = gamma_st(P.M, h, lt);
+            A[a * ld + b] = g;
+            A[b * ld + a] = g;
+            off += 32;
+        }
+    }
+    __syncwarp();
+
+    // LU with partial pivoting on the augmented matrix (n x (n+1))
+    bool singular = false;
+    for (int j = 0; j < n; ++j) {
+        double best = -1.0;
+        int bi = j;
+        for (int r = j + lane; r < n; r += 32) {
+            const double v = fabs(A[r * ld + j]);
+            if (v > best) {
+                best = v;
+                bi = r;
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(FULL, best, off);
+            const int oi = __shfl_xor_sync(FULL, bi, off);
+            if (ob > best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        if (!(best > 0.0)) {  // exactly singular column (or NaN): leave it, x_j := 0 later
+            singular = true;
+            continue;
+        }
+        if (bi != j) {
+            for (int c = j + lane; c <= n; c += 32) {
+                const double tmp = A[j * ld + c];
+                A[j * ld + c] = A[bi * ld + c];
+                A[bi * ld + c] = tmp;
+            }
+            __syncwarp();
+        }
+        const double pinv = 1.0 / A[j * ld + j];
+        // trailing update, lanes over columns j+1..n (rhs included)
+        for (int r = j + 1; r < n; ++r) {
+            const double l = A[r * ld + j] * pinv;
+            for (int c = j + 1 + lane; c <= n; c += 32) A[r * ld + c] = A[r * ld + c] - l * A[j * ld + c];
+        }
+        __syncwarp();
+    }
+    // back substitution
+    for (int j = n - 1; j >= 0; --j) {
+        double acc = 0.0;
+        for (int c = j + 1 + lane; c < n; c += 32) acc += A[j * ld + c] * sol[c];
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+        if (lane == 0) {
+            const double piv = A[j * ld + j];
+            sol[j] = (piv != 0.0) ? (A[j * ld + n] - acc) / piv : 0.0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && singular) P.singular[tl] = 1u;
+
+    // ---- epilogue: predictor.py:646-658 (storage) and :900-905 (mean, std) ----
+    if (P.flags & STIF_KRIG_F32_STORAGE) {
+        double *term64 = xs;                              // k doubles
+        float *w32 = reinterpret_cast<float *>(ys);       // k floats
+        float *term32 = reinterpret_cast<float *>(ts);    // k floats
+        const double resid0 = P.oresid[0];
+        __syncwarp();
+        for (int e = lane; e < k; e += 32) {
+            float w = 0.f, g = 0.f;
+            unsigned id = 0u;
+            double r = resid0;                            // padded slots index observation 0
+            if (e < m) {
+                w = (float)sol[e];
+                g = (float)g0[e];
+                id = ids[e];
+                r = P.oresid[id];
+            }
+            w32[e] = w;
+            term64[e] = (double)w * r;                    // f32 * f64 -> f64
+            term32[e] = w * g;                            // f32 * f32 -> f32
+            if (P.w_out) P.w_out[(size_t)tg * k + e] = w;
+            if (P.g_out) P.g_out[(size_t)tg * k + e] = g;
+            if (P.idx_out) P.idx_out[(size_t)tg * k + e] = id;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            P.mean[tg] = numpy_row_sum<double>(term64, k);
+            P.std[tg] = (double)sqrtf(numpy_row_sum<float>(term32, k));
+            if (P.nused_out) P.nused_out[tg] = m;
+        }
+    } else {
+        double am = 0.0, av = 0.0;
+        for (int e = lane; e < m; e += 32) {
+            am += sol[e] * P.oresid[ids[e]];
+            av += sol[e] * g0[e];
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            am += __shfl_xor_sync(FULL, am, off);
+            av += __shfl_xor_sync(FULL, av, off);
+        }
+        for (int e = lane; e < k; e += 32) {
+            const bool in = e < m;
+            if (P.w_out) P.w_out[(size_t)tg * k + e] = in ? (float)sol[e] : 0.f;
+            if (P.g_out) P.g_out[(size_t)tg * k + e] = in ? (float)g0[e] : 0.f;
+            if (P.idx_out) P.idx_out[(size_t)tg * k + e] = in ? ids[e] : 0u;
+        }
+        if (lane == 0) {
+            P.mean[tg] = am;
+            P.std[tg] = sqrt(av);
+            if (P.nused_out) P.nused_out[tg] = m;
+        }
+    }
+}
+
+// stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += sum(singular)
+__global__ void stats_kernel(const unsigned *exam_n, const unsigned *cand_n, const int *sel_n,
+                             const unsigned *singular, int n, unsigned long long *stats)
+{
+    unsigned long long a = 0, b = 0, c = 0, d = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        a += exam_n[i];
+        b += cand_n[i];
+        c += sel_n[i] < 0 ? 1 : 0;
+        d += singular[i];
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(FULL, a, off);
+        b += __shfl_xor_sync(FULL, b, off);
+        c += __shfl_xor_sync(FULL, c, off);
+        d += __shfl_xor_sync(FULL, d, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&stats[0], a);
+        if (b) atomicAdd(&stats[1], b);
+        if (c) atomicAdd(&stats[2], c);
+        if (d) atomicAdd(&stats[3], d);
+    }
+}
+
+static int build_model(const KrigModel &km, Model &M)
+{
+    memset(&M, 0, sizeof(M));
+    M.st = km.st_model;
+    M.ks = km.space_model;
+    M.kt = km.time_model;
+    M.km = km.metric_model;
+    const double *x = km.x;
+    auto inv_of = [](int kind, double r) {
+        if (kind == STIF_M_SPHERICAL) return 1.0 / (r / 1.0);   // a = r/1.   variogram_models.py:40
+        const double a = r / 2.0;                                // a = r/2.   variogram_models.py:70
+        return 1.0 / (a * a);
+    };
+    switch (km.st_model) {
+    case STIF_ST_SUM:
+    case STIF_ST_PRODUCT:
+    case STIF_ST_PRODUCT_SUM:  // x = [r_s, r_t, c0_s, c0_t, b_s, b_t (, k)]
+        M.rs = x[0]; M.rt = x[1]; M.c0s = x[2]; M.c0t = x[3]; M.bs = x[4]; M.bt = x[5];
+        M.k = (km.st_model == STIF_ST_PRODUCT_SUM) ? x[6] : 0.0;
+        break;
+    case STIF_ST_METRIC:       // x = [r, c0, b, ani]
+        M.rm = x[0]; M.c0m = x[1]; M.bm = x[2]; M.ani2 = x[3] * x[3];
+        break;
+    case STIF_ST_SUM_METRIC:   // x = [r_s, r_t, r_m, c0_s, c0_t, c0_m, b_s, b_t, b_m, ani]
+        M.rs = x[0]; M.rt = x[1]; M.rm = x[2]; M.c0s = x[3]; M.c0t = x[4]; M.c0m = x[5];
+        M.bs = x[6]; M.bt = x[7]; M.bm = x[8]; M.ani2 = x[9] * x[9];
+        break;
+    default:
+        set_error("unknown space-time model id %d", km.st_model);
+        return STIF_EINVAL;
+    }
+    M.is = inv_of(M.ks, M.rs);
+    M.it = inv_of(M.kt, M.rt);
+    M.im = inv_of(M.km, M.rm);
+    return STIF_OK;
+}
+
+}  // namespace krig
+}  // namespace stif
+
 using namespace stif;
-extern "C" {
-int stif_kriging_set_obs(stif_ctx *, const double *, const double *, const double *, const double *, int64_t, int) { set_error("kriging not built yet"); return STIF_ESTATE; }
-int stif_kriging_set_model(stif_ctx *, int, int, int, int, const double *, int) { set_error("kriging not built yet"); return STIF_ESTATE; }
-int stif_variogram_model_eval(stif_ctx *, const double *, const double *, int64_t, double *) { set_error("kriging not built yet"); return STIF_ESTATE; }
-int stif_kriging_predict_host(stif_ctx *, const double *, const double *, const double *, const int64_t *, int64_t, int, int, double, double, int, double *, double *, float *, float *, uint32_t *, int32_t *) { set_error("kriging not built yet"); return STIF_ESTATE; }
-int stif_kriging_predict_dev(stif_ctx *, const double *, const double *, const double *, const int64_t *, int64_t, int, int, double, double, int, double *, double *, float *, float *, uint32_t *, int32_t *, void *) { set_error("kriging not built yet"); return STIF_ESTATE; }
-int stif_kriging_stats(stif_ctx *, uint64_t *) { set_error("kriging not built yet"); return STIF_ESTATE; }
+using namespace stif::krig;
+
+namespace {
+
+enum Scratch {
+    S_GRIDHDR = 0, S_OKEYS, S_OIDX, S_OKEYS_S, S_OIDX_S, S_CUB, S_OBS_SORTED, S_CELL_START,
+    S_TKEYS, S_TFLAGS, S_SEL_IDX, S_SEL_GAMMA, S_STAGE, S_EVAL
+};
+
+int check_ctx(stif_ctx *c, const char *who)
+{
+    if (!c) {
+        set_error("%s: ctx is NULL", who);
+        return STIF_EINVAL;
+    }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaSetDevice(%d): %s", who, c->device, cudaGetErrorString(e));
+        return STIF_ECUDA;
+    }
+    return STIF_OK;
+}
+
+int64_t max_cells_for(int64_t n_obs)
+{
+    int64_t mc = 2 * n_obs;
+    if (mc < 4096) mc = 4096;
+    if (mc > (1 << 24)) mc = (1 << 24);
+    return mc;
+}
+
+// Build (or reuse) the space-time grid for the current observation set and radii.
+int ensure_grid(stif_ctx *c, double smax, double tmax, cudaStream_t st)
+{
+    const int64_t n = c->n_obs;
+    if (c->grid_nobs == n && c->grid_smax == smax && c->grid_tmax == tmax) return STIF_OK;
+    const int64_t max_cells = max_cells_for(n);
+    const double *ox = c->k_obs.as<double>();
+    const double *oy = ox + n, *ot = oy + n;
+    STIF_TRY(c->k_scratch[S_GRIDHDR].reserve(6 * 8 + sizeof(GridDims)));
+    STIF_TRY(c->k_scratch[S_OKEYS].reserve(4 * (size_t)n));
+    STIF_TRY(c->k_scratch[S_OIDX].reserve(4 * (size_t)n));
+    STIF_TRY(c->k_scratch[S_OKEYS_S].reserve(4 * (size_t)n));
+    STIF_TRY(c->k_scratch[S_OIDX_S].reserve(4 * (size_t)n));
+    STIF_TRY(c->k_scratch[S_OBS_SORTED].reserve(sizeof(double4) * (size_t)n));
+    STIF_TRY(c->k_scratch[S_CELL_START].reserve(4 * (size_t)(max_cells + 2)));
+    double *bbox = c->k_scratch[S_GRIDHDR].as<double>();
+    GridDims *gd = reinterpret_cast<GridDims *>(bbox + 6);
+    // min keys start at all-ones, max keys at zero
+    STIF_CUDA(cudaMemsetAsync(bbox, 0xff, 3 * 8, st));
+    STIF_CUDA(cudaMemsetAsync(bbox + 3, 0x00, 3 * 8, st));
+    const int tb = 256;
+    int nb = (int)((n + tb - 1) / tb);
+    if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+    if (nb < 1) nb = 1;
+    bbox_kernel<<<nb, tb, 0, st>>>(ox, oy, ot, n, bbox);
+    grid_dims_kernel<<<1, 1, 0, st>>>(bbox, smax, tmax, max_cells, gd);
+    const unsigned nbn = (unsigned)((n + tb - 1) / tb);
+    unsigned *keys = c->k_scratch[S_OKEYS].as<unsigned>(), *idx = c->k_scratch[S_OIDX].as<unsigned>();
+    unsigned *keys_s = c->k_scratch[S_OKEYS_S].as<unsigned>(), *idx_s = c->k_scratch[S_OIDX_S].as<unsigned>();
+    obs_keys_kernel<<<nbn, tb, 0, st>>>(ox, oy, ot, n, gd, keys, idx);
+    size_t tmp = 0;
+    STIF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys_s, idx, idx_s, (int)n, 0, 25, st));
+    STIF_TRY(c->k_scratch[S_CUB].reserve(tmp));
+    STIF_CUDA(cub::DeviceRadixSort::SortPairs(c->k_scratch[S_CUB].p, tmp, keys, keys_s, idx, idx_s,
+                                              (int)n, 0, 25, st));
+    obs_gather_kernel<<<nbn, tb, 0, st>>>(ox, oy, ot, idx_s, n, c->k_scratch[S_OBS_SORTED].as<double4>());
+    cell_start_kernel<<<(unsigned)((max_cells + 1 + tb - 1) / tb), tb, 0, st>>>(
+        keys_s, n, gd, max_cells, c->k_scratch[S_CELL_START].as<unsigned>());
+    STIF_CUDA(cudaGetLastError());
+    c->grid_nobs = n;
+    c->grid_smax = smax;
+    c->grid_tmax = tmax;
+    return STIF_OK;
+}
+
+}  // namespace
+
+extern "C" int stif_kriging_set_obs(stif_ctx *c, const double *x, const double *y, const double *t,
+                                    const double *resid, int64_t n, int on_device)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_set_obs"));
+    if (n < 0 || n >= 0x7fffffff || (n > 0 && (!x || !y || !t || !resid))) {
+        set_error("stif_kriging_set_obs: bad arguments (n=%lld)", (long long)n);
+        return STIF_EINVAL;
+    }
+    STIF_TRY(c->k_obs.reserve(sizeof(double) * 4 * (size_t)(n > 0 ? n : 1)));
+    double *d = c->k_obs.as<double>();
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    if (n > 0) {
+        STIF_CUDA(cudaMemcpyAsync(d, x, bytes, kind, c->stream));
+        STIF_CUDA(cudaMemcpyAsync(d + n, y, bytes, kind, c->stream));
+        STIF_CUDA(cudaMemcpyAsync(d + 2 * n, t, bytes, kind, c->stream));
+        STIF_CUDA(cudaMemcpyAsync(d + 3 * n, resid, bytes, kind, c->stream));
+    }
+    STIF_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_obs = n;
+    c->grid_nobs = -1;  // invalidate the grid
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_set_model(stif_ctx *c, int st_model, int space_model, int time_model,
+                                      int metric_model, const double *params, int nparams)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_set_model"));
+    static const int need[5] = {6, 6, 7, 4, 10};
+    if (st_model < 0 || st_model > 4) {
+        set_error("stif_kriging_set_model: unknown space-time model id %d", st_model);
+        return STIF_EINVAL;
+    }
+    const int models[3] = {space_model, time_model, metric_model};
+    for (int m : models) {
+        if (m != STIF_M_SPHERICAL && m != STIF_M_GAUSSIAN) {
+            set_error("stif_kriging_set_model: unknown marginal model id %d", m);
+            return STIF_EINVAL;
+        }
+    }
+    if (!params || nparams != need[st_model]) {
+        set_error("stif_kriging_set_model: model %d needs %d parameters, got %d", st_model,
+                  need[st_model], nparams);
+        return STIF_EINVAL;
+    }
+    c->model.st_model = st_model;
+    c->model.space_model = space_model;
+    c->model.time_model = time_model;
+    c->model.metric_model = metric_model;
+    c->model.nparams = nparams;
+    for (int i = 0; i < nparams; ++i) c->model.x[i] = params[i];
+    return STIF_OK;
+}
+
+extern "C" int stif_variogram_model_eval(stif_ctx *c, const double *h, const double *t, int64_t n,
+                                         double *out)
+{
+    STIF_TRY(check_ctx(c, "stif_variogram_model_eval"));
+    if (c->model.st_model < 0) {
+        set_error("stif_variogram_model_eval: no variogram model set (fit a variogram model first)");
+        return STIF_ESTATE;
+    }
+    if (n < 0 || (n > 0 && (!h || !t || !out))) {
+        set_error("stif_variogram_model_eval: bad arguments");
+        return STIF_EINVAL;
+    }
+    if (n == 0) return STIF_OK;
+    Model M;
+    STIF_TRY(build_model(c->model, M));
+    STIF_TRY(c->k_scratch[S_EVAL].reserve(3 * sizeof(double) * (size_t)n));
+    double *dh = c->k_scratch[S_EVAL].as<double>(), *dt = dh + n, *dout = dt + n;
+    STIF_CUDA(cudaMemcpyAsync(dh, h, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    STIF_CUDA(cudaMemcpyAsync(dt, t, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    model_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(M, dh, dt, n, dout);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaMemcpyAsync(out, dout, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    STIF_CUDA(cudaStreamSynchronize(c->stream));
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const double *ty,
+                                        const double *tt, const int64_t *leave_out, int64_t n_targets,
+                                        int min_pts, int max_pts, double smax, double tmax, int flags,
+                                        double *mean_out, double *std_out, float *w_out,
+                                        float *gamma_out, uint32_t *idx_out, int32_t *n_used_out,
+                                        void *stream_v)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_predict"));
+    if (c->model.st_model < 0) {
+        set_error("No Kriging function defined. Did you fit a variogram model?");  // predictor.py:852-854
+        return STIF_ESTATE;
+    }
+    if (c->n_obs <= 0) {
+        set_error("stif_kriging_predict: no observations set (stif_kriging_set_obs)");
+        return STIF_ESTATE;
+    }
+    if (max_pts < 1 || max_pts > KMAX) {
+        set_error("stif_kriging_predict: max_kriging_points must be in [1, %d], got %d", KMAX, max_pts);
+        return STIF_EINVAL;
+    }
+    if (n_targets < 0 || (n_targets > 0 && (!tx || !ty || !tt || !mean_out || !std_out))) {
+        set_error("stif_kriging_predict: bad arguments");
+        return STIF_EINVAL;
+    }
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    c->last_stream = st;
+    STIF_TRY(c->k_stats.reserve(4 * sizeof(unsigned long long)));
+    STIF_CUDA(cudaMemsetAsync(c->k_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    STIF_CUDA(cudaEventRecord(c->ev[0], st));
+    c->n_phase = 3;
+    if (n_targets == 0) {
+        for (int i = 1; i <= 3; ++i) STIF_CUDA(cudaEventRecord(c->ev[i], st));
+        return STIF_OK;
+    }
+    Model M;
+    STIF_TRY(build_model(c->model, M));
+    STIF_TRY(ensure_grid(c, smax, tmax, st));
+    STIF_CUDA(cudaEventRecord(c->ev[1], st));
+
+    const int k = max_pts;
+    int ld = k + 2;
+    if ((ld & 1) == 0) ld += 1;
+    const int warp_doubles = (k + 1) * ld + 5 * (k + 1) + (k + 2) / 2 + 1;
+    const size_t warp_bytes = sizeof(double) * (size_t)warp_doubles;
+    int wpb = (int)((size_t)(200 * 1024) / warp_bytes);
+    if (wpb > 8) wpb = 8;
+    if (wpb < 1) wpb = 1;
+    const size_t solve_smem = warp_bytes * wpb;
+    STIF_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)solve_smem));
+
+    // chunk so that the selection scratch stays below ~16 GB
+    const size_t per_target = (size_t)k * 12 + 32;
+    int64_t chunk = (int64_t)((16ull << 30) / per_target);
+    if (chunk > n_targets) chunk = n_targets;
+    if (chunk > 0x7fffff00) chunk = 0x7fffff00;
+    STIF_TRY(c->k_scratch[S_TKEYS].reserve(4 * 4 * (size_t)chunk));
+    STIF_TRY(c->k_scratch[S_TFLAGS].reserve(4 * 4 * (size_t)chunk));
+    STIF_TRY(c->k_scratch[S_SEL_IDX].reserve(4 * (size_t)chunk * k));
+    STIF_TRY(c->k_scratch[S_SEL_GAMMA].reserve(8 * (size_t)chunk * k));
+    unsigned *tkeys = c->k_scratch[S_TKEYS].as<unsigned>();
+    unsigned *tidx = tkeys + chunk, *tkeys_s = tidx + chunk, *tidx_s = tkeys_s + chunk;
+    int *sel_n = c->k_scratch[S_TFLAGS].as<int>();
+    unsigned *cand_n = reinterpret_cast<unsigned *>(sel_n + chunk);
+    unsigned *exam_n = cand_n + chunk, *singular = exam_n + chunk;
+    double *bbox = c->k_scratch[S_GRIDHDR].as<double>();
+    GridDims *gd = reinterpret_cast<GridDims *>(bbox + 6);
+    const double *ox = c->k_obs.as<double>();
+    const int64_t n_obs = c->n_obs;
+
+    for (int64_t c0 = 0; c0 < n_targets; c0 += chunk) {
+        const int nc = (int)((n_targets - c0 < chunk) ? (n_targets - c0) : chunk);
+        const int tb = 256;
+        target_keys_kernel<<<(nc + tb - 1) / tb, tb, 0, st>>>(tx + c0, ty + c0, tt + c0, nc, gd, tkeys, tidx);
+        size_t tmp = 0;
+        STIF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, tkeys, tkeys_s, tidx, tidx_s, nc, 0, 25, st));
+        STIF_TRY(c->k_scratch[S_CUB].reserve(tmp));
+        STIF_CUDA(cub::DeviceRadixSort::SortPairs(c->k_scratch[S_CUB].p, tmp, tkeys, tkeys_s, tidx,
+                                                  tidx_s, nc, 0, 25, st));
+        STIF_CUDA(cudaMemsetAsync(singular, 0, 4 * (size_t)nc, st));
+
+        SearchParams SP;
+        SP.obs = c->k_scratch[S_OBS_SORTED].as<double4>();
+        SP.cell_start = c->k_scratch[S_CELL_START].as<unsigned>();
+        SP.gd = gd;
+        SP.tx = tx;
+        SP.ty = ty;
+        SP.tt = tt;
+        SP.leave_out = reinterpret_cast<const long long *>(leave_out);
+        SP.order = tidx_s;
+        SP.c0 = c0;
+        SP.n = nc;
+        SP.smax2 = smax * smax;   // space_dist_max**2, data.py:207
+        SP.tmax = tmax;
+        SP.k = k;
+        SP.min_pts = min_pts;
+        SP.M = M;
+        SP.sel_n = sel_n;
+        SP.sel_idx = c->k_scratch[S_SEL_IDX].as<unsigned>();
+        SP.sel_gamma = c->k_scratch[S_SEL_GAMMA].as<double>();
+        SP.cand_n = cand_n;
+        SP.exam_n = exam_n;
+        search_kernel<<<(nc + SEARCH_WARPS - 1) / SEARCH_WARPS, SEARCH_WARPS * 32, 0, st>>>(SP);
+        STIF_CUDA(cudaGetLastError());
+        if (c0 + chunk >= n_targets) STIF_CUDA(cudaEventRecord(c->ev[2], st));
+
+        SolveParams QP;
+        QP.ox = ox;
+        QP.oy = ox + n_obs;
+        QP.ot = ox + 2 * n_obs;
+        QP.oresid = ox + 3 * n_obs;
+        QP.order = tidx_s;
+        QP.c0 = c0;
+        QP.n = nc;
+        QP.k = k;
+        QP.ld = ld;
+        QP.flags = flags;
+        QP.M = M;
+        QP.sel_n = sel_n;
+        QP.sel_idx = SP.sel_idx;
+        QP.sel_gamma = SP.sel_gamma;
+        QP.mean = mean_out;
+        QP.std = std_out;
+        QP.w_out = w_out;
+        QP.g_out = gamma_out;
+        QP.idx_out = idx_out;
+        QP.nused_out = n_used_out;
+        QP.singular = singular;
+        solve_kernel<<<(nc + wpb - 1) / wpb, wpb * 32, solve_smem, st>>>(QP, wpb, warp_doubles);
+        STIF_CUDA(cudaGetLastError());
+        stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,
+                                                 c->k_stats.as<unsigned long long>());
+        STIF_CUDA(cudaGetLastError());
+    }
+    STIF_CUDA(cudaEventRecord(c->ev[3], st));
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_predict_host(stif_ctx *c, const double *tx, const double *ty,
+                                         const double *tt, const int64_t *leave_out, int64_t n,
+                                         int min_pts, int max_pts, double smax, double tmax, int flags,
+                                         double *mean_out, double *std_out, float *w_out,
+                                         float *gamma_out, uint32_t *idx_out, int32_t *n_used_out)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_predict"));
+    if (n < 0 || (n > 0 && (!tx || !ty || !tt || !mean_out || !std_out))) {
+        set_error("stif_kriging_predict: bad arguments");
+        return STIF_EINVAL;
+    }
+    if (max_pts < 1 || max_pts > KMAX) {
+        set_error("stif_kriging_predict: max_kriging_points must be in [1, %d], got %d", KMAX, max_pts);
+        return STIF_EINVAL;
+    }
+    if (n == 0) return STIF_OK;
+    const size_t N = (size_t)n, k = (size_t)max_pts;
+    // layout: tx ty tt leave | mean std | w g idx nused
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_tx = take(8 * N), o_ty = take(8 * N), o_tt = take(8 * N);
+    const size_t o_lo = take(leave_out ? 8 * N : 0);
+    const size_t o_mean = take(8 * N), o_std = take(8 * N);
+    const size_t o_w = take(w_out ? 4 * N * k : 0), o_g = take(gamma_out ? 4 * N * k : 0);
+    const size_t o_idx = take(idx_out ? 4 * N * k : 0), o_nu = take(n_used_out ? 4 * N : 0);
+    STIF_TRY(c->k_scratch[S_STAGE].reserve(off));
+    char *b = c->k_scratch[S_STAGE].as<char>();
+    cudaStream_t st = c->stream;
+    STIF_CUDA(cudaMemcpyAsync(b + o_tx, tx, 8 * N, cudaMemcpyHostToDevice, st));
+    STIF_CUDA(cudaMemcpyAsync(b + o_ty, ty, 8 * N, cudaMemcpyHostToDevice, st));
+    STIF_CUDA(cudaMemcpyAsync(b + o_tt, tt, 8 * N, cudaMemcpyHostToDevice, st));
+    if (leave_out) STIF_CUDA(cudaMemcpyAsync(b + o_lo, leave_out, 8 * N, cudaMemcpyHostToDevice, st));
+    STIF_TRY(stif_kriging_predict_dev(
+        c, (double *)(b + o_tx), (double *)(b + o_ty), (double *)(b + o_tt),
+        leave_out ? (int64_t *)(b + o_lo) : nullptr, n, min_pts, max_pts, smax, tmax, flags,
+        (double *)(b + o_mean), (double *)(b + o_std), w_out ? (float *)(b + o_w) : nullptr,
+        gamma_out ? (float *)(b + o_g) : nullptr, idx_out ? (uint32_t *)(b + o_idx) : nullptr,
+        n_used_out ? (int32_t *)(b + o_nu) : nullptr, st));
+    STIF_CUDA(cudaMemcpyAsync(mean_out, b + o_mean, 8 * N, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaMemcpyAsync(std_out, b + o_std, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (w_out) STIF_CUDA(cudaMemcpyAsync(w_out, b + o_w, 4 * N * k, cudaMemcpyDeviceToHost, st));
+    if (gamma_out) STIF_CUDA(cudaMemcpyAsync(gamma_out, b + o_g, 4 * N * k, cudaMemcpyDeviceToHost, st));
+    if (idx_out) STIF_CUDA(cudaMemcpyAsync(idx_out, b + o_idx, 4 * N * k, cudaMemcpyDeviceToHost, st));
+    if (n_used_out) STIF_CUDA(cudaMemcpyAsync(n_used_out, b + o_nu, 4 * N, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_stats(stif_ctx *c, uint64_t out[4])
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_stats"));
+    if (!out) {
+        set_error("stif_kriging_stats: NULL argument");
+        return STIF_EINVAL;
+    }
+    for (int i = 0; i < 4; ++i) out[i] = 0;
+    if (!c->k_stats.p) return STIF_OK;
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    STIF_CUDA(cudaStreamSynchronize(st));
+    unsigned long long h[4];
+    STIF_CUDA(cudaMemcpy(h, c->k_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = h[i];
+    return STIF_OK;
 }

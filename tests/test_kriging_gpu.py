@@ -1,0 +1,178 @@
+"""GPU parity: libstif_b200 kriging (neighbour search, top-k, assemble + solve, epilogue)
+vs the CPU oracle, through the C ABI (stif_kriging_predict_host).
+
+Tolerances (north star): neighbour sets identical (ties broken by index); kriging mean and
+variance within 1e-9 relative in float64 mode.  In float32-storage mode (the stock
+reference's arithmetic) weights/gammas must agree to 1 float32 ulp and mean/std to the
+float32 rounding that implies."""
+import numpy as np
+import pytest
+
+from oracle import kriging as ok
+from stif_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+SUM_METRIC = ("sum_metric", "spherical", "spherical", "spherical")
+PRODUCT_SUM = ("product_sum", "spherical", "spherical", "spherical")
+P_SUM_METRIC = [400, 60, 500, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0]
+P_PRODUCT_SUM = [300, 60, 0.8, 0.7, 0.15, 0.10, 0.4]
+RTOL = 1e-9
+
+
+def synth(n_obs, n_tgt, seed=20261020, extent=300.0):
+    rng = np.random.default_rng(seed)
+    space = rng.uniform(0, extent, (n_obs, 2))
+    t = rng.uniform(0, 365, n_obs)
+    z = np.sin(space[:, 0] / 150) + np.cos(space[:, 1] / 200) + 0.5 * np.sin(t / 30) + 0.3 * rng.normal(size=n_obs)
+    tsp = rng.uniform(0, extent, (n_tgt, 2))
+    tt = rng.uniform(30, 365, n_tgt)
+    return space, t, z, tsp, tt
+
+
+def gpu_predict(ctx, space, t, z, tsp, tt, models, params, min_pts, k, smax, tmax, leave=None, f32=True):
+    x, y = _native.split_space(space)
+    ctx.kriging_set_obs(x, y, t, z)
+    ctx.kriging_set_model(*models, params)
+    tx, ty = _native.split_space(tsp)
+    flags = _native.KRIG_F32_STORAGE if f32 else 0
+    mean, std, w, g, idx, nused = ctx.kriging_predict_host(tx, ty, tt, min_pts, k, smax, tmax, leave_out=leave,
+                                                           flags=flags, want_weights=True)
+    return dict(mean=mean, std=std, w=w, gamma=g, idx=idx, n_used=nused)
+
+
+def compare(g, o, z, f32):
+    n = len(o["mean"])
+    ok_rows = o["tie"] == 0
+    assert ok_rows.mean() > 0.9
+    assert np.array_equal(g["n_used"][ok_rows], o["n_used"][ok_rows])
+    # neighbour sets (and their order) identical
+    assert np.array_equal(g["idx"][ok_rows], o["idx"][ok_rows])
+    # gamma-vector: same formula, float32-rounded -> allow 1 ulp
+    assert np.all(np.abs(g["gamma"][ok_rows] - o["gamma"][ok_rows]) <= np.spacing(np.abs(o["gamma"][ok_rows])))
+    wscale = np.abs(o["w"]).max(axis=1, keepdims=True) + 1e-30
+    solved = o["n_used"] > 0
+    nonsing = ok_rows & solved & (o["rank"] == o["n_used"] + 1)
+    assert nonsing.sum() > 0.9 * solved.sum()
+    skipped = ~solved
+    assert np.all(g["mean"][skipped] == 0) and np.all(g["std"][skipped] == 0)
+    # weights agree to float32 resolution of the row
+    assert np.all(np.abs(g["w"][nonsing] - o["w"][nonsing]) <= 2.0 ** -22 * wscale[nonsing])
+    resid_abs = np.abs(z[o["idx"].astype(np.int64)])
+    mscale = np.sum(np.abs(o["w"].astype(np.float64)) * resid_abs, axis=1) + 1e-300
+    vscale = np.sum(np.abs(o["w"].astype(np.float64) * o["gamma"]), axis=1) + 1e-300
+    dm = np.abs(g["mean"] - o["mean"])[nonsing]
+    var_g, var_o = g["std"] ** 2, o["std"] ** 2
+    both_nan = np.isnan(var_g) & np.isnan(var_o)
+    dv = np.where(both_nan, 0.0, np.abs(var_g - var_o))[nonsing]
+    if f32:
+        # a weight may land on the other side of a float32 rounding boundary
+        assert np.all(dm <= 2.0 ** -22 * mscale[nonsing])
+        assert np.mean(dm <= RTOL * mscale[nonsing]) > 0.8
+        assert np.all(dv <= 2.0 ** -20 * vscale[nonsing])
+    else:
+        assert np.all(dm <= RTOL * mscale[nonsing]), dm.max()
+        assert np.all(dv <= RTOL * vscale[nonsing]), dv.max()
+
+
+@pytest.mark.parametrize("f32", [False, True])
+@pytest.mark.parametrize("models,params,k", [
+    (SUM_METRIC, P_SUM_METRIC, 50),
+    (PRODUCT_SUM, P_PRODUCT_SUM, 20),
+    (("sum_metric", "gaussian", "spherical", "gaussian"), P_SUM_METRIC, 10),
+    (("sum", "spherical", "gaussian", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 16),
+    (("metric", "spherical", "spherical", "spherical"), [500, 1.0, 0.05, 5.0], 33),
+    (("product", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 8),
+])
+def test_models(ctx, models, params, k, f32):
+    space, t, z, tsp, tt = synth(20000, 400)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=f32)
+    o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32_storage=f32)
+    compare(g, o, z, f32)
+
+
+def test_k100_many_candidates(ctx):
+    # > 512 candidates per target exercises the streaming select
+    space, t, z, tsp, tt = synth(60000, 120, seed=7)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 100, 60.0, 60.0, f32=False)
+    o = ok.predict(space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 100, 60.0, 60.0, f32_storage=False)
+    assert o["n_cand"].max() > 600
+    compare(g, o, z, False)
+
+
+def test_min_points_and_empty(ctx):
+    space, t, z, tsp, tt = synth(3000, 300, seed=3)
+    tt[:50] = -5.0            # before every observation: causal filter leaves nothing
+    tsp[50:60] = 1e6          # far outside the grid
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 10, 12, 30.0, 30.0)
+    o = ok.predict(space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 10, 12, 30.0, 30.0)
+    assert np.all(g["n_used"][:60] == -1) and np.all(g["mean"][:60] == 0) and np.all(g["std"][:60] == 0)
+    assert (o["n_used"] == -1).sum() > 60
+    compare(g, o, z, True)
+
+
+def test_leave_out(ctx):
+    space, t, z, _, _ = synth(5000, 1, seed=5)
+    sel = np.arange(0, 5000, 10)
+    tsp, tt = space[sel], t[sel]
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 20, 60.0, 60.0, leave=sel, f32=False)
+    o = ok.predict(space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 20, 60.0, 60.0, leave_out_idxs=sel,
+                   f32_storage=False)
+    for i, s in enumerate(sel):
+        assert s not in g["idx"][i][:max(g["n_used"][i], 0)]
+    compare(g, o, z, False)
+    # without leave-out the observation itself (h=0, t=0) is the first neighbour
+    g2 = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 20, 60.0, 60.0, f32=False)
+    assert np.mean(np.any(g2["idx"] == sel[:, None], axis=1)) > 0.99
+
+
+def test_integer_times_strict_radii(ctx):
+    # lattice in space and integer days: candidates exactly ON the radii must be excluded
+    gx, gy = np.meshgrid(np.arange(12.0), np.arange(12.0))
+    pts = np.column_stack([gx.ravel(), gy.ravel()])
+    days = np.arange(40)
+    space = np.repeat(pts, len(days), axis=0)
+    t = np.tile(days, len(pts)).astype(np.int64)
+    rng = np.random.default_rng(2)
+    z = rng.normal(size=len(t))
+    tsp = pts[rng.integers(0, len(pts), 200)] + 0.0
+    tt = rng.integers(5, 40, 200)
+    for f32 in (True, False):
+        g = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, [6, 9, 0.8, 0.7, 0.15, 0.10, 0.4], 1, 30, 3.0, 4,
+                        f32=f32)
+        o = ok.predict(space, t, z, tsp, tt, PRODUCT_SUM, [6, 9, 0.8, 0.7, 0.15, 0.10, 0.4], 1, 30, 3.0, 4,
+                       f32_storage=f32)
+        # ties are everywhere on a lattice: compare the candidate counts (filter parity) and
+        # the untied rows only
+        ctx_stats = ctx.kriging_stats()
+        assert ctx_stats["candidates_in_window"] == int(o["n_cand"].sum())
+        if (o["tie"] == 0).mean() > 0.9:
+            compare(g, o, z, f32)
+
+
+def test_model_eval(ctx):
+    rng = np.random.default_rng(0)
+    h = rng.uniform(0, 700, 1000)
+    t = rng.uniform(0, 100, 1000)
+    for models, params in [(SUM_METRIC, P_SUM_METRIC), (PRODUCT_SUM, P_PRODUCT_SUM),
+                           (("sum_metric", "gaussian", "gaussian", "gaussian"), P_SUM_METRIC)]:
+        ctx.kriging_set_model(*models, params)
+        got = ctx.variogram_model_eval(h, t)
+        want = ok.gamma(models, params, h, t)
+        assert np.allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_errors(ctx):
+    c2 = _native.Context(0)
+    z = np.zeros(4)
+    with pytest.raises(ValueError):
+        c2.kriging_predict_host(z, z, z, 1, 10, 1.0, 1.0)      # no model / obs
+    c2.kriging_set_model(*SUM_METRIC, P_SUM_METRIC)
+    with pytest.raises(ValueError):
+        c2.kriging_predict_host(z, z, z, 1, 10, 1.0, 1.0)      # no observations
+    c2.kriging_set_obs(z, z, z, z)
+    with pytest.raises(ValueError):
+        c2.kriging_predict_host(z, z, z, 1, 1000, 1.0, 1.0)    # k too large
+    with pytest.raises(ValueError):
+        c2.kriging_set_model("sum_metric", "spherical", "spherical", "spherical", [1, 2, 3])
+    c2.close()

@@ -1,0 +1,486 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark of the STIF hot path on B200.
+
+    python bench.py --gpus 1 --steps K --warmup W              # N = 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W  # N > 1, one rank per GPU
+    python bench.py --impl reference ...                        # CPU oracle port of the reference
+
+Prints ONE JSON line (rank 0).  The headline metric is BASELINE.json's first half --
+all-pairs space-time variogram pairs/s -- on configs[1] (C2: 100k observations, 30x30 bins)
+at N = 1 and on configs[2] (C3: 1M observations, tile pairs sharded over ranks + one NCCL
+all-reduce of the histograms) at N > 1.  The second half -- kriging predictions/s, k = 50,
+configs[3] (C4) -- is reported in the same line under "kriging" with the same sub-keys.
+
+A "step" is one pass of the hot path over the whole synthetic workload.  `value` has the
+inputs resident in HBM; `e2e` goes through the C ABI's host-pointer entry point with pinned
+host buffers (H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C2_N = 100_000
+C3_N = 1_000_000
+VARIO = dict(space_dist_max=30.0, time_dist_max=30.0, n_space_bins=30, n_time_bins=30)
+C4_OBS = 1_000_000
+C4_TARGETS_PER_GPU = 1_250_000       # 10M targets over 8 GPUs
+C4_MODEL = ("sum_metric", "spherical", "spherical", "spherical")
+C4_PARAMS = [400, 60, 500, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0]
+C4_K = 50
+C4_RADII = (30.0, 30.0)
+FP64_PER_PAIR = 7.0                  # dx dy mul fma cmp dt cmp
+FP64_PER_BINNED = 8.0
+
+
+def synth_variogram(n):
+    """SURVEY 8(d) C2/C3 generator."""
+    rng = np.random.default_rng(20261019)
+    x = rng.uniform(0, 100, n)
+    y = rng.uniform(0, 100, n)
+    t = rng.integers(0, 365, n).astype(np.float64)   # int64 days; exact in float64
+    v = rng.normal(size=n)
+    return x, y, t, v
+
+
+def synth_kriging(n_obs, n_targets, rank=0):
+    """SURVEY 8(d) C4 generator (targets drawn per rank so shards differ)."""
+    rng = np.random.default_rng(20261020)
+    x = rng.uniform(0, 1000, n_obs)
+    y = rng.uniform(0, 1000, n_obs)
+    t = rng.uniform(0, 365, n_obs)
+    z = np.sin(x / 150) + np.cos(y / 200) + 0.5 * np.sin(t / 30) + 0.3 * rng.normal(size=n_obs)
+    trng = np.random.default_rng(20261020 + 1000 + rank)
+    tx = trng.uniform(0, 1000, n_targets)
+    ty = trng.uniform(0, 1000, n_targets)
+    tt = trng.uniform(30, 365, n_targets)
+    return (x, y, t, z), (tx, ty, tt)
+
+
+def kriging_flops(k, cbar, f_gamma=42.0):
+    """algorithmic FP64 flops per prediction (FMA = 2)."""
+    return cbar * f_gamma + k * (k - 1) / 2 * f_gamma + (k + 1) ** 3 / 3 + 2 * (k + 1) ** 2 + 4 * k
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index, period=0.005):
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+            return self
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "power_w_max": (max(self.power) if self.power else None)}
+
+
+def pinned(a):
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    out = t.numpy()
+    out[...] = a
+    return out, t
+
+
+# ----------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from stif_b200 import _native, parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference "
+                         "for the CPU oracle port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _native.Context(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    # measured FP64 issue peak (MEASURED_PEAKS.json has HBM and bf16 only)
+    ctx.bench_dfma(1024)
+    dfma_rate, _ = ctx.bench_dfma(8192)
+
+    # ---------------- variogram ----------------
+    workload = args.workload
+    if workload == "auto":
+        workload = "c2" if world == 1 else "c3"
+    n = C2_N if workload == "c2" else C3_N
+    x, y, t, v = synth_variogram(n)
+    pairs = n * (n - 1) // 2
+    ns, nt = VARIO["n_space_bins"], VARIO["n_time_bins"]
+    dx, dy, dt_, dv = (torch.from_numpy(a).to(dev) for a in (x, y, t, v))
+    counts = torch.zeros(ns * nt, dtype=torch.int64, device=dev)
+    sums = torch.zeros(ns * nt, dtype=torch.float64, device=dev)
+
+    def vario_step():
+        ctx.variogram_dev(dx.data_ptr(), dy.data_ptr(), dt_.data_ptr(), dv.data_ptr(), n,
+                          VARIO["space_dist_max"], VARIO["time_dist_max"], ns, nt,
+                          counts.data_ptr(), sums.data_ptr(), part=rank, nparts=world, stream=stream)
+        if world > 1:
+            dist.all_reduce(counts)     # the path's one real exchange: 14.4 KB of histograms
+            dist.all_reduce(sums)
+
+    for _ in range(args.warmup):
+        vario_step()
+    barrier()
+    sampler = ClockSampler(local_rank).start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pair_ms = 0.0
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_l2()
+        if world > 1:
+            dist.barrier()
+        starts[i].record()
+        vario_step()
+        ends[i].record()
+        ends[i].synchronize()
+        pair_ms += ctx.last_phase_ms()[1]
+    barrier()
+    wall_bracket = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = max_over_ranks(sum(step_ms))
+    ms_per_step = total_ms / args.steps
+    value = pairs / (ms_per_step * 1e-3)
+    stats = ctx.variogram_stats()
+    binned_total = int(counts.sum().item())
+    f_binned = binned_total / pairs
+    lane_instr_per_pair = FP64_PER_PAIR + FP64_PER_BINNED * f_binned
+    pair_ms_avg = max_over_ranks(pair_ms) / args.steps
+    achieved = pairs * lane_instr_per_pair / world / (pair_ms_avg * 1e-3)   # per GPU
+    roofline = {
+        "bound": "fp64_issue", "kernel": "stif::vario::pair_kernel",
+        "achieved": achieved, "peak": dfma_rate, "unit": "FP64 lane-instr/s per GPU",
+        "frac": achieved / dfma_rate,
+        "peak_source": "measured live: register-resident DFMA microbenchmark (stif_bench_dfma); "
+                       "nominal 148 SM x 64 lanes x 1.965 GHz = 1.861e13",
+        "frac_of_nominal": achieved / 1.861e13,
+        "algorithmic_lane_instr_per_pair": lane_instr_per_pair,
+        "kernel_ms": pair_ms_avg,
+        "pairs_evaluated_frac": stats["pairs_evaluated"] * world / pairs,
+        "traffic": None,
+        "note": "tile pairs outside the time window are culled (SURVEY 8d allows it); rate is "
+                "per algorithmic pair, so frac may exceed the un-culled FP64 bound",
+    }
+
+    # e2e through the host-pointer C ABI with pinned buffers
+    (hx, _kx), (hy, _ky), (ht, _kt), (hv, _kv) = pinned(x), pinned(y), pinned(t), pinned(v)
+
+    def vario_e2e():
+        c, s = ctx.variogram_host(hx, hy, ht, hv, VARIO["space_dist_max"], VARIO["time_dist_max"], ns, nt,
+                                  part=rank, nparts=world)
+        return parallel.allreduce_histograms(c, s)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        vario_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_host, s_host = vario_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    assert int(c_host.sum()) == binned_total
+    e2e = {"value": pairs / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 16 * ns * nt}
+
+    out = {
+        "metric": "variogram_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong" if workload == "c3" else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": ("C2: synthetic 100k observations x 365 days, all-pairs space-time variogram, "
+                         "30x30 lag bins, smax=30 tmax=30" if workload == "c2" else
+                         "C3: synthetic 1M observations, all-pairs variogram, 30x30 lag bins, tile pairs "
+                         "sharded over ranks + NCCL all-reduce of the histograms"),
+            "n_obs": n, "pairs": pairs, "binned_pairs": binned_total,
+            "l2": "256 MB device write between steps (outside the per-step CUDA-event pairs); "
+                  "inputs (32 B/obs) are L2-resident by design",
+            "timing": "per-step CUDA events on torch's current stream, summed; max over ranks",
+            "parallelism": f"tile-pair partition x{world}",
+        },
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 6 * args.steps,
+        "roofline": roofline, "wall_s_bracket": wall_bracket,
+    }
+
+    # ---------------- kriging (C4 share per GPU) ----------------
+    if not args.no_kriging:
+        out["kriging"] = run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier,
+                                          max_over_ranks, flush_l2, dfma_rate)
+
+    # ---------------- CPU baseline (rank 0, N = 1) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_variogram_baseline(x, y, t, v, n)
+        if "kriging" in out:
+            out["kriging"]["cpu_baseline"] = cpu_kriging_baseline()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, max_over_ranks, flush_l2,
+                     dfma_rate):
+    import torch
+    n_t = args.kriging_targets or C4_TARGETS_PER_GPU
+    steps = max(1, min(args.steps, args.kriging_steps))
+    (ox, oy, ot, oz), (tx, ty, tt) = synth_kriging(C4_OBS, n_t, rank)
+    ctx.kriging_set_obs(ox, oy, ot, oz)
+    ctx.kriging_set_model(*C4_MODEL, C4_PARAMS)
+    dtx, dty, dtt = (torch.from_numpy(a).to(dev) for a in (tx, ty, tt))
+    mean = torch.zeros(n_t, dtype=torch.float64, device=dev)
+    std = torch.zeros(n_t, dtype=torch.float64, device=dev)
+
+    def step():
+        ctx.kriging_predict_dev(dtx.data_ptr(), dty.data_ptr(), dtt.data_ptr(), n_t, 1, C4_K,
+                                C4_RADII[0], C4_RADII[1], mean.data_ptr(), std.data_ptr(), stream=stream)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank).start()
+    tot_ms, search_ms, solve_ms = 0.0, 0.0, 0.0
+    for _ in range(steps):
+        flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step()
+        e.record()
+        e.synchronize()
+        tot_ms += s.elapsed_time(e)
+        ph = ctx.last_phase_ms()
+        search_ms += ph[1]
+        solve_ms += ph[2]
+    barrier()
+    clocks = sampler.stop()
+    ms_per_step = max_over_ranks(tot_ms) / steps
+    st = ctx.kriging_stats()
+    cbar = st["candidates_in_window"] / n_t
+    flops = kriging_flops(C4_K, cbar)
+    solve_ms_avg = max_over_ranks(solve_ms) / steps
+    achieved = n_t * flops / (solve_ms_avg * 1e-3) / 1e12
+    peak_tf = 2 * dfma_rate / 1e12
+
+    (hx, _a), (hy, _b), (ht, _c) = pinned(tx), pinned(ty), pinned(tt)
+    ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m_host, s_host = ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1])
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / steps
+    return {
+        "metric": "kriging_predictions_per_s", "value": n_t * world / (ms_per_step * 1e-3),
+        "unit": "predictions/s", "n_gpus": world, "steps": steps, "ms_per_step": ms_per_step,
+        "scaling": "weak", "dtype": "f64",
+        "config": {"workload": "C4 share: 1M observations (replicated), 1.25M targets per GPU, k=50, "
+                               "sum_metric/spherical, radii 30/30, float32-storage emulation on",
+                   "n_obs": C4_OBS, "targets_per_gpu": n_t, "k": C4_K,
+                   "candidates_per_target": cbar,
+                   "candidates_examined_per_target": st["candidates_examined"] / n_t,
+                   "l2": "256 MB device write between steps"},
+        "phases_ms": {"search": max_over_ranks(search_ms) / steps, "solve": solve_ms_avg},
+        "e2e": {"value": n_t * world / e2e_s, "unit": "predictions/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t},
+        "gpu_launches": 4 * steps,
+        "roofline": {"bound": "fp64", "kernel": "stif::krig::solve_kernel", "achieved": achieved,
+                     "peak": peak_tf, "unit": "TFLOP/s per GPU", "frac": achieved / peak_tf,
+                     "flops_per_prediction": flops, "kernel_ms": solve_ms_avg, "traffic": None,
+                     "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)"},
+        "clocks": clocks,
+        "checksum": {"mean_sum": float(np.nansum(m_host)), "nan": int(np.isnan(m_host).sum())},
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# CPU oracle port (cpu_baseline leg and --impl reference)
+# ----------------------------------------------------------------------------------------
+def cpu_variogram_baseline(x, y, t, v, n, target_pairs=1.2e9):
+    from oracle import variogram as ov
+    rows = int(min(n, max(1, target_pairs // n)))
+    space = np.column_stack([x, y])
+    ov.raw(space[:2000], t[:2000], v[:2000], 30.0, 30.0, 30, 30)          # warm
+    t0 = time.perf_counter()
+    h, c = ov.raw(space, t, v, VARIO["space_dist_max"], VARIO["time_dist_max"], 30, 30, i_begin=0, i_end=rows)
+    dt = time.perf_counter() - t0
+    sample_pairs = rows * n - rows * (rows + 1) // 2
+    return {"value": sample_pairs / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+            "sample": f"rows 0..{rows} of the {n}-observation upper triangle = {sample_pairs} pairs in "
+                      f"{dt:.1f} s (the reference loop is serial: 1 core)",
+            "host_cores": os.cpu_count()}
+
+
+def cpu_kriging_baseline(n_targets=8000):
+    from oracle import kriging as ok
+    (ox, oy, ot, oz), (tx, ty, tt) = synth_kriging(C4_OBS, n_targets, 0)
+    space = np.column_stack([ox, oy])
+    tsp = np.column_stack([tx, ty])
+    threads = os.cpu_count() or 1
+    ok.predict(space[:5000], ot[:5000], oz[:5000], tsp[:16], tt[:16], C4_MODEL, C4_PARAMS, 1, C4_K, 30.0, 30.0)
+    t0 = time.perf_counter()
+    ok.predict(space, ot, oz, tsp, tt, C4_MODEL, C4_PARAMS, 1, C4_K, C4_RADII[0], C4_RADII[1], n_threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": n_targets / dt, "unit": "predictions/s", "cores": threads, "kind": "port",
+            "sample": f"{n_targets} targets against all 1M observations (dense filter like "
+                      f"Data.get_kriging_idxs, dgelsd solve) in {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle port of the reference's path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    workload = args.workload
+    if workload == "auto":
+        workload = "c2" if world == 1 else "c3"
+    n = C2_N if workload == "c2" else C3_N
+    x, y, t, v = synth_variogram(n)
+    from oracle import variogram as ov
+    space = np.column_stack([x, y])
+    per_step_pairs = 3e8 if args.steps > 3 else 1e9
+    rows = int(max(1, per_step_pairs // n))
+    for _ in range(min(args.warmup, 2)):
+        ov.raw(space, t, v, 30.0, 30.0, 30, 30, i_begin=0, i_end=max(1, rows // 10))
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        b = (s * rows) % max(1, n // 2)
+        ov.raw(space, t, v, VARIO["space_dist_max"], VARIO["time_dist_max"], 30, 30, i_begin=b, i_end=b + rows)
+    dt = time.perf_counter() - t0
+    sample_pairs = 0
+    for s in range(args.steps):
+        b = (s * rows) % max(1, n // 2)
+        sample_pairs += sum(n - 1 - i for i in range(b, min(b + rows, n)))
+    rate = sample_pairs / dt
+    pairs = n * (n - 1) // 2
+    out = {
+        "impl": "reference", "metric": "variogram_pairs_per_s", "value": rate, "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": pairs / rate * 1e3, "higher_is_better": True,
+        "scaling": "strong" if workload == "c3" else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: synthetic 100k observations, 30x30 bins" if workload == "c2" else
+                               "C3: synthetic 1M observations, 30x30 bins",
+                   "n_obs": n, "pairs": pairs,
+                   "note": "ms_per_step is the full workload extrapolated from the measured per-pair "
+                           "rate (rate is N-independent); each timed step is a bounded sample"},
+        "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} steps x {rows} rows of the upper triangle "
+                                   f"({sample_pairs} pairs, {dt:.1f} s); serial like the reference loop"},
+        "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not args.no_kriging:
+        kb = cpu_kriging_baseline(n_targets=8000)
+        out["kriging"] = {"impl": "reference", "metric": "kriging_predictions_per_s", "value": kb["value"],
+                          "unit": "predictions/s", "cpu_baseline": kb,
+                          "e2e": {"value": kb["value"], "unit": "predictions/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"])
+    ap.add_argument("--no-kriging", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kriging-steps", type=int, default=3)
+    ap.add_argument("--kriging-targets", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

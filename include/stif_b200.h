@@ -86,6 +86,24 @@ int stif_variogram_host(stif_ctx *ctx, const double *x, const double *y, const d
                         double mean, int flags, int part, int nparts,
                         uint64_t *counts_host, double *sums_host);
 
+/* Sampled-pair branch of _pair_index_generator (stif/utils.py:94-101), reached when the
+ * caller passes el_max: n_samples draws of an ordered pair (i, j) with replacement, each
+ * index uniform in [0, n); draws with i == j are skipped but still count.  The reference's
+ * RNG (numba MT19937) is seeded from the OS, so its results are not reproducible and parity
+ * is statistical only; this implementation is reproducible for a given `seed`
+ * (counter-based Philox4x32-10, one counter per draw). */
+int stif_variogram_sampled_dev(stif_ctx *ctx, const double *x, const double *y, const double *t,
+                               const double *v, int64_t n, double space_dist_max,
+                               double time_dist_max, int n_space_bins, int n_time_bins, int mode,
+                               double mean, uint64_t n_samples, uint64_t seed,
+                               uint64_t *counts_dev, double *sums_dev, void *stream);
+
+int stif_variogram_sampled_host(stif_ctx *ctx, const double *x, const double *y, const double *t,
+                                const double *v, int64_t n, double space_dist_max,
+                                double time_dist_max, int n_space_bins, int n_time_bins, int mode,
+                                double mean, uint64_t n_samples, uint64_t seed,
+                                uint64_t *counts_host, double *sums_host);
+
 /* Statistics of the last variogram call on this context (after a synchronise):
  * out[0] = algorithmic pairs of this partition's share (n(n-1)/2 when nparts == 1),
  * out[1] = pairs actually evaluated (tile pairs visited x tile area),

@@ -45,6 +45,14 @@ SIGNATURES = {
                                            ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            _vp, _vp]),
+    "stif_variogram_sampled_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64,
+                                                  ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                  ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, _vp]),
+    "stif_variogram_sampled_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64,
+                                                   ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                   ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "stif_variogram_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "stif_kriging_set_obs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int]),
     "stif_kriging_set_model": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -171,6 +179,25 @@ class Context:
             float(time_dist_max), int(n_space_bins), int(n_time_bins), int(mode), float(mean),
             int(flags), int(part), int(nparts), counts_ptr, sums_ptr, stream or None),
             "stif_variogram_dev")
+
+    def variogram_sampled_host(self, x, y, t, v, space_dist_max, time_dist_max, n_space_bins,
+                               n_time_bins, n_samples, mode=0, mean=0.0, seed=None, seed_offset=0):
+        """Sampled-pair branch (el_max).  seed=None draws a fresh seed (like the reference's
+        OS-seeded RNG); pass an int for a reproducible call."""
+        x, y, t, v = _f64(x), _f64(y), _f64(t), _f64(v)
+        n = len(x)
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        seed = (int(seed) + 0x9E3779B97F4A7C15 * int(seed_offset)) & 0xFFFFFFFFFFFFFFFF
+        nb = int(n_space_bins) * int(n_time_bins)
+        counts = np.zeros(max(nb, 0), dtype=np.uint64)
+        sums = np.zeros(max(nb, 0), dtype=np.float64)
+        _check(self._lib.stif_variogram_sampled_host(
+            self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(v), n, float(space_dist_max),
+            float(time_dist_max), int(n_space_bins), int(n_time_bins), int(mode), float(mean),
+            int(n_samples), seed, _ptr(counts), _ptr(sums)), "stif_variogram_sampled_host")
+        shape = (int(n_space_bins), int(n_time_bins))
+        return counts.reshape(shape), sums.reshape(shape)
 
     def variogram_stats(self):
         out = (ctypes.c_uint64 * 4)()

@@ -364,6 +364,110 @@ __global__ void reduce_kernel(Params P, int nblocks, const double *x, const doub
     sums[b] = s;
 }
 
+
+// ---- sampled-pair branch (el_max / n_samples, stif/utils.py:94-101) -------------------
+// n_samples draws of an ordered pair (i, j), each index uniform in [0, n), i == j skipped
+// (the draw still counts).  The reference uses numba's OS-seeded MT19937, so only
+// statistical parity is possible; here a counter-based Philox4x32-10 stream makes a call
+// reproducible for a given seed.
+__device__ __forceinline__ void philox4x32_10(unsigned long long ctr, unsigned long long key,
+                                              unsigned out[4])
+{
+    unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+    unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+struct SampledParams {
+    const double *x, *y, *t, *v;
+    long long n;
+    unsigned long long n_samples, seed;
+    double smax, tmax;
+};
+
+__global__ void __launch_bounds__(VT) sampled_kernel(Params P, SampledParams Q)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_sum = reinterpret_cast<double *>(smem_raw);
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_sum + P.n_bins);
+    const int tid = threadIdx.x;
+    for (int b = tid; b < P.n_bins; b += VT) {
+        s_sum[b] = 0.0;
+        s_cnt[b] = 0u;
+    }
+    unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
+    double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
+    for (int b = tid; b < P.n_bins; b += VT) my_cnt[b] = 0ull;
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * VT;
+    unsigned long long done = 0;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * VT;; base += stride) {
+        // block-uniform loop bounds so the periodic flush barrier is safe
+        if (base >= Q.n_samples) break;
+        const unsigned long long sidx = base + tid;
+        if (sidx < Q.n_samples) {
+            unsigned r[4];
+            philox4x32_10(sidx, Q.seed, r);
+            const unsigned long long ri = ((unsigned long long)r[1] << 32) | r[0];
+            const unsigned long long rj = ((unsigned long long)r[3] << 32) | r[2];
+            const long long i = (long long)__umul64hi(ri, (unsigned long long)Q.n);
+            const long long j = (long long)__umul64hi(rj, (unsigned long long)Q.n);
+            if (i != j) {
+                const double dx = __dsub_rn(Q.x[i], Q.x[j]), dy = __dsub_rn(Q.y[i], Q.y[j]);
+                const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
+                const double lag_s = __dsqrt_rn(d2);
+                const double lag_t = fabs(__dsub_rn(Q.t[i], Q.t[j]));
+                if (!(lag_s > Q.smax) && !(lag_t > Q.tmax) && d2 == d2 && lag_t == lag_t) {
+                    const long long bs = __double2ll_rz(__dmul_rn(lag_s, P.inv_ws));
+                    const long long bt = __double2ll_rz(__dmul_rn(lag_t, P.inv_wt));
+                    if (bs >= 0 && bs < P.n_space_bins && bt >= 0 && bt < P.n_time_bins) {
+                        double a, b;
+                        if (P.mode == 0) {
+                            a = __dsub_rn(Q.v[i], Q.v[j]);
+                            b = a;
+                        } else {
+                            a = __dsub_rn(Q.v[i], P.mean);
+                            b = __dsub_rn(Q.v[j], P.mean);
+                        }
+                        const int bin = (int)bs * P.n_time_bins + (int)bt;
+                        atomicAdd(&s_sum[bin], __dmul_rn(a, b));
+                        atomicAdd(&s_cnt[bin], 1u);
+                    }
+                }
+            }
+        }
+        if (++done == (1ull << 22)) {  // 2^22 x 256 samples per block < 2^32
+            __syncthreads();
+            for (int b = tid; b < P.n_bins; b += VT) {
+                my_cnt[b] += s_cnt[b];
+                s_cnt[b] = 0u;
+            }
+            __syncthreads();
+            done = 0;
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < P.n_bins; b += VT) {
+        my_cnt[b] += s_cnt[b];
+        my_sum[b] = s_sum[b];
+    }
+}
+
 // Largest double T with sqrt_rn(T) <= smax (host; IEEE sqrt is correctly rounded and
 // monotone, so sqrt_rn(d2) > smax  <=>  d2 > T).
 static double sqrt_cut_threshold(double smax)
@@ -585,6 +689,114 @@ extern "C" int stif_variogram_host(stif_ctx *c, const double *x, const double *y
     }
     STIF_TRY(stif_variogram_dev(c, dx, dy, dt, dv, n, smax, tmax, ns, nt, mode, mean, flags, part,
                                 nparts, dc, ds, st));
+    STIF_CUDA(cudaMemcpyAsync(counts_host, dc, nb * 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaMemcpyAsync(sums_host, ds, nb * 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
+    return STIF_OK;
+}
+
+extern "C" int stif_variogram_sampled_dev(stif_ctx *c, const double *x, const double *y,
+                                          const double *t, const double *v, int64_t n, double smax,
+                                          double tmax, int ns, int nt, int mode, double mean,
+                                          uint64_t n_samples, uint64_t seed, uint64_t *counts_dev,
+                                          double *sums_dev, void *stream_v)
+{
+    if (!c) {
+        set_error("stif_variogram_sampled: ctx is NULL");
+        return STIF_EINVAL;
+    }
+    if (ns <= 0 || nt <= 0 || (int64_t)ns * nt > MAX_BINS || n < 0 || (mode != 0 && mode != 1) ||
+        !counts_dev || !sums_dev || (n > 0 && (!x || !y || !t || !v))) {
+        set_error("stif_variogram_sampled: bad arguments (n=%lld, bins %d x %d)", (long long)n, ns, nt);
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    c->last_stream = st;
+    const int n_bins = ns * nt;
+    STIF_CUDA(cudaEventRecord(c->ev[0], st));
+    STIF_CUDA(cudaEventRecord(c->ev[1], st));
+    c->n_phase = 3;
+    if (n < 2 || n_samples == 0) {
+        STIF_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * n_bins, st));
+        STIF_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * n_bins, st));
+        STIF_CUDA(cudaEventRecord(c->ev[2], st));
+        STIF_CUDA(cudaEventRecord(c->ev[3], st));
+        return STIF_OK;
+    }
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.n_bins = n_bins;
+    P.n_time_bins = nt;
+    P.n_space_bins = ns;
+    P.mode = mode;
+    P.tmax = tmax;
+    const double ws = smax / (double)ns, wt = tmax / (double)nt;
+    P.inv_ws = 1.0 / ws;
+    P.inv_wt = 1.0 / wt;
+    P.mean = mean;
+    SampledParams Q;
+    Q.x = x;
+    Q.y = y;
+    Q.t = t;
+    Q.v = v;
+    Q.n = n;
+    Q.n_samples = n_samples;
+    Q.seed = seed;
+    Q.smax = smax;
+    Q.tmax = tmax;
+    const size_t smem = (sizeof(double) + sizeof(unsigned)) * (size_t)n_bins;
+    STIF_CUDA(cudaFuncSetAttribute(sampled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    int grid = c->sm_count * 4;
+    const unsigned long long want = (n_samples + VT - 1) / VT;
+    if ((unsigned long long)grid > want) grid = (int)want;
+    STIF_TRY(c->v_partial.reserve((sizeof(double) + sizeof(unsigned long long)) * (size_t)grid * n_bins));
+    P.partial_sum = c->v_partial.as<double>();
+    P.partial_cnt = reinterpret_cast<unsigned long long *>(P.partial_sum + (size_t)grid * n_bins);
+    sampled_kernel<<<grid, VT, smem, st>>>(P, Q);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaEventRecord(c->ev[2], st));
+    reduce_kernel<<<(n_bins + 127) / 128, 128, 0, st>>>(
+        P, grid, x, y, t, v, n, smax, ws, wt, 0, reinterpret_cast<unsigned long long *>(counts_dev),
+        sums_dev);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaEventRecord(c->ev[3], st));
+    return STIF_OK;
+}
+
+extern "C" int stif_variogram_sampled_host(stif_ctx *c, const double *x, const double *y,
+                                           const double *t, const double *v, int64_t n, double smax,
+                                           double tmax, int ns, int nt, int mode, double mean,
+                                           uint64_t n_samples, uint64_t seed, uint64_t *counts_host,
+                                           double *sums_host)
+{
+    if (!c) {
+        set_error("stif_variogram_sampled: ctx is NULL");
+        return STIF_EINVAL;
+    }
+    if (ns <= 0 || nt <= 0 || (int64_t)ns * nt > MAX_BINS || n < 0) {
+        set_error("stif_variogram_sampled: bad sizes (n=%lld, bins %d x %d)", (long long)n, ns, nt);
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    const size_t nb = (size_t)ns * nt;
+    const size_t in_bytes = sizeof(double) * (size_t)n;
+    const size_t out_off = (4 * in_bytes + 255) / 256 * 256;
+    STIF_TRY(c->v_stage.reserve(out_off + nb * 16));
+    char *base = c->v_stage.as<char>();
+    double *dx = (double *)base, *dy = dx + n, *dt = dy + n, *dv = dt + n;
+    uint64_t *dc = (uint64_t *)(base + out_off);
+    double *ds = (double *)(base + out_off + nb * 8);
+    cudaStream_t st = c->stream;
+    if (n > 0) {
+        STIF_CUDA(cudaMemcpyAsync(dx, x, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dy, y, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dt, t, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dv, v, in_bytes, cudaMemcpyHostToDevice, st));
+    }
+    STIF_TRY(stif_variogram_sampled_dev(c, dx, dy, dt, dv, n, smax, tmax, ns, nt, mode, mean,
+                                        n_samples, seed, dc, ds, st));
     STIF_CUDA(cudaMemcpyAsync(counts_host, dc, nb * 8, cudaMemcpyDeviceToHost, st));
     STIF_CUDA(cudaMemcpyAsync(sums_host, ds, nb * 8, cudaMemcpyDeviceToHost, st));
     STIF_CUDA(cudaStreamSynchronize(st));

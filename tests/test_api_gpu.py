@@ -1,0 +1,149 @@
+"""GPU: the reference-facing Python API (Predictor / get_variogram) end to end, checked
+against the golden vectors of the unmodified reference and the reference's own (loose)
+test assertions."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from sklearn.linear_model import LinearRegression
+
+from oracle import kriging as ok
+from stif_b200 import Data, Predictor
+from stif_b200.utils import get_covariogram, get_variogram
+
+pytestmark = pytest.mark.gpu
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="module")
+def pm10(golden_dir):
+    d = load(golden_dir, "pm10.npz")
+    return pd.DataFrame({"x": d["x"], "y": d["y"], "time": d["time"], "PM10": d["pm10"]})
+
+
+def test_get_variogram_matches_reference_pm10(golden_dir, pm10, ctx):
+    g = load(golden_dir, "variogram_pm10.npz")
+    space = pm10[["x", "y"]].to_numpy()        # F-ordered, like the reference sees it
+    vg, norm, ws, wt = get_variogram(space, pm10["time"].to_numpy(), pm10["PM10"].to_numpy(), 6e5, 7, 10, 7,
+                                     None, ctx=ctx)
+    assert norm.dtype == np.float64 and norm.sum() == 9009481
+    assert np.array_equal(norm, g["norm"])                                    # bit-exact counts
+    assert np.allclose(vg, g["variogram"], rtol=1e-12, atol=0, equal_nan=True)
+    assert (ws, wt) == tuple(g["widths"])
+    cg, cnorm, _, _ = get_covariogram(space, pm10["time"].to_numpy(), pm10["PM10"].to_numpy(), 5e5, 10, 8, 5,
+                                      None, ctx=ctx)
+    assert np.array_equal(cnorm, g["cnorm"])
+    assert np.allclose(cg, g["covariogram"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    vb, nb, _, _ = get_variogram(space, pm10["time"].to_numpy(), pm10["PM10"].to_numpy() > 20, 6e5, 7, 10, 7,
+                                 None, ctx=ctx)
+    assert np.array_equal(nb, g["norm_binary"])
+    assert np.allclose(vb, g["variogram_binary"], rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_get_variogram_matches_reference_synth(golden_dir, ctx):
+    g = load(golden_dir, "variogram_synth.npz")
+    vg, norm, _, _ = get_variogram(g["space"], g["t_int"], g["v"], 30.0, 30, 30, 30, None, ctx=ctx)
+    assert np.array_equal(norm, g["norm_int"])
+    assert np.allclose(vg, g["vg_int"], rtol=1e-12, atol=0, equal_nan=True)
+    vg, norm, _, _ = get_variogram(g["space"], g["t_flt"], g["v"], 30.0, 30.0, 30, 30, None, ctx=ctx)
+    assert np.array_equal(norm, g["norm_flt"])
+    assert np.allclose(vg, g["vg_flt"], rtol=1e-12, atol=0, equal_nan=True)
+    vg, norm, _, _ = get_variogram(np.asfortranarray(g["space"]), g["t_int"], g["vb"], 25.0, 12, 7, 5, None, ctx=ctx)
+    assert np.array_equal(norm, g["norm_bool"])
+    assert np.allclose(vg, g["vg_bool"], rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_codegen_fingerprint_on_gpu(golden_dir, ctx):
+    """The adversarial 3-point cases (FMA form, reciprocal multiply, peeled first pair)."""
+    g = load(golden_dir, "variogram_adversarial.npz")
+    for i in range(len(g["kind"])):
+        ns, nt = int(g["ns"][i]), int(g["nt"][i])
+        space = np.column_stack([g["x"][i], g["y"][i]])
+        _, norm, _, _ = get_variogram(space, g["t"][i], g["v"], g["smax"][i], g["tmax"][i], ns, nt, None, ctx=ctx)
+        assert np.array_equal(norm, g["norm"][i, : ns * nt].reshape(ns, nt)), (i, g["kind"][i])
+
+
+@pytest.mark.parametrize("name", ["c4", "c5", "gauss", "metric"])
+def test_kriging_matches_reference_synth(golden_dir, ctx, name):
+    g = load(golden_dir, "kriging_synth.npz")
+    k, smax, tmax, min_pts = g[f"{name}_cfg"]
+    df = pd.DataFrame({"x": g["space"][:, 0], "y": g["space"][:, 1], "time": g["t"], "z": g["z"]})
+    p = Predictor(Data(df, space_cols=["x", "y"], time_col="time", predictand_col="z"), context=ctx)
+    p._variogram_bins_space = np.array([1.0])
+    p._variogram_bins_time = np.array([1.0])
+    st, sp, tm, mm = (str(s) for s in g[f"{name}_models"])
+    p.set_variogram_model(g[f"{name}_params"], st, sp, tm, mm)
+    w, gv, idx = p._get_kriging_weights(g["tsp"], g["tt"], int(min_pts), int(k), smax, tmax)
+    mean, std = p.get_kriging_prediction(g["tsp"], g["tt"], int(min_pts), int(k), smax, tmax)
+    assert w.dtype == np.float32 and gv.dtype == np.float32 and idx.dtype == np.uint32
+    assert np.array_equal(idx, g[f"{name}_idx"])                     # neighbour sets identical
+    assert np.all(np.abs(gv - g[f"{name}_gamma"]) <= np.spacing(np.abs(g[f"{name}_gamma"])))
+    wscale = np.abs(g[f"{name}_w"]).max(axis=1, keepdims=True) + 1e-30
+    assert np.all(np.abs(w - g[f"{name}_w"]) <= 2.0 ** -21 * wscale)
+    zabs = np.abs(g["z"][g[f"{name}_idx"].astype(np.int64)])
+    mscale = np.sum(np.abs(g[f"{name}_w"].astype(np.float64)) * zabs, axis=1) + 1e-300
+    dm = np.abs(mean - g[f"{name}_mean"])
+    assert np.all(dm <= 2.0 ** -21 * mscale)
+    assert np.mean(dm <= 1e-9 * mscale) > 0.8
+    both = ~(np.isnan(std) | np.isnan(g[f"{name}_std"]))
+    assert np.array_equal(np.isnan(std), np.isnan(g[f"{name}_std"])) or both.mean() > 0.95
+    assert np.allclose(std[both], g[f"{name}_std"][both], rtol=1e-4, atol=1e-6)
+
+
+def test_reference_test_kriging_prediction(pm10, ctx):
+    """tests/test_predictor.py:291-324 of the reference, all-pairs instead of el_max."""
+    data = Data(pm10, space_cols=["x", "y"], time_col="time", predictand_col="PM10",
+                covariate_cols=["x", "y", "time"])
+    p = Predictor(data, LinearRegression(), context=ctx)
+    p.fit_covariate_model()
+    p.calc_empirical_variogram(space_dist_max=6e5, time_dist_max=7, n_time_bins=7)
+    assert np.isclose(np.nanmin(p._variogram), 27.8, rtol=0.5)      # :203-204
+    assert np.isclose(np.nanmax(p._variogram), 136.0, rtol=0.5)
+    p.fit_variogram_model()
+    assert p._variogram_fit.fun < 100                                # :287
+    sample = pm10.iloc[21000:21025]
+    mean, std = p.get_kriging_prediction(sample[["x", "y"]].to_numpy(), sample["time"].to_numpy())
+    assert np.isclose(mean[0], -5.3, atol=3.0)                       # :324
+    grid = p._get_variogram_model_grid()
+    assert grid.shape == p._variogram.shape and np.all(np.isfinite(grid))
+
+
+def test_reference_test_predict_and_el_max(pm10, ctx, tmp_path):
+    """tests/test_predictor.py:451-480 (predict, no covariate model, sampled variogram)."""
+    data = Data(pm10, space_cols=["x", "y"], time_col="time", predictand_col="PM10")
+    p = Predictor(data, context=ctx)
+    p.calc_empirical_variogram(space_dist_max=6e5, time_dist_max=7, n_time_bins=7, el_max=1e7)
+    sampled = p._variogram.copy()
+    assert np.isclose(np.nanmin(sampled), 27.8, rtol=0.5) and np.isclose(np.nanmax(sampled), 136.0, rtol=0.5)
+    assert 3e5 < p._variogram_samples_per_bin.sum() < 3.7e5           # 1e7 * 9.0e6 / (n^2/2) draws binned
+    p.calc_empirical_variogram(space_dist_max=6e5, time_dist_max=7, n_time_bins=7)
+    assert np.allclose(sampled, p._variogram, rtol=0.05)              # sampling error only
+    path = str(tmp_path / "vg.npz")
+    p.save_empirical_variogram(path)
+    q = Predictor(data, context=ctx)
+    q.load_empirical_variogram(path)
+    assert np.allclose(q._variogram, p._variogram, rtol=0.01, equal_nan=True)   # :258
+    p.fit_variogram_model(st_model="sum_metric")
+    mean, std = p.predict(pm10.iloc[21000:21200],
+                          kriging_params=dict(min_kriging_points=10, max_kriging_points=100, space_dist_max=2e5))
+    assert np.isclose(np.nanmean(mean), 10, rtol=0.5)                 # :479-480
+    assert np.isclose(np.nanmean(std), 5, rtol=0.8)
+
+
+def test_cross_validation_with_leave_out(pm10, ctx):
+    """tests/test_predictor.py:370-414 shape: kriging CV with leave_out_idxs and idxs=train."""
+    sub = pm10.iloc[::4].reset_index(drop=True)
+    data = Data(sub, space_cols=["x", "y"], time_col="time", predictand_col="PM10",
+                covariate_cols=["x", "y", "time"])
+    p = Predictor(data, LinearRegression(), cv_splits=3, context=ctx)
+    p.calc_cross_validation(kriging=True, max_test_samples=200, geostat_params=dict(
+        variogram_params=dict(space_dist_max=6e5, time_dist_max=7, n_time_bins=7),
+        kriging_params=dict(min_kriging_points=1, max_kriging_points=10, space_dist_max=2e5)))
+    from sklearn.metrics import explained_variance_score
+    scores = p.get_cross_val_metric(explained_variance_score)
+    assert len(scores) == 3 and all(np.isfinite(s) for s in scores)
+    assert max(scores) > 0.2

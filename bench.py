@@ -159,7 +159,12 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = _native.Context(local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: the kernels, the NCCL all-reduce and the timing
+    # events all go to it (the C ABI treats a NULL stream as "the context's own stream")
+    bench_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(bench_stream)
+    stream = bench_stream.cuda_stream
+    assert stream != 0
 
     def barrier():
         if world > 1:

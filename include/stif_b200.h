@@ -11,8 +11,9 @@
  *   - every function returns 0 on success or a negative STIF_E* code and never throws;
  *     stif_last_error() returns a thread-local message for the last failure.
  *   - "_dev" entry points take DEVICE pointers (e.g. torch tensors' data_ptr()) and a
- *     cudaStream_t passed as void* (NULL = the context's own stream); they enqueue work
- *     and return without synchronising.  The matching host-pointer entry points copy
+ *     cudaStream_t passed as void* (NULL = the context's own stream; pass cudaStreamLegacy,
+ *     (void*)1, for the legacy default stream); they enqueue work and return without
+ *     synchronising.  The matching host-pointer entry points copy
  *     in, run, copy out and synchronise.
  *   - observations are structure-of-arrays float64 (x, y, t, value).  int64 times and
  *     bool values are converted by the caller; the conversion is exact below 2^53.

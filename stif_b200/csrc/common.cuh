@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/stif_b200.h"
 
@@ -83,6 +84,8 @@ struct stif_ctx {
     stif::DevBuf v_partial;    // per-block partial histograms
     stif::DevBuf v_stats;      // device counters
     stif::DevBuf v_stage;      // staging for host entry point
+    stif::DevBuf v_thr;        // d2 bin thresholds
+    std::vector<double> v_thr_host;
     uint64_t v_stats_host[4] = {0, 0, 0, 0};
 
     // ---- kriging state ----

@@ -95,6 +95,7 @@ int stif_ctx_destroy(stif_ctx *c)
     c->v_partial.release();
     c->v_stats.release();
     c->v_stage.release();
+    c->v_thr.release();
     c->k_obs.release();
     c->k_stats.release();
     for (auto &b : c->k_scratch) b.release();

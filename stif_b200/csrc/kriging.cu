@@ -554,31 +554,40 @@ __device__ T numpy_row_sum(const T *a, int n)
     return (T)0 + res;
 }
 
-__global__ void solve_kernel(SolveParams P, int warps_per_block, int warp_doubles)
+// One CTA of WPT warps per target.  The augmented system [A | b] ((m+1) x (m+2)) lives in
+// shared memory, row-major.  Lanes own columns (c = j+1+lane+32q, q < NCH), warps own row
+// groups, so every thread updates its elements with LDS + DFMA + STS while the pivot row's
+// entries and the row multipliers sit in registers.  The pivot of step j+1 is found while
+// column j+1 is being updated in step j (no separate search pass).
+template <int NCH, int WPT>
+__global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_doubles)
 {
     extern __shared__ __align__(16) double smem_d[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * warps_per_block + warp;
-    if (slot >= P.n) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NT = WPT * 32;
+    const int slot = blockIdx.x;
     const unsigned tl = P.order[slot];
     const int64_t tg = P.c0 + tl;
     const int k = P.k, ld = P.ld;
-    double *A = smem_d + (size_t)warp * warp_doubles;  // (k+1) x ld, row-major; column n = rhs
+    double *A = smem_d;                                // (k+1) x ld; column n = rhs
     double *xs = A + (size_t)(k + 1) * ld;             // [k+1]
     double *ys = xs + (k + 1);
     double *ts = ys + (k + 1);
     double *sol = ts + (k + 1);                        // [k+1]
     double *g0 = sol + (k + 1);                        // [k+1]
-    unsigned *ids = reinterpret_cast<unsigned *>(g0 + (k + 1));  // [k+1]
+    double *pv = g0 + (k + 1);                         // [8] per-warp pivot candidates
+    int *pr = reinterpret_cast<int *>(pv + 8);         // [8]
+    unsigned *ids = reinterpret_cast<unsigned *>(pr + 8);  // [k+1]
+    (void)cta_doubles;
 
     const int m = P.sel_n[tl];
     if (m <= 0) {
-        if (lane == 0) {
+        if (tid == 0) {
             P.mean[tg] = 0.0;
             P.std[tg] = 0.0;
             if (P.nused_out) P.nused_out[tg] = m < 0 ? -1 : 0;
         }
-        for (int e = lane; e < k; e += 32) {
+        for (int e = tid; e < k; e += NT) {
             if (P.w_out) P.w_out[(size_t)tg * k + e] = 0.f;
             if (P.g_out) P.g_out[(size_t)tg * k + e] = 0.f;
             if (P.idx_out) P.idx_out[(size_t)tg * k + e] = 0u;
@@ -586,7 +595,7 @@ __global__ void solve_kernel(SolveParams P, int warps_per_block, int warp_double
         return;
     }
     const int n = m + 1;
-    for (int e = lane; e < m; e += 32) {
+    for (int e = tid; e < m; e += NT) {
         const unsigned id = P.sel_idx[(size_t)tl * k + e];
         ids[e] = id;
         xs[e] = P.ox[id];
@@ -598,18 +607,18 @@ __global__ void solve_kernel(SolveParams P, int warps_per_block, int warp_double
         A[e * ld + m] = 1.0;      // Lagrange column            predictor.py:578
         A[m * ld + e] = 1.0;      // Lagrange row
     }
-    if (lane == 0) {
+    if (tid == 0) {
         A[m * ld + m] = 0.0;      // predictor.py:580
         A[m * ld + n] = 1.0;
     }
-    __syncwarp();
+    __syncthreads();
     // gamma matrix, predictor.py:573-575 (diagonal = gamma(0,0), no special case)
-    const double gdiag = gamma_st(P.M, 0.0, 0.0);
-    for (int e = lane; e < m; e += 32) A[e * ld + e] = gdiag;
     {
+        const double gdiag = gamma_st(P.M, 0.0, 0.0);
+        for (int e = tid; e < m; e += NT) A[e * ld + e] = gdiag;
         const int npairs = m * (m - 1) / 2;
-        int a = 0, off = lane;  // pair (a, a+1+off)
-        for (int e = lane; e < npairs; e += 32) {
+        int a = 0, off = tid;  // pair (a, a+1+off)
+        for (int e = tid; e < npairs; e += NT) {
             while (off >= m - 1 - a) {
                 off -= (m - 1 - a);
                 ++a;
@@ -621,60 +630,126 @@ __global__ void solve_kernel(SolveParams P, int warps_per_block, int warp_double
             const double g = gamma_st(P.M, h, lt);
             A[a * ld + b] = g;
             A[b * ld + a] = g;
-            off += 32;
+            off += NT;
         }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // LU with partial pivoting on the augmented matrix (n x (n+1))
+    // ---- LU with partial pivoting (row swaps), right-hand side carried as column n ----
+    // first pivot: every warp scans column 0 redundantly (no exchange needed)
+    double best = -1.0;
+    int bi = 0;
+    for (int r = lane; r < n; r += 32) {
+        const double v = fabs(A[r * ld]);
+        if (v > best) {
+            best = v;
+            bi = r;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(FULL, best, off);
+        const int oi = __shfl_xor_sync(FULL, bi, off);
+        if (ob > best || (ob == best && oi < bi)) {
+            best = ob;
+            bi = oi;
+        }
+    }
     bool singular = false;
     for (int j = 0; j < n; ++j) {
-        double best = -1.0;
-        int bi = j;
-        for (int r = j + lane; r < n; r += 32) {
-            const double v = fabs(A[r * ld + j]);
-            if (v > best) {
-                best = v;
-                bi = r;
+        // (best, bi) = pivot of column j, known to every thread
+        const bool skip = !(best > 0.0);   // exactly singular column (or NaN): x_j := 0
+        if (!skip && bi != j) {
+            for (int c = j + tid; c <= n; c += NT) {
+                const double tmp = A[j * ld + c];
+                A[j * ld + c] = A[bi * ld + c];
+                A[bi * ld + c] = tmp;
             }
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ob = __shfl_xor_sync(FULL, best, off);
-            const int oi = __shfl_xor_sync(FULL, bi, off);
+        __syncthreads();
+        double nbest = -1.0;
+        int nbi = j + 1;
+        double pinv = 0.0;
+        if (!skip) {
+            pinv = 1.0 / A[j * ld + j];
+            double u[NCH];
+            bool ok[NCH];
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+                const int c = j + 1 + lane + 32 * q;
+                ok[q] = c <= n;
+                u[q] = ok[q] ? A[j * ld + c] : 0.0;
+            }
+            double *colp = A + j + 1 + lane;   // this lane's first column
+            for (int r = j + 1 + 4 * warp; r < n; r += 4 * WPT) {
+                double *row0 = colp + r * ld;
+                const bool r1 = r + 1 < n, r2 = r + 2 < n, r3 = r + 3 < n;
+                const double l0 = A[r * ld + j] * pinv;
+                const double l1 = r1 ? A[(r + 1) * ld + j] * pinv : 0.0;
+                const double l2 = r2 ? A[(r + 2) * ld + j] * pinv : 0.0;
+                const double l3 = r3 ? A[(r + 3) * ld + j] * pinv : 0.0;
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    if (ok[q]) {
+                        const double v0 = __fma_rn(-l0, u[q], row0[32 * q]);
+                        row0[32 * q] = v0;
+                        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                        if (r1) {
+                            v1 = __fma_rn(-l1, u[q], row0[ld + 32 * q]);
+                            row0[ld + 32 * q] = v1;
+                        }
+                        if (r2) {
+                            v2 = __fma_rn(-l2, u[q], row0[2 * ld + 32 * q]);
+                            row0[2 * ld + 32 * q] = v2;
+                        }
+                        if (r3) {
+                            v3 = __fma_rn(-l3, u[q], row0[3 * ld + 32 * q]);
+                            row0[3 * ld + 32 * q] = v3;
+                        }
+                        if (q == 0 && lane == 0) {   // column j+1: candidates for the next pivot
+                            const double a0 = fabs(v0), a1 = fabs(v1), a2 = fabs(v2), a3 = fabs(v3);
+                            if (a0 > nbest) { nbest = a0; nbi = r; }
+                            if (r1 && a1 > nbest) { nbest = a1; nbi = r + 1; }
+                            if (r2 && a2 > nbest) { nbest = a2; nbi = r + 2; }
+                            if (r3 && a3 > nbest) { nbest = a3; nbi = r + 3; }
+                        }
+                    }
+                }
+            }
+        } else {
+            singular = true;
+            // column j untouched: candidates for column j+1 are its current entries
+            if (lane == 0) {
+                for (int r = j + 1 + warp; r < n; r += WPT) {
+                    const double a0 = fabs(A[r * ld + j + 1]);
+                    if (a0 > nbest) { nbest = a0; nbi = r; }
+                }
+            }
+        }
+        if (lane == 0) {
+            pv[warp] = nbest;
+            pr[warp] = nbi;
+        }
+        __syncthreads();
+        if (tid == 0) A[j * ld + j] = pinv;   // 1/pivot (0 for a skipped column)
+        best = pv[0];
+        bi = pr[0];
+#pragma unroll
+        for (int w = 1; w < WPT; ++w) {
+            const double ob = pv[w];
+            const int oi = pr[w];
             if (ob > best || (ob == best && oi < bi)) {
                 best = ob;
                 bi = oi;
             }
         }
-        if (!(best > 0.0)) {  // exactly singular column (or NaN): leave it, x_j := 0 later
-            singular = true;
-            continue;
-        }
-        if (bi != j) {
-            for (int c = j + lane; c <= n; c += 32) {
-                const double tmp = A[j * ld + c];
-                A[j * ld + c] = A[bi * ld + c];
-                A[bi * ld + c] = tmp;
-            }
-            __syncwarp();
-        }
-        const double pinv = 1.0 / A[j * ld + j];
-        // trailing update, lanes over columns j+1..n (rhs included)
-        for (int r = j + 1; r < n; ++r) {
-            const double l = A[r * ld + j] * pinv;
-            for (int c = j + 1 + lane; c <= n; c += 32) A[r * ld + c] = A[r * ld + c] - l * A[j * ld + c];
-        }
-        __syncwarp();
     }
-    // back substitution
+    __syncthreads();
+    if (warp != 0) return;
+    // back substitution, column oriented: x_j = b_j / U_jj, then b_r -= U_rj x_j (r < j)
     for (int j = n - 1; j >= 0; --j) {
-        double acc = 0.0;
-        for (int c = j + 1 + lane; c < n; c += 32) acc += A[j * ld + c] * sol[c];
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-        if (lane == 0) {
-            const double piv = A[j * ld + j];
-            sol[j] = (piv != 0.0) ? (A[j * ld + n] - acc) / piv : 0.0;
-        }
+        const double xj = A[j * ld + n] * A[j * ld + j];
+        for (int r = lane; r < j; r += 32) A[r * ld + n] = __fma_rn(-A[r * ld + j], xj, A[r * ld + n]);
+        if (lane == 0) sol[j] = xj;
         __syncwarp();
     }
     if (lane == 0 && singular) P.singular[tl] = 1u;
@@ -999,14 +1074,8 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     const int k = max_pts;
     int ld = k + 2;
     if ((ld & 1) == 0) ld += 1;
-    const int warp_doubles = (k + 1) * ld + 5 * (k + 1) + (k + 2) / 2 + 1;
-    const size_t warp_bytes = sizeof(double) * (size_t)warp_doubles;
-    int wpb = (int)((size_t)(200 * 1024) / warp_bytes);
-    if (wpb > 8) wpb = 8;
-    if (wpb < 1) wpb = 1;
-    const size_t solve_smem = warp_bytes * wpb;
-    STIF_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)solve_smem));
+    const int cta_doubles = (k + 1) * ld + 5 * (k + 1) + 8 + 4 + (k + 2) / 2 + 1;
+    const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
     // chunk so that the selection scratch stays below ~16 GB
     const size_t per_target = (size_t)k * 12 + 32;
@@ -1085,7 +1154,26 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         QP.idx_out = idx_out;
         QP.nused_out = n_used_out;
         QP.singular = singular;
-        solve_kernel<<<(nc + wpb - 1) / wpb, wpb * 32, solve_smem, st>>>(QP, wpb, warp_doubles);
+        {
+            // (column chunks, warps per target) by system size
+            const dim3 grid(nc);
+            const int nch = (k + 2 + 31) / 32;
+#define STIF_SOLVE(NCH_, WPT_)                                                                     \
+    do {                                                                                           \
+        STIF_CUDA(cudaFuncSetAttribute(solve_kernel<NCH_, WPT_>,                                   \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem)); \
+        solve_kernel<NCH_, WPT_><<<grid, WPT_ * 32, solve_smem, st>>>(QP, cta_doubles);            \
+    } while (0)
+            if (k <= 16) STIF_SOLVE(1, 1);
+            else if (nch == 1) STIF_SOLVE(1, 2);
+            else if (k <= 32) STIF_SOLVE(2, 2);
+            else if (nch == 2) STIF_SOLVE(2, 4);
+            else if (k <= 64) STIF_SOLVE(3, 4);
+            else if (nch == 3) STIF_SOLVE(3, 8);
+            else if (nch == 4) STIF_SOLVE(4, 8);
+            else STIF_SOLVE(5, 8);
+#undef STIF_SOLVE
+        }
         STIF_CUDA(cudaGetLastError());
         stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,
                                                  c->k_stats.as<unsigned long long>());

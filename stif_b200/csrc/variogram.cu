@@ -25,6 +25,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <vector>
 
 namespace stif {
 namespace vario {
@@ -54,6 +55,9 @@ struct Params {
     double *partial_sum;           // [grid][n_bins]
     unsigned long long *partial_cnt;  // [grid][n_bins]
     unsigned long long *stats;     // [4]
+    const double *thr;    // [n_space_bins + 2] d2 thresholds: bin b <=> thr[b] <= d2 < thr[b+1]
+    int use_thr;          // 0: evaluate sqrt/mul/trunc per binned pair (degenerate widths)
+    float inv_ws_f;       // float copy of inv_ws for the first guess
 };
 
 __global__ void pack_keys_kernel(const double *t, int64_t n, double *keys, unsigned *idx)
@@ -150,6 +154,8 @@ struct Smem {
     unsigned short *q;     // [QCAP][VT]
     double *s_sum;         // [n_bins]
     unsigned *s_cnt;       // [n_bins]
+    double *s_thr;         // [n_space_bins + 2]
+    unsigned *stg;         // [VT/32][64] per-warp staging of compacted queue entries
 };
 
 __device__ __forceinline__ void st_shared_u16(unsigned addr, unsigned short v)
@@ -157,19 +163,46 @@ __device__ __forceinline__ void st_shared_u16(unsigned addr, unsigned short v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
-__device__ __forceinline__ void drain(const Smem &S, const Params &P, int tid, int cnt)
+// Histogram update of one binned pair: shared-memory atomics (the FP64 add is a CAS loop on
+// sm_100a -- ATOMS.CAST.SPIN.64 -- the count a native ATOMS.POPC.INC).  A warp-aggregated
+// variant (match_any + shuffle reduction per distinct bin) was measured 2x SLOWER on C2
+// (profiles/r01_notes.md): a warp's 32 staged pairs spread over ~25 distinct bins, so there
+// is little to aggregate and the extra shuffles dominate.
+__device__ __forceinline__ void accumulate(const Smem &S, int bin /* < 0: nothing */, double val)
 {
-    for (int s = 0; s < cnt; ++s) {
-        const unsigned e = S.q[s * VT + tid];
-        const int j = e & 0xff, r = e >> 8;
-        const double4 pi = S.s_i[r * VT + tid];
+    if (bin >= 0) {
+        atomicAdd(&S.s_sum[bin], val);
+        atomicAdd(&S.s_cnt[bin], 1u);
+    }
+}
+
+// Bin one in-window pair per lane.  e = (owner lane << 16) | (r << 8) | j.
+__device__ __forceinline__ void bin_entry(const Smem &S, const Params &P, int warp_base, int lane,
+                                          unsigned e, bool have)
+{
+    int bin = -1;
+    double val = 0.0;
+    if (have) {
+        const int j = e & 0xff, r = (e >> 8) & 0xff, owner = e >> 16;
+        const double4 pi = S.s_i[r * VT + warp_base + owner];
         const double4 pj = S.s_j[j];
         const double dx = __dsub_rn(pi.x, pj.x);
         const double dy = __dsub_rn(pi.y, pj.y);
         const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
-        const double lag_s = __dsqrt_rn(d2);
         const double lag_t = fabs(__dsub_rn(pi.z, pj.z));
-        const long long bs = __double2ll_rz(__dmul_rn(lag_s, P.inv_ws));
+        long long bs;
+        if (P.use_thr) {
+            // trunc(sqrt_rn(d2)*inv_ws) is monotone in d2: look the bin up in the exact d2
+            // thresholds (host-bisected with the reference's formula) from a float guess
+            int b = __float2int_rz(fminf(__fsqrt_rn(__double2float_rn(d2)) * P.inv_ws_f,
+                                         (float)P.n_space_bins));
+            b = b < 0 ? 0 : b;
+            while (d2 < S.s_thr[b]) --b;
+            while (d2 >= S.s_thr[b + 1]) ++b;
+            bs = b;
+        } else {
+            bs = __double2ll_rz(__dmul_rn(__dsqrt_rn(d2), P.inv_ws));
+        }
         const long long bt = __double2ll_rz(__dmul_rn(lag_t, P.inv_wt));
         if (bs >= 0 && bs < P.n_space_bins && bt >= 0 && bt < P.n_time_bins) {
             double a, b;
@@ -180,10 +213,43 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, int tid, i
                 a = __dsub_rn(pi.w, P.mean);
                 b = __dsub_rn(pj.w, P.mean);
             }
-            const int bin = (int)bs * P.n_time_bins + (int)bt;
-            atomicAdd(&S.s_sum[bin], __dmul_rn(a, b));
-            atomicAdd(&S.s_cnt[bin], 1u);
+            bin = (int)bs * P.n_time_bins + (int)bt;
+            val = __dmul_rn(a, b);
         }
+    }
+    accumulate(S, bin, val);
+}
+
+// Drain the 32 per-thread queues of a warp.  Slot s of every lane that has one is compacted
+// (ballot) into the warp's staging buffer; whenever 32 entries are staged they are binned
+// with all lanes active.  `nst` (warp-uniform) carries the < 32 leftovers to the next call;
+// `flush` bins them too (end of an item, before the tiles are replaced).
+__device__ __forceinline__ void drain(const Smem &S, const Params &P, int tid, int cnt, int &nst,
+                                      bool flush)
+{
+    const int lane = tid & 31, warp_base = tid & ~31;
+    unsigned *stg = S.stg + (tid >> 5) * 64;
+    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+    for (int s = 0; s < maxcnt; ++s) {
+        const bool has = s < cnt;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (has) stg[nst + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)lane << 16) | S.q[s * VT + tid];
+        nst += __popc(bal);
+        __syncwarp();
+        if (nst >= 32) {
+            bin_entry(S, P, warp_base, lane, stg[lane], true);
+            const int rem = nst - 32;
+            const unsigned mv = (lane < rem) ? stg[32 + lane] : 0u;
+            __syncwarp();
+            if (lane < rem) stg[lane] = mv;
+            nst = rem;
+            __syncwarp();
+        }
+    }
+    if (flush && nst > 0) {
+        bin_entry(S, P, warp_base, lane, stg[lane], lane < nst);
+        nst = 0;
+        __syncwarp();
     }
 }
 
@@ -202,6 +268,7 @@ __device__ __forceinline__ unsigned scan_item(const Smem &S, const Params &P, in
     }
     const double tcut = P.tcut, tmax = P.tmax;
     unsigned npass = 0;
+    int nst = 0;
     // 32-bit shared-window address of this thread's next free queue slot
     const unsigned qbase = (unsigned)__cvta_generic_to_shared(S.q + tid);
     unsigned qa = qbase;
@@ -209,7 +276,7 @@ __device__ __forceinline__ unsigned scan_item(const Smem &S, const Params &P, in
     for (int jb = 0; jb < TJ; jb += VG) {
         if (__any_sync(0xffffffffu, qa > qhigh)) {
             const int cnt = (int)((qa - qbase) / (2 * VT));
-            drain(S, P, tid, cnt);
+            drain(S, P, tid, cnt, nst, false);
             npass += cnt;
             qa = qbase;
         }
@@ -233,7 +300,7 @@ __device__ __forceinline__ unsigned scan_item(const Smem &S, const Params &P, in
         }
     }
     const int cnt = (int)((qa - qbase) / (2 * VT));
-    drain(S, P, tid, cnt);
+    drain(S, P, tid, cnt, nst, true);
     npass += cnt;
     return npass;
 }
@@ -246,13 +313,16 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
     S.s_j = S.s_i + TI;
     S.q = reinterpret_cast<unsigned short *>(S.s_j + TJ);
     S.s_sum = reinterpret_cast<double *>(S.q + QCAP * VT);
-    S.s_cnt = reinterpret_cast<unsigned *>(S.s_sum + P.n_bins);
+    S.s_thr = S.s_sum + P.n_bins;
+    S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
+    S.stg = S.s_cnt + P.n_bins;
 
     const int tid = threadIdx.x;
     for (int b = tid; b < P.n_bins; b += VT) {
         S.s_sum[b] = 0.0;
         S.s_cnt[b] = 0u;
     }
+    for (int b = tid; b < P.n_space_bins + 2; b += VT) S.s_thr[b] = P.thr[b];
     unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
     double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
     for (int b = tid; b < P.n_bins; b += VT) my_cnt[b] = 0ull;
@@ -470,6 +540,29 @@ __global__ void __launch_bounds__(VT) sampled_kernel(Params P, SampledParams Q)
 
 // Largest double T with sqrt_rn(T) <= smax (host; IEEE sqrt is correctly rounded and
 // monotone, so sqrt_rn(d2) > smax  <=>  d2 > T).
+// thr[k] (k = 1..ns) = smallest d2 >= 0 with trunc(sqrt_rn(d2) * inv_ws) >= k; thr[0] = -1,
+// thr[ns+1] = +inf.  Bisection over the (monotone) bit patterns of non-negative doubles with
+// the reference's exact formula, so the device needs no sqrt to find a bin.
+static void bin_thresholds(double inv_ws, int ns, double *thr)
+{
+    auto bin_of = [&](double d2) -> double {
+        const double f = sqrt(d2) * inv_ws;
+        return (f >= 9.0e18) ? 9.0e18 : (double)(long long)f;
+    };
+    thr[0] = -1.0;
+    thr[ns + 1] = INFINITY;
+    for (int k = 1; k <= ns; ++k) {
+        unsigned long long lo = 0, hi = 0x7ff0000000000000ull;  // +0 .. +inf
+        while (lo < hi) {
+            const unsigned long long mid = lo + ((hi - lo) >> 1);
+            double d;
+            memcpy(&d, &mid, 8);
+            if (bin_of(d) >= (double)k) hi = mid; else lo = mid + 1;
+        }
+        memcpy(&thr[k], &lo, 8);
+    }
+}
+
 static double sqrt_cut_threshold(double smax)
 {
     if (isnan(smax)) return -1.0;                 // "lag > NaN" is never true in IEEE, but
@@ -604,9 +697,22 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     P.inv_wt = 1.0 / wt;
     P.mean = mean;
     P.stats = c->v_stats.as<unsigned long long>();
+    P.inv_ws_f = (float)P.inv_ws;
+    P.use_thr = (P.inv_ws > 0.0 && isfinite(P.inv_ws) && isfinite((double)P.inv_ws_f)) ? 1 : 0;
+    {
+        // context-owned host copy: stays valid until the next call, so no synchronisation
+        std::vector<double> &thr = c->v_thr_host;
+        thr.assign((size_t)ns + 2, 0.0);
+        if (P.use_thr) bin_thresholds(P.inv_ws, ns, thr.data());
+        STIF_TRY(c->v_thr.reserve(sizeof(double) * thr.size()));
+        STIF_CUDA(cudaMemcpyAsync(c->v_thr.p, thr.data(), sizeof(double) * thr.size(),
+                                  cudaMemcpyHostToDevice, st));
+        P.thr = c->v_thr.as<double>();
+    }
 
     const size_t smem = sizeof(double4) * (TI + TJ) + sizeof(unsigned short) * QCAP * VT +
-                        (sizeof(double) + sizeof(unsigned)) * (size_t)n_bins;
+                        (sizeof(double) + sizeof(unsigned)) * (size_t)n_bins +
+                        sizeof(double) * ((size_t)ns + 2) + sizeof(unsigned) * 64 * (VT / 32);
     STIF_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     int occ = 0;

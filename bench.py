@@ -303,7 +303,7 @@ def run_b200(args):
         if "kriging" in out:
             out["kriging"]["cpu_baseline"] = cpu_kriging_baseline()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -465,10 +465,30 @@ def run_reference(args):
                           "unit": "predictions/s", "cpu_baseline": kb,
                           "e2e": {"value": kb["value"], "unit": "predictions/s", "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to
+    stdout) get stderr instead; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

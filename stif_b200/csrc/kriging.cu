@@ -636,41 +636,48 @@ __global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_
     __syncthreads();
 
     // ---- LU with partial pivoting (row swaps), right-hand side carried as column n ----
-    // first pivot: every warp scans column 0 redundantly (no exchange needed)
-    double best = -1.0;
-    int bi = 0;
-    for (int r = lane; r < n; r += 32) {
-        const double v = fabs(A[r * ld]);
-        if (v > best) {
-            best = v;
-            bi = r;
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(FULL, best, off);
-        const int oi = __shfl_xor_sync(FULL, bi, off);
-        if (ob > best || (ob == best && oi < bi)) {
-            best = ob;
-            bi = oi;
-        }
-    }
+    // Per step: warp 0 selects the pivot of column j (lanes over rows, packed-key argmax),
+    // swaps the two rows and leaves 1/pivot in A[j][j] (0 = column skipped: exactly singular
+    // or NaN, x_j := 0); after a barrier every warp updates its row groups.
     bool singular = false;
     for (int j = 0; j < n; ++j) {
-        // (best, bi) = pivot of column j, known to every thread
-        const bool skip = !(best > 0.0);   // exactly singular column (or NaN): x_j := 0
-        if (!skip && bi != j) {
-            for (int c = j + tid; c <= n; c += NT) {
-                const double tmp = A[j * ld + c];
-                A[j * ld + c] = A[bi * ld + c];
-                A[bi * ld + c] = tmp;
+        if (warp == 0) {
+            // key = |value| bits with the low byte replaced by (255 - row): one u64 max gives
+            // the largest magnitude and, among (near-)equal ones, the smallest row
+            unsigned long long key = 0ull;
+            for (int r = j + lane; r < n; r += 32) {
+                const unsigned long long kb =
+                    ((unsigned long long)__double_as_longlong(fabs(A[r * ld + j])) & ~0xffull) |
+                    (unsigned long long)(255 - r);
+                key = kb > key ? kb : key;
             }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(FULL, key, off);
+                key = o > key ? o : key;
+            }
+            const int bi = 255 - (int)(key & 0xffull);
+            const double bv = __longlong_as_double((long long)(key & ~0xffull));
+            double pinv = 0.0;
+            if (bv > 0.0 && bv < INFINITY) {   // NaN and 0 fall through: skip the column
+                if (bi != j) {
+                    for (int c = j + lane; c <= n; c += 32) {
+                        const double tmp = A[j * ld + c];
+                        A[j * ld + c] = A[bi * ld + c];
+                        A[bi * ld + c] = tmp;
+                    }
+                    __syncwarp();
+                }
+                pinv = 1.0 / A[j * ld + j];
+            }
+            __syncwarp();
+            if (lane == 0) A[j * ld + j] = pinv;
         }
         __syncthreads();
-        double nbest = -1.0;
-        int nbi = j + 1;
-        double pinv = 0.0;
-        if (!skip) {
-            pinv = 1.0 / A[j * ld + j];
+        const double pinv = A[j * ld + j];
+        if (pinv != 0.0) {
+            const int nrows = n - (j + 1);     // rows j+1 .. n-1 are still active
+            const int nfull = nrows >> 2;      // groups of 4 rows; group g belongs to warp g % WPT
             double u[NCH];
             bool ok[NCH];
 #pragma unroll
@@ -679,69 +686,36 @@ __global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_
                 ok[q] = c <= n;
                 u[q] = ok[q] ? A[j * ld + c] : 0.0;
             }
-            double *colp = A + j + 1 + lane;   // this lane's first column
-            for (int r = j + 1 + 4 * warp; r < n; r += 4 * WPT) {
-                double *row0 = colp + r * ld;
-                const bool r1 = r + 1 < n, r2 = r + 2 < n, r3 = r + 3 < n;
-                const double l0 = A[r * ld + j] * pinv;
-                const double l1 = r1 ? A[(r + 1) * ld + j] * pinv : 0.0;
-                const double l2 = r2 ? A[(r + 2) * ld + j] * pinv : 0.0;
-                const double l3 = r3 ? A[(r + 3) * ld + j] * pinv : 0.0;
+            const int c0 = j + 1 + lane;       // this lane's first column
+            double *rowp = A + (j + 1 + 4 * warp) * ld;
+            const int gstride = 4 * WPT * ld;
+            for (int g = warp; g < nfull; g += WPT, rowp += gstride) {
+                const double l0 = rowp[j] * pinv, l1 = rowp[ld + j] * pinv;
+                const double l2 = rowp[2 * ld + j] * pinv, l3 = rowp[3 * ld + j] * pinv;
 #pragma unroll
                 for (int q = 0; q < NCH; ++q) {
                     if (ok[q]) {
-                        const double v0 = __fma_rn(-l0, u[q], row0[32 * q]);
-                        row0[32 * q] = v0;
-                        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
-                        if (r1) {
-                            v1 = __fma_rn(-l1, u[q], row0[ld + 32 * q]);
-                            row0[ld + 32 * q] = v1;
-                        }
-                        if (r2) {
-                            v2 = __fma_rn(-l2, u[q], row0[2 * ld + 32 * q]);
-                            row0[2 * ld + 32 * q] = v2;
-                        }
-                        if (r3) {
-                            v3 = __fma_rn(-l3, u[q], row0[3 * ld + 32 * q]);
-                            row0[3 * ld + 32 * q] = v3;
-                        }
-                        if (q == 0 && lane == 0) {   // column j+1: candidates for the next pivot
-                            const double a0 = fabs(v0), a1 = fabs(v1), a2 = fabs(v2), a3 = fabs(v3);
-                            if (a0 > nbest) { nbest = a0; nbi = r; }
-                            if (r1 && a1 > nbest) { nbest = a1; nbi = r + 1; }
-                            if (r2 && a2 > nbest) { nbest = a2; nbi = r + 2; }
-                            if (r3 && a3 > nbest) { nbest = a3; nbi = r + 3; }
-                        }
+                        double *e = rowp + c0 + 32 * q;
+                        e[0] = __fma_rn(-l0, u[q], e[0]);
+                        e[ld] = __fma_rn(-l1, u[q], e[ld]);
+                        e[2 * ld] = __fma_rn(-l2, u[q], e[2 * ld]);
+                        e[3 * ld] = __fma_rn(-l3, u[q], e[3 * ld]);
                     }
+                }
+            }
+            if (warp == nfull % WPT) {         // the 0..3 leftover rows
+                for (int r = j + 1 + 4 * nfull; r < n; ++r) {
+                    double *row = A + r * ld;
+                    const double l0 = row[j] * pinv;
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q)
+                        if (ok[q]) row[c0 + 32 * q] = __fma_rn(-l0, u[q], row[c0 + 32 * q]);
                 }
             }
         } else {
             singular = true;
-            // column j untouched: candidates for column j+1 are its current entries
-            if (lane == 0) {
-                for (int r = j + 1 + warp; r < n; r += WPT) {
-                    const double a0 = fabs(A[r * ld + j + 1]);
-                    if (a0 > nbest) { nbest = a0; nbi = r; }
-                }
-            }
-        }
-        if (lane == 0) {
-            pv[warp] = nbest;
-            pr[warp] = nbi;
         }
         __syncthreads();
-        if (tid == 0) A[j * ld + j] = pinv;   // 1/pivot (0 for a skipped column)
-        best = pv[0];
-        bi = pr[0];
-#pragma unroll
-        for (int w = 1; w < WPT; ++w) {
-            const double ob = pv[w];
-            const int oi = pr[w];
-            if (ob > best || (ob == best && oi < bi)) {
-                best = ob;
-                bi = oi;
-            }
-        }
     }
     __syncthreads();
     if (warp != 0) return;

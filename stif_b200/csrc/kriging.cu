@@ -554,32 +554,37 @@ __device__ T numpy_row_sum(const T *a, int n)
     return (T)0 + res;
 }
 
+// ---- solve: shared pieces ------------------------------------------------------------
 // One CTA of WPT warps per target.  The augmented system [A | b] ((m+1) x (m+2)) lives in
-// shared memory, row-major.  Lanes own columns (c = j+1+lane+32q, q < NCH), warps own row
-// groups, so every thread updates its elements with LDS + DFMA + STS while the pivot row's
-// entries and the row multipliers sit in registers.  The pivot of step j+1 is found while
-// column j+1 is being updated in step j (no separate search pass).
-template <int NCH, int WPT>
-__global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_doubles)
-{
-    extern __shared__ __align__(16) double smem_d[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NT = WPT * 32;
-    const int slot = blockIdx.x;
-    const unsigned tl = P.order[slot];
-    const int64_t tg = P.c0 + tl;
-    const int k = P.k, ld = P.ld;
-    double *A = smem_d;                                // (k+1) x ld; column n = rhs
-    double *xs = A + (size_t)(k + 1) * ld;             // [k+1]
-    double *ys = xs + (k + 1);
-    double *ts = ys + (k + 1);
-    double *sol = ts + (k + 1);                        // [k+1]
-    double *g0 = sol + (k + 1);                        // [k+1]
-    double *pv = g0 + (k + 1);                         // [8] per-warp pivot candidates
-    int *pr = reinterpret_cast<int *>(pv + 8);         // [8]
-    unsigned *ids = reinterpret_cast<unsigned *>(pr + 8);  // [k+1]
-    (void)cta_doubles;
+// shared memory, row-major with leading dimension ld (odd), zero-padded to NR x NC
+// (multiples of 8) so the tensor-core tiles need no bounds checks.
+struct SolveSmem {
+    double *A;                       // NR x ld; column n = rhs
+    double *xs, *ys, *ts, *sol, *g0; // [k+1] each
+    unsigned *ids;                   // [k+1]
+};
 
+__device__ __forceinline__ SolveSmem carve(double *base, int k, int ld, int nr)
+{
+    SolveSmem S;
+    S.A = base;
+    S.xs = base + (size_t)nr * ld;
+    S.ys = S.xs + (k + 1);
+    S.ts = S.ys + (k + 1);
+    S.sol = S.ts + (k + 1);
+    S.g0 = S.sol + (k + 1);
+    S.ids = reinterpret_cast<unsigned *>(S.g0 + (k + 1));
+    return S;
+}
+
+// Loads the selection, assembles [A | b] (predictor.py:573-585) and zero-fills the padding.
+// Returns m (neighbours used); m <= 0 means the outputs were written (zeros) and the CTA is done.
+template <int NT>
+__device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl, int64_t tg, int tid,
+                           int nr, int nc)
+{
+    const int k = P.k, ld = P.ld;
+    double *A = S.A;
     const int m = P.sel_n[tl];
     if (m <= 0) {
         if (tid == 0) {
@@ -592,17 +597,21 @@ __global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_
             if (P.g_out) P.g_out[(size_t)tg * k + e] = 0.f;
             if (P.idx_out) P.idx_out[(size_t)tg * k + e] = 0u;
         }
-        return;
+        return m;
     }
     const int n = m + 1;
+    // padding: rows n..nr-1 (all columns) and columns n+1..nc-1 of the real rows
+    for (int e = n * ld + tid; e < nr * ld; e += NT) A[e] = 0.0;
+    for (int r = tid; r < n; r += NT)
+        for (int c = n + 1; c < nc; ++c) A[r * ld + c] = 0.0;
     for (int e = tid; e < m; e += NT) {
         const unsigned id = P.sel_idx[(size_t)tl * k + e];
-        ids[e] = id;
-        xs[e] = P.ox[id];
-        ys[e] = P.oy[id];
-        ts[e] = P.ot[id];
+        S.ids[e] = id;
+        S.xs[e] = P.ox[id];
+        S.ys[e] = P.oy[id];
+        S.ts[e] = P.ot[id];
         const double g = P.sel_gamma[(size_t)tl * k + e];
-        g0[e] = g;
+        S.g0[e] = g;
         A[e * ld + n] = g;        // rhs = [gamma_vector; 1]   predictor.py:582-585
         A[e * ld + m] = 1.0;      // Lagrange column            predictor.py:578
         A[m * ld + e] = 1.0;      // Lagrange row
@@ -613,113 +622,53 @@ __global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_
     }
     __syncthreads();
     // gamma matrix, predictor.py:573-575 (diagonal = gamma(0,0), no special case)
-    {
-        const double gdiag = gamma_st(P.M, 0.0, 0.0);
-        for (int e = tid; e < m; e += NT) A[e * ld + e] = gdiag;
-        const int npairs = m * (m - 1) / 2;
-        int a = 0, off = tid;  // pair (a, a+1+off)
-        for (int e = tid; e < npairs; e += NT) {
-            while (off >= m - 1 - a) {
-                off -= (m - 1 - a);
-                ++a;
-            }
-            const int b = a + 1 + off;
-            const double dx = xs[a] - xs[b], dy = ys[a] - ys[b];
-            const double h = sqrt(dx * dx + dy * dy);          // utils.py:40-44
-            const double lt = fabs(ts[a] - ts[b]);             // utils.py:19-22
-            const double g = gamma_st(P.M, h, lt);
-            A[a * ld + b] = g;
-            A[b * ld + a] = g;
-            off += NT;
+    const double gdiag = gamma_st(P.M, 0.0, 0.0);
+    for (int e = tid; e < m; e += NT) A[e * ld + e] = gdiag;
+    const int npairs = m * (m - 1) / 2;
+    int a = 0, off = tid;  // pair (a, a+1+off)
+    for (int e = tid; e < npairs; e += NT) {
+        while (off >= m - 1 - a) {
+            off -= (m - 1 - a);
+            ++a;
         }
+        const int b = a + 1 + off;
+        const double dx = S.xs[a] - S.xs[b], dy = S.ys[a] - S.ys[b];
+        const double h = sqrt(dx * dx + dy * dy);          // utils.py:40-44
+        const double lt = fabs(S.ts[a] - S.ts[b]);         // utils.py:19-22
+        const double g = gamma_st(P.M, h, lt);
+        A[a * ld + b] = g;
+        A[b * ld + a] = g;
+        off += NT;
     }
     __syncthreads();
+    return m;
+}
 
-    // ---- LU with partial pivoting (row swaps), right-hand side carried as column n ----
-    // Per step: warp 0 selects the pivot of column j (lanes over rows, packed-key argmax),
-    // swaps the two rows and leaves 1/pivot in A[j][j] (0 = column skipped: exactly singular
-    // or NaN, x_j := 0); after a barrier every warp updates its row groups.
-    bool singular = false;
-    for (int j = 0; j < n; ++j) {
-        if (warp == 0) {
-            // key = |value| bits with the low byte replaced by (255 - row): one u64 max gives
-            // the largest magnitude and, among (near-)equal ones, the smallest row
-            unsigned long long key = 0ull;
-            for (int r = j + lane; r < n; r += 32) {
-                const unsigned long long kb =
-                    ((unsigned long long)__double_as_longlong(fabs(A[r * ld + j])) & ~0xffull) |
-                    (unsigned long long)(255 - r);
-                key = kb > key ? kb : key;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(FULL, key, off);
-                key = o > key ? o : key;
-            }
-            const int bi = 255 - (int)(key & 0xffull);
-            const double bv = __longlong_as_double((long long)(key & ~0xffull));
-            double pinv = 0.0;
-            if (bv > 0.0 && bv < INFINITY) {   // NaN and 0 fall through: skip the column
-                if (bi != j) {
-                    for (int c = j + lane; c <= n; c += 32) {
-                        const double tmp = A[j * ld + c];
-                        A[j * ld + c] = A[bi * ld + c];
-                        A[bi * ld + c] = tmp;
-                    }
-                    __syncwarp();
-                }
-                pinv = 1.0 / A[j * ld + j];
-            }
-            __syncwarp();
-            if (lane == 0) A[j * ld + j] = pinv;
-        }
-        __syncthreads();
-        const double pinv = A[j * ld + j];
-        if (pinv != 0.0) {
-            const int nrows = n - (j + 1);     // rows j+1 .. n-1 are still active
-            const int nfull = nrows >> 2;      // groups of 4 rows; group g belongs to warp g % WPT
-            double u[NCH];
-            bool ok[NCH];
-#pragma unroll
-            for (int q = 0; q < NCH; ++q) {
-                const int c = j + 1 + lane + 32 * q;
-                ok[q] = c <= n;
-                u[q] = ok[q] ? A[j * ld + c] : 0.0;
-            }
-            const int c0 = j + 1 + lane;       // this lane's first column
-            double *rowp = A + (j + 1 + 4 * warp) * ld;
-            const int gstride = 4 * WPT * ld;
-            for (int g = warp; g < nfull; g += WPT, rowp += gstride) {
-                const double l0 = rowp[j] * pinv, l1 = rowp[ld + j] * pinv;
-                const double l2 = rowp[2 * ld + j] * pinv, l3 = rowp[3 * ld + j] * pinv;
-#pragma unroll
-                for (int q = 0; q < NCH; ++q) {
-                    if (ok[q]) {
-                        double *e = rowp + c0 + 32 * q;
-                        e[0] = __fma_rn(-l0, u[q], e[0]);
-                        e[ld] = __fma_rn(-l1, u[q], e[ld]);
-                        e[2 * ld] = __fma_rn(-l2, u[q], e[2 * ld]);
-                        e[3 * ld] = __fma_rn(-l3, u[q], e[3 * ld]);
-                    }
-                }
-            }
-            if (warp == nfull % WPT) {         // the 0..3 leftover rows
-                for (int r = j + 1 + 4 * nfull; r < n; ++r) {
-                    double *row = A + r * ld;
-                    const double l0 = row[j] * pinv;
-#pragma unroll
-                    for (int q = 0; q < NCH; ++q)
-                        if (ok[q]) row[c0 + 32 * q] = __fma_rn(-l0, u[q], row[c0 + 32 * q]);
-                }
-            }
-        } else {
-            singular = true;
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    if (warp != 0) return;
-    // back substitution, column oriented: x_j = b_j / U_jj, then b_r -= U_rj x_j (r < j)
+// Packed pivot key: |value| bits with the low byte replaced by (255 - row); one unsigned max
+// yields the largest magnitude and, among (near-)equal ones, the smallest row.  The warp max
+// uses two 32-bit REDUX instead of a 5-round 64-bit shuffle tree.
+__device__ __forceinline__ unsigned long long pivot_key(double v, int r)
+{
+    return ((unsigned long long)__double_as_longlong(fabs(v)) & ~0xffull) | (unsigned long long)(255 - r);
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long key)
+{
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+    const unsigned ml = __reduce_max_sync(FULL, lo);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// Back substitution (warp 0; column oriented: x_j = b_j * (1/U_jj), then b_r -= U_rj x_j for
+// r < j) and the fused epilogue: predictor.py:646-658 (storage) and :900-905 (mean, std).
+__device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, unsigned tl, int64_t tg,
+                             int lane, bool singular)
+{
+    const int k = P.k, ld = P.ld, n = m + 1;
+    double *A = S.A, *sol = S.sol, *g0 = S.g0;
+    const unsigned *ids = S.ids;
     for (int j = n - 1; j >= 0; --j) {
         const double xj = A[j * ld + n] * A[j * ld + j];
         for (int r = lane; r < j; r += 32) A[r * ld + n] = __fma_rn(-A[r * ld + j], xj, A[r * ld + n]);
@@ -727,12 +676,10 @@ __global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_
         __syncwarp();
     }
     if (lane == 0 && singular) P.singular[tl] = 1u;
-
-    // ---- epilogue: predictor.py:646-658 (storage) and :900-905 (mean, std) ----
     if (P.flags & STIF_KRIG_F32_STORAGE) {
-        double *term64 = xs;                              // k doubles
-        float *w32 = reinterpret_cast<float *>(ys);       // k floats
-        float *term32 = reinterpret_cast<float *>(ts);    // k floats
+        double *term64 = S.xs;                            // k doubles
+        float *w32 = reinterpret_cast<float *>(S.ys);     // k floats
+        float *term32 = reinterpret_cast<float *>(S.ts);  // k floats
         const double resid0 = P.oresid[0];
         __syncwarp();
         for (int e = lane; e < k; e += 32) {
@@ -780,6 +727,122 @@ __global__ void __launch_bounds__(WPT * 32) solve_kernel(SolveParams P, int cta_
             if (P.nused_out) P.nused_out[tg] = m;
         }
     }
+}
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- solve: blocked LU, trailing update on the FP64 tensor cores -----------------------
+// Right-looking blocked LU with partial pivoting, block 8.  Per panel:
+//   1. warp 0 factorises the 8-column panel (lanes over rows; REDUX pivot search; row swaps
+//      over all columns from the panel start; NEGATED multipliers stored in place; 1/pivot on
+//      the diagonal, 0 = column skipped because it is exactly singular or NaN);
+//   2. U12 = L11^-1 A12: one thread per column to the right of the panel;
+//   3. A22 += (-L21) U12 as 8x8 tiles of two mma.sync.m8n8k4.f64 (DMMA) each, tiles dealt
+//      round-robin to the warps.  512 FMAs per tensor instruction instead of 32 per DFMA: the
+//      scalar shared-memory LU was issue-bound (ncu: 78 % issue-active at 27 % FP64 pipe).
+// The right-hand side is column n and is transformed with the matrix.
+template <int WPT>
+__global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int nr, int nc)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    constexpr int NT = WPT * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned tl = P.order[blockIdx.x];
+    const int64_t tg = P.c0 + tl;
+    const int ld = P.ld;
+    const SolveSmem S = carve(smem_d, P.k, ld, nr);
+    double *A = S.A;
+    const int m = solve_setup<NT>(P, S, tl, tg, tid, nr, nc);
+    if (m <= 0) return;
+    const int n = m + 1;
+    bool singular = false;
+
+    for (int jb = 0; jb < n; jb += 8) {
+        if (warp == 0) {
+            // ---- 1. panel factorisation, columns jb .. jb+7 (pivot columns only while < n) ----
+            for (int jj = 0; jj < 8 && jb + jj < n; ++jj) {
+                const int j = jb + jj;
+                unsigned long long key = 0ull;
+                for (int r = j + lane; r < n; r += 32) {
+                    const unsigned long long kb = pivot_key(A[r * ld + j], r);
+                    key = kb > key ? kb : key;
+                }
+                key = warp_max_u64(key);
+                const int bi = 255 - (int)(key & 0xffull);
+                const double bv = __longlong_as_double((long long)(key & ~0xffull));
+                double pinv = 0.0;
+                if (bv > 0.0 && bv < INFINITY) {
+                    if (bi != j) {
+                        for (int c = jb + lane; c < nc; c += 32) {
+                            const double tmp = A[j * ld + c];
+                            A[j * ld + c] = A[bi * ld + c];
+                            A[bi * ld + c] = tmp;
+                        }
+                        __syncwarp();
+                    }
+                    pinv = 1.0 / A[j * ld + j];
+                } else {
+                    singular = true;
+                }
+                // pivot row inside the panel, right of the diagonal
+                double u[7];
+#pragma unroll
+                for (int cc = 0; cc < 7; ++cc) u[cc] = (cc >= jj) ? A[j * ld + jb + cc + 1] : 0.0;
+                for (int r = j + 1 + lane; r < n; r += 32) {
+                    double *row = A + r * ld + jb;
+                    const double mneg = -(row[jj] * pinv);   // negated multiplier
+                    row[jj] = mneg;
+#pragma unroll
+                    for (int cc = 0; cc < 7; ++cc)
+                        if (cc >= jj) row[cc + 1] = __fma_rn(mneg, u[cc], row[cc + 1]);
+                }
+                __syncwarp();
+                if (lane == 0) A[j * ld + j] = pinv;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (jb + 8 > n) break;    // rhs column inside the panel: nothing left to transform
+        // ---- 2. U12: rows jb..jb+7 of the columns right of the panel ----
+        for (int c = jb + 8 + tid; c < nc; c += NT) {
+            double uu[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double acc = A[(jb + i) * ld + c];
+#pragma unroll
+                for (int q = 0; q < i; ++q) acc = __fma_rn(A[(jb + i) * ld + jb + q], uu[q], acc);
+                uu[i] = acc;
+            }
+#pragma unroll
+            for (int i = 1; i < 8; ++i) A[(jb + i) * ld + c] = uu[i];
+        }
+        __syncthreads();
+        // ---- 3. trailing update on the tensor cores ----
+        {
+            const int g = lane >> 2, t = lane & 3;
+            const int r_lo = jb + 8, ntr = (nr - r_lo) >> 3, ntc = (nc - r_lo) >> 3;
+            for (int tile = warp; tile < ntr * ntc; tile += WPT) {
+                const int ti = tile / ntc, tj = tile - ti * ntc;
+                const int r0 = r_lo + 8 * ti, c0 = r_lo + 8 * tj;
+                const double a0 = A[(r0 + g) * ld + jb + t], a1 = A[(r0 + g) * ld + jb + 4 + t];
+                const double b0 = A[(jb + t) * ld + c0 + g], b1 = A[(jb + 4 + t) * ld + c0 + g];
+                double *cp = A + (r0 + g) * ld + c0 + 2 * t;
+                double c0v = cp[0], c1v = cp[1];
+                dmma884(c0v, c1v, a0, b0);
+                dmma884(c0v, c1v, a1, b1);
+                cp[0] = c0v;
+                cp[1] = c1v;
+            }
+        }
+        __syncthreads();
+    }
+    if (warp != 0) return;
+    solve_finish(P, S, m, tl, tg, lane, singular);
 }
 
 // stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += sum(singular)
@@ -1046,9 +1109,10 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     STIF_CUDA(cudaEventRecord(c->ev[1], st));
 
     const int k = max_pts;
-    int ld = k + 2;
-    if ((ld & 1) == 0) ld += 1;
-    const int cta_doubles = (k + 1) * ld + 5 * (k + 1) + 8 + 4 + (k + 2) / 2 + 1;
+    const int nr_pad = (k + 1 + 7) / 8 * 8;      // rows of the padded system
+    const int nc_pad = (k + 2 + 7) / 8 * 8;      // columns incl. the right-hand side
+    const int ld = nc_pad + 1;                   // odd leading dimension
+    const int cta_doubles = nr_pad * ld + 5 * (k + 1) + (k + 2) / 2 + 1;
     const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
     // chunk so that the selection scratch stays below ~16 GB
@@ -1129,23 +1193,17 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         QP.nused_out = n_used_out;
         QP.singular = singular;
         {
-            // (column chunks, warps per target) by system size
             const dim3 grid(nc);
-            const int nch = (k + 2 + 31) / 32;
-#define STIF_SOLVE(NCH_, WPT_)                                                                     \
+#define STIF_SOLVE(WPT_)                                                                           \
     do {                                                                                           \
-        STIF_CUDA(cudaFuncSetAttribute(solve_kernel<NCH_, WPT_>,                                   \
+        STIF_CUDA(cudaFuncSetAttribute(solve_blk_kernel<WPT_>,                                     \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem)); \
-        solve_kernel<NCH_, WPT_><<<grid, WPT_ * 32, solve_smem, st>>>(QP, cta_doubles);            \
+        solve_blk_kernel<WPT_><<<grid, WPT_ * 32, solve_smem, st>>>(QP, nr_pad, nc_pad);           \
     } while (0)
-            if (k <= 16) STIF_SOLVE(1, 1);
-            else if (nch == 1) STIF_SOLVE(1, 2);
-            else if (k <= 32) STIF_SOLVE(2, 2);
-            else if (nch == 2) STIF_SOLVE(2, 4);
-            else if (k <= 64) STIF_SOLVE(3, 4);
-            else if (nch == 3) STIF_SOLVE(3, 8);
-            else if (nch == 4) STIF_SOLVE(4, 8);
-            else STIF_SOLVE(5, 8);
+            if (k <= 16) STIF_SOLVE(1);
+            else if (k <= 32) STIF_SOLVE(2);
+            else if (k <= 64) STIF_SOLVE(4);
+            else STIF_SOLVE(8);
 #undef STIF_SOLVE
         }
         STIF_CUDA(cudaGetLastError());

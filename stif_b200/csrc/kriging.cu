@@ -562,6 +562,7 @@ struct SolveSmem {
     double *A;                       // NR x ld; column n = rhs
     double *xs, *ys, *ts, *sol, *g0; // [k+1] each
     unsigned *ids;                   // [k+1]
+    int *piv;                        // [8] pivot rows of the current panel
 };
 
 __device__ __forceinline__ SolveSmem carve(double *base, int k, int ld, int nr)
@@ -573,7 +574,8 @@ __device__ __forceinline__ SolveSmem carve(double *base, int k, int ld, int nr)
     S.ts = S.ys + (k + 1);
     S.sol = S.ts + (k + 1);
     S.g0 = S.sol + (k + 1);
-    S.ids = reinterpret_cast<unsigned *>(S.g0 + (k + 1));
+    S.piv = reinterpret_cast<int *>(S.g0 + (k + 1));
+    S.ids = reinterpret_cast<unsigned *>(S.piv + 8);
     return S;
 }
 
@@ -776,19 +778,24 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
                 const int bi = 255 - (int)(key & 0xffull);
                 const double bv = __longlong_as_double((long long)(key & ~0xffull));
                 double pinv = 0.0;
+                int prow = j;                     // row swapped with row j (j = no swap)
                 if (bv > 0.0 && bv < INFINITY) {
                     if (bi != j) {
-                        for (int c = jb + lane; c < nc; c += 32) {
-                            const double tmp = A[j * ld + c];
-                            A[j * ld + c] = A[bi * ld + c];
-                            A[bi * ld + c] = tmp;
+                        // swap inside the panel now; the columns to its right are swapped by
+                        // their owner threads in step 2 (off warp 0's critical path)
+                        if (lane < 8) {
+                            const double tmp = A[j * ld + jb + lane];
+                            A[j * ld + jb + lane] = A[bi * ld + jb + lane];
+                            A[bi * ld + jb + lane] = tmp;
                         }
+                        prow = bi;
                         __syncwarp();
                     }
                     pinv = 1.0 / A[j * ld + j];
                 } else {
                     singular = true;
                 }
+                if (lane == 0) S.piv[jj] = prow;
                 // pivot row inside the panel, right of the diagonal
                 double u[7];
 #pragma unroll
@@ -810,6 +817,16 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
         if (jb + 8 > n) break;    // rhs column inside the panel: nothing left to transform
         // ---- 2. U12: rows jb..jb+7 of the columns right of the panel ----
         for (int c = jb + 8 + tid; c < nc; c += NT) {
+            // deferred row swaps of this panel, in pivot order
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int pr = S.piv[i];
+                if (pr != jb + i) {
+                    const double tmp = A[(jb + i) * ld + c];
+                    A[(jb + i) * ld + c] = A[pr * ld + c];
+                    A[pr * ld + c] = tmp;
+                }
+            }
             double uu[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1112,7 +1129,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     const int nr_pad = (k + 1 + 7) / 8 * 8;      // rows of the padded system
     const int nc_pad = (k + 2 + 7) / 8 * 8;      // columns incl. the right-hand side
     const int ld = nc_pad + 1;                   // odd leading dimension
-    const int cta_doubles = nr_pad * ld + 5 * (k + 1) + (k + 2) / 2 + 1;
+    const int cta_doubles = nr_pad * ld + 5 * (k + 1) + 4 + (k + 2) / 2 + 1;
     const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
     // chunk so that the selection scratch stays below ~16 GB

@@ -563,6 +563,7 @@ struct SolveSmem {
     double *xs, *ys, *ts, *sol, *g0; // [k+1] each
     unsigned *ids;                   // [k+1]
     int *piv;                        // [8] pivot rows of the current panel
+    unsigned long long *scale;       // bits of max |entry| of the assembled system
 };
 
 __device__ __forceinline__ SolveSmem carve(double *base, int k, int ld, int nr)
@@ -574,9 +575,27 @@ __device__ __forceinline__ SolveSmem carve(double *base, int k, int ld, int nr)
     S.ts = S.ys + (k + 1);
     S.sol = S.ts + (k + 1);
     S.g0 = S.sol + (k + 1);
-    S.piv = reinterpret_cast<int *>(S.g0 + (k + 1));
+    S.scale = reinterpret_cast<unsigned long long *>(S.g0 + (k + 1));
+    S.piv = reinterpret_cast<int *>(S.scale + 1);
     S.ids = reinterpret_cast<unsigned *>(S.piv + 8);
     return S;
+}
+
+// Packed pivot key: |value| bits with the low byte replaced by (255 - row); one unsigned max
+// yields the largest magnitude and, among (near-)equal ones, the smallest row.  The warp max
+// uses two 32-bit REDUX instead of a 5-round 64-bit shuffle tree.
+__device__ __forceinline__ unsigned long long pivot_key(double v, int r)
+{
+    return ((unsigned long long)__double_as_longlong(fabs(v)) & ~0xffull) | (unsigned long long)(255 - r);
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long key)
+{
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+    const unsigned ml = __reduce_max_sync(FULL, lo);
+    return ((unsigned long long)mh << 32) | ml;
 }
 
 // Loads the selection, assembles [A | b] (predictor.py:573-585) and zero-fills the padding.
@@ -621,10 +640,12 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl
     if (tid == 0) {
         A[m * ld + m] = 0.0;      // predictor.py:580
         A[m * ld + n] = 1.0;
+        *S.scale = 0ull;
     }
     __syncthreads();
     // gamma matrix, predictor.py:573-575 (diagonal = gamma(0,0), no special case)
     const double gdiag = gamma_st(P.M, 0.0, 0.0);
+    double amax = fmax(fabs(gdiag), 1.0);   // largest |entry| (the border holds ones)
     for (int e = tid; e < m; e += NT) A[e * ld + e] = gdiag;
     const int npairs = m * (m - 1) / 2;
     int a = 0, off = tid;  // pair (a, a+1+off)
@@ -640,27 +661,15 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl
         const double g = gamma_st(P.M, h, lt);
         A[a * ld + b] = g;
         A[b * ld + a] = g;
+        amax = fmax(amax, fabs(g));         // fmax ignores NaN
         off += NT;
+    }
+    {
+        const unsigned long long wm = warp_max_u64((unsigned long long)__double_as_longlong(amax));
+        if ((tid & 31) == 0) atomicMax(S.scale, wm);
     }
     __syncthreads();
     return m;
-}
-
-// Packed pivot key: |value| bits with the low byte replaced by (255 - row); one unsigned max
-// yields the largest magnitude and, among (near-)equal ones, the smallest row.  The warp max
-// uses two 32-bit REDUX instead of a 5-round 64-bit shuffle tree.
-__device__ __forceinline__ unsigned long long pivot_key(double v, int r)
-{
-    return ((unsigned long long)__double_as_longlong(fabs(v)) & ~0xffull) | (unsigned long long)(255 - r);
-}
-
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long key)
-{
-    const unsigned hi = (unsigned)(key >> 32);
-    const unsigned mh = __reduce_max_sync(FULL, hi);
-    const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
-    const unsigned ml = __reduce_max_sync(FULL, lo);
-    return ((unsigned long long)mh << 32) | ml;
 }
 
 // Back substitution (warp 0; column oriented: x_j = b_j * (1/U_jj), then b_r -= U_rj x_j for
@@ -763,6 +772,10 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
     if (m <= 0) return;
     const int n = m + 1;
     bool singular = false;
+    // rank tolerance: a pivot below n * 8 eps * max|entry| is rounding noise of an exactly
+    // singular system (duplicate observations); that column is skipped (x_j := 0).  dgelsd
+    // (rcond = eps) would return the minimum-norm solution instead: best-effort parity.
+    const double tol = __longlong_as_double((long long)*S.scale) * (1.8e-15 * (double)n);
 
     for (int jb = 0; jb < n; jb += 8) {
         if (warp == 0) {
@@ -779,7 +792,7 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
                 const double bv = __longlong_as_double((long long)(key & ~0xffull));
                 double pinv = 0.0;
                 int prow = j;                     // row swapped with row j (j = no swap)
-                if (bv > 0.0 && bv < INFINITY) {
+                if (bv > tol && bv < INFINITY) {
                     if (bi != j) {
                         // swap inside the panel now; the columns to its right are swapped by
                         // their owner threads in step 2 (off warp 0's critical path)
@@ -1129,7 +1142,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     const int nr_pad = (k + 1 + 7) / 8 * 8;      // rows of the padded system
     const int nc_pad = (k + 2 + 7) / 8 * 8;      // columns incl. the right-hand side
     const int ld = nc_pad + 1;                   // odd leading dimension
-    const int cta_doubles = nr_pad * ld + 5 * (k + 1) + 4 + (k + 2) / 2 + 1;
+    const int cta_doubles = nr_pad * ld + 5 * (k + 1) + 1 + 4 + (k + 2) / 2 + 1;
     const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
     // chunk so that the selection scratch stays below ~16 GB

@@ -176,3 +176,60 @@ def test_errors(ctx):
     with pytest.raises(ValueError):
         c2.kriging_set_model("sum_metric", "spherical", "spherical", "spherical", [1, 2, 3])
     c2.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, 55, 63, 64, 65, 96, 127, 128])
+def test_every_kernel_variant(ctx, k):
+    """max_kriging_points selects the (warps per target, panel count) variant of the solve
+    kernel and the padding of the system; sweep the boundaries."""
+    space, t, z, tsp, tt = synth(30000, 96, seed=100 + k, extent=200.0)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, k, 40.0, 40.0, f32=False)
+    o = ok.predict(space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, k, 40.0, 40.0, f32_storage=False)
+    assert o["n_cand"].max() > k
+    compare(g, o, z, False)
+
+
+def test_fewer_observations_than_k(ctx):
+    space, t, z, tsp, tt = synth(12, 40, seed=8, extent=20.0)
+    tt[:] = 400.0
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 50, 1e3, 1e3, f32=False)
+    o = ok.predict(space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 50, 1e3, 1e3, f32_storage=False)
+    assert np.all(o["n_used"] == 12)
+    compare(g, o, z, False)
+
+
+def test_duplicate_observations_are_flagged_not_fatal(ctx):
+    """Two identical observations make the system exactly singular: dgelsd returns the
+    minimum-norm solution, the LU skips the zero pivot (documented best-effort parity).  The
+    call must succeed, flag the targets, and still honour sum(w) == 1."""
+    space, t, z, tsp, tt = synth(2000, 50, seed=4, extent=60.0)
+    space[1000:] = space[:1000]
+    t[1000:] = t[:1000]
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 20, 30.0, 30.0, f32=False)
+    st = ctx.kriging_stats()
+    assert st["targets_singular"] > 0
+    used = g["n_used"] > 0
+    assert np.all(np.isfinite(g["mean"][used]))
+    assert np.allclose(g["w"][used].sum(axis=1), 1.0, atol=1e-4)
+
+
+def test_huge_radii_streaming_select(ctx):
+    """Every observation is a candidate (tens of buffer refills per target)."""
+    space, t, z, tsp, tt = synth(6000, 40, seed=12)
+    tt[:] = 366.0
+    g = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 1e4, 1e4, f32=False)
+    o = ok.predict(space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 1e4, 1e4, f32_storage=False)
+    assert np.all(o["n_cand"] == 6000)
+    compare(g, o, z, False)
+
+
+def test_saturated_model_ties_broken_by_index(ctx):
+    """Search radius far beyond the model ranges: most candidates sit at the sill, i.e. exact
+    gamma ties at the top-k boundary -- the rule is lowest observation index."""
+    space, t, z, tsp, tt = synth(4000, 60, seed=15, extent=100.0)
+    params = [0.5, 0.5, 0.5, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 1.0]   # ranges 0.5, radii 50
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, params, 1, 10, 50.0, 50.0, f32=False)
+    o = ok.predict(space, t, z, tsp, tt, SUM_METRIC, params, 1, 10, 50.0, 50.0, f32_storage=False)
+    assert o["tie"].mean() > 0.5
+    # oracle applies the same (gamma, index) rule: the sets must agree even on tied rows
+    assert np.array_equal(g["idx"], o["idx"])

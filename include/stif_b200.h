@@ -152,6 +152,10 @@ int stif_variogram_model_eval(stif_ctx *ctx, const double *h, const double *t, i
                                    mean/std reductions and reproduce numpy's pairwise
                                    f32/f64 summation (stock reference, predictor.py:610-618,
                                    :900-905).  Without it everything stays float64. */
+#define STIF_KRIG_FORCE_LU 2    /* solve every system with the pivoted LU (skip the covariance-form
+                                   Cholesky fast path that valid variogram models take) */
+#define STIF_KRIG_TRY_CHOL 4    /* try the Cholesky fast path for any model (targets whose
+                                   covariance matrix is not positive definite still go to the LU) */
 
 /* Predict n_targets points.  leave_out may be NULL; entry < 0 = none
  * (stif/data.py:204-205).  mean_out/std_out: n_targets doubles.  Optional outputs
@@ -179,6 +183,11 @@ int stif_kriging_predict_dev(stif_ctx *ctx, const double *tx, const double *ty,
  * search window, out[2] = targets with fewer than min_pts candidates,
  * out[3] = targets whose system was flagged singular / non-finite (NaN result). */
 int stif_kriging_stats(stif_ctx *ctx, uint64_t out[4]);
+
+/* out[0] = targets of the last call that the covariance-form Cholesky kernel handed to the
+ * pivoted LU (not positive definite / singular); out[1] = 1 if the Cholesky path was enabled
+ * for the call's model, else 0. */
+int stif_kriging_solver_stats(stif_ctx *ctx, uint64_t out[2]);
 
 /* Device time in ms of the phases of the last call, measured with CUDA events on the
  * launching stream: variogram: [0]=sort/prepare [1]=pair kernel [2]=reduce;

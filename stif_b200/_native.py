@@ -21,6 +21,8 @@ STIF_ENONFINITE = -5
 VARIO_PEEL = 1
 VARIO_NO_CULL = 2
 KRIG_F32_STORAGE = 1
+KRIG_FORCE_LU = 2
+KRIG_TRY_CHOL = 4
 
 ST_MODELS = {"sum": 0, "product": 1, "product_sum": 2, "metric": 3, "sum_metric": 4}
 MARGINAL_MODELS = {"spherical": 0, "gaussian": 1}
@@ -65,6 +67,7 @@ SIGNATURES = {
                                                 ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                                 ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "stif_kriging_stats": (ctypes.c_int, [_vp, _c_u64_p]),
+    "stif_kriging_solver_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "stif_last_phase_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "stif_bench_dfma": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_float)]),
 }
@@ -279,6 +282,11 @@ class Context:
         _check(self._lib.stif_kriging_stats(self._h, out), "stif_kriging_stats")
         return {"candidates_examined": int(out[0]), "candidates_in_window": int(out[1]),
                 "targets_below_min": int(out[2]), "targets_singular": int(out[3])}
+
+    def kriging_solver_stats(self):
+        out = (ctypes.c_uint64 * 2)()
+        _check(self._lib.stif_kriging_solver_stats(self._h, out), "stif_kriging_solver_stats")
+        return {"cholesky_to_lu": int(out[0]), "cholesky_enabled": bool(out[1])}
 
     # ---- measurement -------------------------------------------------------------
     def last_phase_ms(self):

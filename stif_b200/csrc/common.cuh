@@ -91,10 +91,12 @@ struct stif_ctx {
     // ---- kriging state ----
     int64_t n_obs = 0;
     stif::DevBuf k_obs;        // obs SoA (x, y, t, resid) as given
+    stif::DevBuf k_obs4;       // obs AoS {x, y, t, resid}, original order (neighbour gathers)
     stif::KrigModel model;
     stif::DevBuf k_scratch[16];
     stif::DevBuf k_stats;
     uint64_t k_stats_host[4] = {0, 0, 0, 0};
+    int k_chol_enabled = 0;    // last predict call tried the covariance-form kernel
     // grid cache key
     double grid_smax = -1, grid_tmax = -1;
     int64_t grid_nobs = -1;

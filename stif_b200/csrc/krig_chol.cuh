@@ -1,0 +1,378 @@
+// krig_chol.cuh -- covariance-form kriging solve: one warp per target, tiled Cholesky with the
+// rank-4 updates on the FP64 tensor cores.  Included by kriging.cu (namespace stif::krig).
+//
+// Replaces calc_kriging_weights (stif/predictor.py:566-593) for VALID variogram models.
+// The reference solves the bordered system  [Gamma 1; 1' 0] [w; lam] = [gamma0; 1]  with LAPACK
+// dgelsd.  With sum(w) = 1 the same weights solve the covariance form
+//      C w - lam 1 = c0,   C = c 11' - Gamma,  c0 = c 1 - gamma0,   c = gamma(inf, inf) (the sill),
+// and C is symmetric positive definite whenever gamma is a valid variogram (sum / metric /
+// sum_metric of spherical or gaussian marginals with non-negative sills and nuggets).  Then
+//      C = L L',  yv = L^-1 c0,  yu = L^-1 1,  lam = (1 - yu.yv) / (yu.yu),  w = L^-T (yv + lam yu):
+// a third of the flops of the pivoted LU, no pivot search, and half the shared memory, so a
+// whole target fits one warp (no CTA barriers) and ~12 targets are resident per SM.
+// Any pivot <= tol (not positive definite: product / product_sum models, unconstrained
+// Nelder-Mead parameters, duplicate observations) sends the target to the pivoted-LU kernel.
+//
+// Storage: lower triangle as 8x8 tiles (row-major, 16-byte chunks XOR-swizzled so that the
+// row-wise LDS.128 of the panel step and the mma fragment loads are both conflict-free).  Rows
+// m and m+1 of the tiled matrix hold c0' and 1', so the forward substitutions ride along with
+// the factorisation.
+//
+// Per tile column Jc (left-looking):
+//   1. tiles (I, Jc), I >= Jc:  C -= sum over all earlier 4-column panels q of L(I,q) L(Jc,q)'
+//      -- accumulators in registers, 2 LDS + 1 DMMA (m8n8k4) per panel and tile;
+//   2. panel 2Jc (columns 8Jc..8Jc+3): every lane factors the 4x4 diagonal block redundantly in
+//      registers (rsqrt = MUFU.RSQ64H + one cubic Newton step), then lanes own rows and
+//      forward-substitute their 4 entries;
+//   3. columns 8Jc+4..8Jc+7 of the same tiles -= panel 2Jc (one DMMA per tile, masked store);
+//   4. panel 2Jc+1 likewise.
+
+struct CholParams {
+    const double4 *obs4;     // observations in ORIGINAL order: {x, y, t, resid}
+    double csill;            // c
+    double cdiag;            // c - gamma(0, 0)
+    double tol;              // pivot tolerance
+    // all-spherical fast path: C = cb + ncs q(h is) + nct q(t it) + ncm q(d im)
+    double is, it, im, ncs, nct, ncm, cb, ani2;
+    unsigned *fail_list;     // targets (chunk-local ids) that need the pivoted LU
+    unsigned *fail_count;
+};
+
+enum { CHOL_SUM_SPH = 0, CHOL_METRIC_SPH = 1, CHOL_SUM_METRIC_SPH = 2, CHOL_GENERIC = 3 };
+
+__device__ __forceinline__ double rsqrt_approx(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// 1/sqrt(x), x > 0 and normal: MUFU.RSQ64H (2^-22) + one cubic step -> ~2^-60 relative.
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    const double y = rsqrt_approx(x);
+    const double t = x * y;
+    const double e = __fma_rn(-t, y, 1.0);
+    const double p = __fma_rn(0.375, e, 0.5);
+    const double q = e * p;
+    return __fma_rn(y, q, y);
+}
+
+// sqrt(x) to <= 1 ulp for x >= 0 (coupled Newton on g ~ sqrt x, h ~ 1/(2 sqrt x)); 0 -> ~1e-140.
+__device__ __forceinline__ double sqrt_fast(double x)
+{
+    x = fmax(x, 1e-280);
+    const double y = rsqrt_approx(x);
+    double g = x * y;
+    double h = 0.5 * y;
+    const double r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    const double d = __fma_rn(-g, g, x);
+    return __fma_rn(d, h, g);
+}
+
+// spherical shape q(u) = 1.5 u - 0.5 u^3 for u <= 1, 1 beyond (variogram_models.py:40-44, r > 0)
+__device__ __forceinline__ double sph_q(double u)
+{
+    u = fmin(u, 1.0);
+    return u * __fma_rn(-0.5, u * u, 1.5);
+}
+
+template <int VAR>
+__device__ __forceinline__ double cov_entry(const Model &M, const CholParams &X, double d2, double lt)
+{
+    if (VAR == CHOL_SUM_SPH) {
+        const double h = sqrt_fast(d2);
+        return __fma_rn(X.nct, sph_q(lt * X.it), __fma_rn(X.ncs, sph_q(h * X.is), X.cb));
+    } else if (VAR == CHOL_METRIC_SPH) {
+        const double dm = sqrt_fast(__fma_rn(X.ani2 * lt, lt, d2));
+        return __fma_rn(X.ncm, sph_q(dm * X.im), X.cb);
+    } else if (VAR == CHOL_SUM_METRIC_SPH) {
+        const double h = sqrt_fast(d2);
+        const double dm = sqrt_fast(__fma_rn(X.ani2 * lt, lt, d2));
+        double c = __fma_rn(X.ncs, sph_q(h * X.is), X.cb);
+        c = __fma_rn(X.nct, sph_q(lt * X.it), c);
+        return __fma_rn(X.ncm, sph_q(dm * X.im), c);
+    } else {
+        return X.csill - gamma_st(M, sqrt(d2), lt);
+    }
+}
+
+__device__ __forceinline__ int chol_swz(int r) { return (((r >> 1) & 1) << 1) | ((r >> 2) & 1); }
+__device__ __forceinline__ int chol_tri(int I) { return (I * (I + 1)) >> 1; }
+// offset (in doubles) of entry (r, c), c <= r (or any entry of a stored tile)
+__device__ __forceinline__ int chol_off(int r, int c)
+{
+    const int ri = r & 7, ci = c & 7;
+    return (chol_tri(r >> 3) + (c >> 3)) * 64 + ri * 8 + ((((ci >> 1) ^ chol_swz(ri)) << 1) | (ci & 1));
+}
+// 16-byte chunk ch (0..3) of row ri of a tile
+__device__ __forceinline__ double2 *chol_chunk(double *tile, int ri, int ch)
+{
+    return reinterpret_cast<double2 *>(tile + ri * 8 + ((ch ^ chol_swz(ri)) << 1));
+}
+
+// Factor the 4-column panel starting at column c0 (tile column Pt, half h) and forward-substitute
+// the rows below.  Returns true if a pivot failed.
+__device__ __forceinline__ bool chol_panel(double *T, int c0, int m, int nrow, double tol, int lane)
+{
+    const int Pt = c0 >> 3, h = (c0 >> 2) & 1;
+    double *Td = T + (chol_tri(Pt) + Pt) * 64;
+    const int r0 = 4 * h;
+    const double2 u0 = *chol_chunk(Td, r0 + 0, 2 * h);
+    const double2 u1 = *chol_chunk(Td, r0 + 1, 2 * h);
+    const double2 u2 = *chol_chunk(Td, r0 + 2, 2 * h), v2 = *chol_chunk(Td, r0 + 2, 2 * h + 1);
+    const double2 u3 = *chol_chunk(Td, r0 + 3, 2 * h), v3 = *chol_chunk(Td, r0 + 3, 2 * h + 1);
+    double d00 = u0.x, d10 = u1.x, d11 = u1.y, d20 = u2.x, d21 = u2.y, d22 = v2.x;
+    double d30 = u3.x, d31 = u3.y, d32 = v3.x, d33 = v3.y;
+    __syncwarp();              // every lane holds the block before its rows are overwritten
+    const int ncol = m - c0;   // real columns in this panel (>= 1); the others pass through
+    if (ncol < 4) { d30 = 0.0; d31 = 0.0; d32 = 0.0; d33 = 1.0; }
+    if (ncol < 3) { d20 = 0.0; d21 = 0.0; d22 = 1.0; }
+    if (ncol < 2) { d10 = 0.0; d11 = 1.0; }
+    bool fail = !(d00 > tol);
+    const double i0 = rsqrt_fast(d00);
+    const double l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
+    d11 = __fma_rn(-l10, l10, d11);
+    d21 = __fma_rn(-l20, l10, d21);
+    d31 = __fma_rn(-l30, l10, d31);
+    d22 = __fma_rn(-l20, l20, d22);
+    d32 = __fma_rn(-l30, l20, d32);
+    d33 = __fma_rn(-l30, l30, d33);
+    fail |= !(d11 > tol);
+    const double i1 = rsqrt_fast(d11);
+    const double l21 = d21 * i1, l31 = d31 * i1;
+    d22 = __fma_rn(-l21, l21, d22);
+    d32 = __fma_rn(-l31, l21, d32);
+    d33 = __fma_rn(-l31, l31, d33);
+    fail |= !(d22 > tol);
+    const double i2 = rsqrt_fast(d22);
+    const double l32 = d32 * i2;
+    d33 = __fma_rn(-l32, l32, d33);
+    fail |= !(d33 > tol);
+    const double i3 = rsqrt_fast(d33);
+    if (fail) return true;
+
+    for (int r = c0 + lane; r < nrow; r += 32) {
+        double *tile = T + (chol_tri(r >> 3) + Pt) * 64;
+        double2 *p0 = chol_chunk(tile, r & 7, 2 * h), *p1 = chol_chunk(tile, r & 7, 2 * h + 1);
+        const double2 q0 = *p0, q1 = *p1;
+        double x0 = q0.x * i0;
+        double x1 = __fma_rn(-x0, l10, q0.y) * i1;
+        double x2 = __fma_rn(-x1, l21, __fma_rn(-x0, l20, q1.x)) * i2;
+        double x3 = __fma_rn(-x2, l32, __fma_rn(-x1, l31, __fma_rn(-x0, l30, q1.y))) * i3;
+        const int i = r - c0;
+        if (i < 4) {   // rows of the diagonal block: 1/L_ii on the diagonal, upper part untouched
+            if (i == 0) { x0 = i0; x1 = q0.y; x2 = q1.x; x3 = q1.y; }
+            if (i == 1) { x1 = i1; x2 = q1.x; x3 = q1.y; }
+            if (i == 2) { x2 = i2; x3 = q1.y; }
+            if (i == 3) { x3 = i3; }
+        }
+        *p0 = make_double2(x0, x1);
+        *p1 = make_double2(x2, x3);
+    }
+    return false;
+}
+
+constexpr int CHOL_G = 8;   // tiles of one tile column updated together (accumulators in registers)
+
+template <int VAR, int ZR>
+__global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParams X)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const int lane = threadIdx.x;
+    const int k = P.k;
+    const int kp = (k + 1) & ~1;
+    const int ntmax = (k + 2 + 7) >> 3;
+    double *T = smem_d;
+    double2 *pxy = reinterpret_cast<double2 *>(T + chol_tri(ntmax) * 64);
+    double *pt = reinterpret_cast<double *>(pxy + kp);
+    double *g0 = pt + kp, *rs = g0 + kp;
+    unsigned *ids = reinterpret_cast<unsigned *>(rs + kp);
+    double *sol = pt;                                   // pt is dead after the assembly
+    const int g = lane >> 2, t = lane & 3, sg = chol_swz(g);
+    const int co = g * 8 + ((t ^ sg) << 1);             // C fragment: row g, columns 2t, 2t+1
+
+    for (int slot = blockIdx.x; slot < P.n; slot += gridDim.x) {
+        const unsigned tl = P.order[slot];
+        const int64_t tg = P.c0 + tl;
+        const int m = P.sel_n[tl];
+        __syncwarp();
+        if (m <= 0) {
+            if (lane == 0) {
+                P.mean[tg] = 0.0;
+                P.std[tg] = 0.0;
+                if (P.nused_out) P.nused_out[tg] = m < 0 ? -1 : 0;
+            }
+            for (int e = lane; e < k; e += 32) {
+                if (P.w_out) P.w_out[(size_t)tg * k + e] = 0.f;
+                if (P.g_out) P.g_out[(size_t)tg * k + e] = 0.f;
+                if (P.idx_out) P.idx_out[(size_t)tg * k + e] = 0u;
+            }
+            continue;
+        }
+        const int nrow = m + 2, nt = (nrow + 7) >> 3;
+        // ---- neighbours, diagonal, the two right-hand-side rows ----
+        for (int e = lane; e < m; e += 32) {
+            const unsigned id = P.sel_idx[(size_t)tl * k + e];
+            const double4 o = X.obs4[id];
+            ids[e] = id;
+            pxy[e] = make_double2(o.x, o.y);
+            pt[e] = o.z;
+            rs[e] = o.w;
+            const double gv = P.sel_gamma[(size_t)tl * k + e];
+            g0[e] = gv;
+            T[chol_off(e, e)] = X.cdiag;
+            T[chol_off(m, e)] = X.csill - gv;
+            T[chol_off(m + 1, e)] = 1.0;
+        }
+        __syncwarp();
+        // ---- C = c - gamma(D_s, D_t), strictly lower triangle; pair e = a(a-1)/2 + b, b < a ----
+        {
+            const int npairs = (m * (m - 1)) >> 1;
+            int a = 1, b = lane;
+            for (int e = lane; e < npairs; e += 32) {
+                while (b >= a) {
+                    b -= a;
+                    ++a;
+                }
+                const double2 pa = pxy[a], pb = pxy[b];
+                const double dx = pa.x - pb.x, dy = pa.y - pb.y;
+                const double d2 = __fma_rn(dy, dy, dx * dx);
+                const double lt = fabs(pt[a] - pt[b]);
+                T[chol_off(a, b)] = cov_entry<VAR>(P.M, X, d2, lt);
+                b += 32;
+            }
+        }
+        __syncwarp();
+        // ---- left-looking tiled Cholesky ----
+        bool fail = false;
+        const int ntc = (m + 7) >> 3;       // tile columns that hold real columns
+        for (int Jc = 0; Jc < ntc && !fail; ++Jc) {
+            if (Jc > 0) {
+                // 1. tiles (I, Jc) -= sum_q L(I, q) L(Jc, q)^T over the 2 Jc earlier panels
+                const double *rowJ = T + chol_tri(Jc) * 64;
+                for (int I0 = Jc; I0 < nt; I0 += CHOL_G) {
+                    double2 acc[CHOL_G];
+#pragma unroll
+                    for (int u = 0; u < CHOL_G; ++u) acc[u] = make_double2(0.0, 0.0);
+                    for (int q = 0; q < 2 * Jc; ++q) {
+                        // fragment element (row g, column 4 (q & 1) + t) of tile (., q >> 1)
+                        const int fo = (q >> 1) * 64 + g * 8 +
+                                       ((((2 * (q & 1) + (t >> 1)) ^ sg) << 1) | (t & 1));
+                        const double bf = rowJ[fo];
+#pragma unroll
+                        for (int u = 0; u < CHOL_G; ++u) {
+                            if (I0 + u < nt) {
+                                const double af = T[chol_tri(I0 + u) * 64 + fo];
+                                dmma884(acc[u].x, acc[u].y, af, bf);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < CHOL_G; ++u) {
+                        if (I0 + u < nt) {
+                            double2 *cp = reinterpret_cast<double2 *>(T + (chol_tri(I0 + u) + Jc) * 64 + co);
+                            double2 cv = *cp;
+                            cv.x -= acc[u].x;
+                            cv.y -= acc[u].y;
+                            *cp = cv;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // 2. left panel
+            fail = chol_panel(T, 8 * Jc, m, nrow, X.tol, lane);
+            __syncwarp();
+            if (fail || 8 * Jc + 4 >= m) break;
+            // 3. right half of the tile column -= left panel
+            {
+                const int fo = Jc * 64 + g * 8 + ((((t >> 1) ^ sg) << 1) | (t & 1));
+                const double bf = T[chol_tri(Jc) * 64 + fo];
+                for (int I = Jc; I < nt; ++I) {
+                    const double af = T[chol_tri(I) * 64 + fo];
+                    double c0v = 0.0, c1v = 0.0;
+                    dmma884(c0v, c1v, af, bf);
+                    if (t >= 2) {
+                        double2 *cp = reinterpret_cast<double2 *>(T + (chol_tri(I) + Jc) * 64 + co);
+                        double2 cv = *cp;
+                        cv.x -= c0v;
+                        cv.y -= c1v;
+                        *cp = cv;
+                    }
+                }
+            }
+            __syncwarp();
+            // 4. right panel
+            fail = chol_panel(T, 8 * Jc + 4, m, nrow, X.tol, lane);
+            __syncwarp();
+        }
+        if (fail) {   // not positive definite / singular: the pivoted LU takes this target
+            if (lane == 0) X.fail_list[atomicAdd(X.fail_count, 1u)] = tl;
+            continue;
+        }
+        // ---- lam and z = yv + lam yu (rows m, m+1 now hold yv', yu') ----
+        double z[ZR];
+        {
+            double yu[ZR], suu = 0.0, suv = 0.0;
+#pragma unroll
+            for (int i = 0; i < ZR; ++i) {
+                const int c = lane + 32 * i;
+                yu[i] = 0.0;
+                z[i] = 0.0;
+                if (c < m) {
+                    z[i] = T[chol_off(m, c)];
+                    yu[i] = T[chol_off(m + 1, c)];
+                    suu = __fma_rn(yu[i], yu[i], suu);
+                    suv = __fma_rn(yu[i], z[i], suv);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                suu += __shfl_xor_sync(FULL, suu, off);
+                suv += __shfl_xor_sync(FULL, suv, off);
+            }
+            const double lam = (1.0 - suv) / suu;
+#pragma unroll
+            for (int i = 0; i < ZR; ++i) z[i] = __fma_rn(lam, yu[i], z[i]);
+        }
+        // ---- back substitution L' w = z, column oriented; lane owns columns lane + 32 i ----
+        {
+            int cofs[ZR], cch[ZR];
+#pragma unroll
+            for (int i = 0; i < ZR; ++i) {
+                const int c = lane + 32 * i;
+                cofs[i] = (c >> 3) * 64 + (c & 1);
+                cch[i] = (c & 7) >> 1;
+            }
+            for (int j = m - 1; j >= 0; --j) {
+                const int rowb = chol_tri(j >> 3) * 64 + (j & 7) * 8, sj = chol_swz(j & 7);
+                const double dinv = T[chol_off(j, j)];
+                double zj = z[0];
+#pragma unroll
+                for (int i = 1; i < ZR; ++i)
+                    if ((j >> 5) == i) zj = z[i];
+                zj = __shfl_sync(FULL, zj, j & 31);
+                const double wj = zj * dinv;
+#pragma unroll
+                for (int i = 0; i < ZR; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < j) z[i] = __fma_rn(-T[rowb + cofs[i] + ((cch[i] ^ sj) << 1)], wj, z[i]);
+                    else if (c == j) z[i] = wj;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < ZR; ++i) {
+            const int c = lane + 32 * i;
+            if (c < m) sol[c] = z[i];
+        }
+        __syncwarp();
+        solve_epilogue(P, sol, g0, ids, rs, reinterpret_cast<double *>(pxy),
+                       reinterpret_cast<float *>(pxy + (kp >> 1)),
+                       reinterpret_cast<float *>(pxy + (kp >> 1)) + kp, m, tg, lane);
+    }
+}

@@ -527,6 +527,7 @@ struct SolveParams {
     unsigned *idx_out;           // nullable
     int *nused_out;              // nullable
     unsigned *singular;          // [n] chunk-local flag
+    const unsigned *count;       // nullable: number of entries of `order` to process (device)
 };
 
 // numpy's pairwise sum of a row of length n <= 128 (numpy/_core/src/umath/loops_utils.h.src),
@@ -672,25 +673,19 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl
     return m;
 }
 
-// Back substitution (warp 0; column oriented: x_j = b_j * (1/U_jj), then b_r -= U_rj x_j for
-// r < j) and the fused epilogue: predictor.py:646-658 (storage) and :900-905 (mean, std).
-__device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, unsigned tl, int64_t tg,
-                             int lane, bool singular)
+// Fused epilogue (one warp): predictor.py:646-658 (storage) and :900-905 (mean, std).
+// sol/g0/ids: the m weights, gamma-vector entries and observation indices; rloc: residuals of
+// the neighbours if the caller staged them (else gathered from P.oresid); sc64/sc32a/sc32b:
+// scratch for k doubles / k floats / k floats.
+__device__ void solve_epilogue(const SolveParams &P, const double *sol, const double *g0,
+                               const unsigned *ids, const double *rloc, double *sc64, float *sc32a,
+                               float *sc32b, int m, int64_t tg, int lane)
 {
-    const int k = P.k, ld = P.ld, n = m + 1;
-    double *A = S.A, *sol = S.sol, *g0 = S.g0;
-    const unsigned *ids = S.ids;
-    for (int j = n - 1; j >= 0; --j) {
-        const double xj = A[j * ld + n] * A[j * ld + j];
-        for (int r = lane; r < j; r += 32) A[r * ld + n] = __fma_rn(-A[r * ld + j], xj, A[r * ld + n]);
-        if (lane == 0) sol[j] = xj;
-        __syncwarp();
-    }
-    if (lane == 0 && singular) P.singular[tl] = 1u;
+    const int k = P.k;
     if (P.flags & STIF_KRIG_F32_STORAGE) {
-        double *term64 = S.xs;                            // k doubles
-        float *w32 = reinterpret_cast<float *>(S.ys);     // k floats
-        float *term32 = reinterpret_cast<float *>(S.ts);  // k floats
+        double *term64 = sc64;
+        float *w32 = sc32a;
+        float *term32 = sc32b;
         const double resid0 = P.oresid[0];
         __syncwarp();
         for (int e = lane; e < k; e += 32) {
@@ -701,7 +696,7 @@ __device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, un
                 w = (float)sol[e];
                 g = (float)g0[e];
                 id = ids[e];
-                r = P.oresid[id];
+                r = rloc ? rloc[e] : P.oresid[id];
             }
             w32[e] = w;
             term64[e] = (double)w * r;                    // f32 * f64 -> f64
@@ -719,7 +714,7 @@ __device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, un
     } else {
         double am = 0.0, av = 0.0;
         for (int e = lane; e < m; e += 32) {
-            am += sol[e] * P.oresid[ids[e]];
+            am += sol[e] * (rloc ? rloc[e] : P.oresid[ids[e]]);
             av += sol[e] * g0[e];
         }
         for (int off = 16; off > 0; off >>= 1) {
@@ -738,6 +733,25 @@ __device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, un
             if (P.nused_out) P.nused_out[tg] = m;
         }
     }
+    __syncwarp();
+}
+
+// Back substitution of the LU (warp 0; column oriented: x_j = b_j * (1/U_jj), then
+// b_r -= U_rj x_j for r < j), then the epilogue.
+__device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, unsigned tl, int64_t tg,
+                             int lane, bool singular)
+{
+    const int ld = P.ld, n = m + 1;
+    double *A = S.A, *sol = S.sol;
+    for (int j = n - 1; j >= 0; --j) {
+        const double xj = A[j * ld + n] * A[j * ld + j];
+        for (int r = lane; r < j; r += 32) A[r * ld + n] = __fma_rn(-A[r * ld + j], xj, A[r * ld + n]);
+        if (lane == 0) sol[j] = xj;
+        __syncwarp();
+    }
+    if (lane == 0 && singular) P.singular[tl] = 1u;
+    solve_epilogue(P, sol, S.g0, S.ids, nullptr, S.xs, reinterpret_cast<float *>(S.ys),
+                   reinterpret_cast<float *>(S.ts), m, tg, lane);
 }
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -763,122 +777,132 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
     extern __shared__ __align__(16) double smem_d[];
     constexpr int NT = WPT * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned tl = P.order[blockIdx.x];
-    const int64_t tg = P.c0 + tl;
     const int ld = P.ld;
     const SolveSmem S = carve(smem_d, P.k, ld, nr);
     double *A = S.A;
-    const int m = solve_setup<NT>(P, S, tl, tg, tid, nr, nc);
-    if (m <= 0) return;
-    const int n = m + 1;
-    bool singular = false;
-    // rank tolerance: a pivot below n * 8 eps * max|entry| is rounding noise of an exactly
-    // singular system (duplicate observations); that column is skipped (x_j := 0).  dgelsd
-    // (rcond = eps) would return the minimum-norm solution instead: best-effort parity.
-    const double tol = __longlong_as_double((long long)*S.scale) * (1.8e-15 * (double)n);
+    const int n_work = P.count ? (int)*P.count : P.n;
+    // persistent CTAs: targets in visit order, strided over the grid
+    for (int slot = blockIdx.x; slot < n_work; slot += gridDim.x) {
+        __syncthreads();   // the previous target's epilogue is done with the shared arrays
+        const unsigned tl = P.order[slot];
+        const int64_t tg = P.c0 + tl;
+        const int m = solve_setup<NT>(P, S, tl, tg, tid, nr, nc);
+        if (m <= 0) continue;
+        const int n = m + 1;
+        bool singular = false;
+        // rank tolerance: a pivot below n * 8 eps * max|entry| is rounding noise of an exactly
+        // singular system (duplicate observations); that column is skipped (x_j := 0).  dgelsd
+        // (rcond = eps) would return the minimum-norm solution instead: best-effort parity.
+        const double tol = __longlong_as_double((long long)*S.scale) * (1.8e-15 * (double)n);
 
-    for (int jb = 0; jb < n; jb += 8) {
-        if (warp == 0) {
-            // ---- 1. panel factorisation, columns jb .. jb+7 (pivot columns only while < n) ----
-            for (int jj = 0; jj < 8 && jb + jj < n; ++jj) {
-                const int j = jb + jj;
-                unsigned long long key = 0ull;
-                for (int r = j + lane; r < n; r += 32) {
-                    const unsigned long long kb = pivot_key(A[r * ld + j], r);
-                    key = kb > key ? kb : key;
-                }
-                key = warp_max_u64(key);
-                const int bi = 255 - (int)(key & 0xffull);
-                const double bv = __longlong_as_double((long long)(key & ~0xffull));
-                double pinv = 0.0;
-                int prow = j;                     // row swapped with row j (j = no swap)
-                if (bv > tol && bv < INFINITY) {
-                    if (bi != j) {
-                        // swap inside the panel now; the columns to its right are swapped by
-                        // their owner threads in step 2 (off warp 0's critical path)
-                        if (lane < 8) {
-                            const double tmp = A[j * ld + jb + lane];
-                            A[j * ld + jb + lane] = A[bi * ld + jb + lane];
-                            A[bi * ld + jb + lane] = tmp;
-                        }
-                        prow = bi;
-                        __syncwarp();
+        for (int jb = 0; jb < n; jb += 8) {
+            if (warp == 0) {
+                // ---- 1. panel factorisation, columns jb .. jb+7 (pivot columns only while < n) ----
+                for (int jj = 0; jj < 8 && jb + jj < n; ++jj) {
+                    const int j = jb + jj;
+                    unsigned long long key = 0ull;
+                    for (int r = j + lane; r < n; r += 32) {
+                        const unsigned long long kb = pivot_key(A[r * ld + j], r);
+                        key = kb > key ? kb : key;
                     }
-                    pinv = 1.0 / A[j * ld + j];
-                } else {
-                    singular = true;
+                    key = warp_max_u64(key);
+                    const int bi = 255 - (int)(key & 0xffull);
+                    const double bv = __longlong_as_double((long long)(key & ~0xffull));
+                    double pinv = 0.0;
+                    int prow = j;                     // row swapped with row j (j = no swap)
+                    if (bv > tol && bv < INFINITY) {
+                        if (bi != j) {
+                            // swap inside the panel now; the columns to its right are swapped by
+                            // their owner threads in step 2 (off warp 0's critical path)
+                            if (lane < 8) {
+                                const double tmp = A[j * ld + jb + lane];
+                                A[j * ld + jb + lane] = A[bi * ld + jb + lane];
+                                A[bi * ld + jb + lane] = tmp;
+                            }
+                            prow = bi;
+                            __syncwarp();
+                        }
+                        pinv = 1.0 / A[j * ld + j];
+                    } else {
+                        singular = true;
+                    }
+                    if (lane == 0) S.piv[jj] = prow;
+                    // pivot row inside the panel, right of the diagonal
+                    double u[7];
+#pragma unroll
+                    for (int cc = 0; cc < 7; ++cc) u[cc] = (cc >= jj) ? A[j * ld + jb + cc + 1] : 0.0;
+                    for (int r = j + 1 + lane; r < n; r += 32) {
+                        double *row = A + r * ld + jb;
+                        const double mneg = -(row[jj] * pinv);   // negated multiplier
+                        row[jj] = mneg;
+#pragma unroll
+                        for (int cc = 0; cc < 7; ++cc)
+                            if (cc >= jj) row[cc + 1] = __fma_rn(mneg, u[cc], row[cc + 1]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) A[j * ld + j] = pinv;
+                    __syncwarp();
                 }
-                if (lane == 0) S.piv[jj] = prow;
-                // pivot row inside the panel, right of the diagonal
-                double u[7];
+            }
+            __syncthreads();
+            if (jb + 8 > n) break;    // rhs column inside the panel: nothing left to transform
+            // ---- 2. U12: rows jb..jb+7 of the columns right of the panel ----
+            for (int c = jb + 8 + tid; c < nc; c += NT) {
+                // deferred row swaps of this panel, in pivot order
 #pragma unroll
-                for (int cc = 0; cc < 7; ++cc) u[cc] = (cc >= jj) ? A[j * ld + jb + cc + 1] : 0.0;
-                for (int r = j + 1 + lane; r < n; r += 32) {
-                    double *row = A + r * ld + jb;
-                    const double mneg = -(row[jj] * pinv);   // negated multiplier
-                    row[jj] = mneg;
-#pragma unroll
-                    for (int cc = 0; cc < 7; ++cc)
-                        if (cc >= jj) row[cc + 1] = __fma_rn(mneg, u[cc], row[cc + 1]);
+                for (int i = 0; i < 8; ++i) {
+                    const int pr = S.piv[i];
+                    if (pr != jb + i) {
+                        const double tmp = A[(jb + i) * ld + c];
+                        A[(jb + i) * ld + c] = A[pr * ld + c];
+                        A[pr * ld + c] = tmp;
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) A[j * ld + j] = pinv;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        if (jb + 8 > n) break;    // rhs column inside the panel: nothing left to transform
-        // ---- 2. U12: rows jb..jb+7 of the columns right of the panel ----
-        for (int c = jb + 8 + tid; c < nc; c += NT) {
-            // deferred row swaps of this panel, in pivot order
+                double uu[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int pr = S.piv[i];
-                if (pr != jb + i) {
-                    const double tmp = A[(jb + i) * ld + c];
-                    A[(jb + i) * ld + c] = A[pr * ld + c];
-                    A[pr * ld + c] = tmp;
+                for (int i = 0; i < 8; ++i) {
+                    double acc = A[(jb + i) * ld + c];
+#pragma unroll
+                    for (int q = 0; q < i; ++q) acc = __fma_rn(A[(jb + i) * ld + jb + q], uu[q], acc);
+                    uu[i] = acc;
+                }
+#pragma unroll
+                for (int i = 1; i < 8; ++i) A[(jb + i) * ld + c] = uu[i];
+            }
+            __syncthreads();
+            // ---- 3. trailing update on the tensor cores ----
+            {
+                const int g = lane >> 2, t = lane & 3;
+                const int r_lo = jb + 8, ntr = (nr - r_lo) >> 3, ntc = (nc - r_lo) >> 3;
+                for (int tile = warp; tile < ntr * ntc; tile += WPT) {
+                    const int ti = tile / ntc, tj = tile - ti * ntc;
+                    const int r0 = r_lo + 8 * ti, c0 = r_lo + 8 * tj;
+                    const double a0 = A[(r0 + g) * ld + jb + t], a1 = A[(r0 + g) * ld + jb + 4 + t];
+                    const double b0 = A[(jb + t) * ld + c0 + g], b1 = A[(jb + 4 + t) * ld + c0 + g];
+                    double *cp = A + (r0 + g) * ld + c0 + 2 * t;
+                    double c0v = cp[0], c1v = cp[1];
+                    dmma884(c0v, c1v, a0, b0);
+                    dmma884(c0v, c1v, a1, b1);
+                    cp[0] = c0v;
+                    cp[1] = c1v;
                 }
             }
-            double uu[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double acc = A[(jb + i) * ld + c];
-#pragma unroll
-                for (int q = 0; q < i; ++q) acc = __fma_rn(A[(jb + i) * ld + jb + q], uu[q], acc);
-                uu[i] = acc;
-            }
-#pragma unroll
-            for (int i = 1; i < 8; ++i) A[(jb + i) * ld + c] = uu[i];
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- 3. trailing update on the tensor cores ----
-        {
-            const int g = lane >> 2, t = lane & 3;
-            const int r_lo = jb + 8, ntr = (nr - r_lo) >> 3, ntc = (nc - r_lo) >> 3;
-            for (int tile = warp; tile < ntr * ntc; tile += WPT) {
-                const int ti = tile / ntc, tj = tile - ti * ntc;
-                const int r0 = r_lo + 8 * ti, c0 = r_lo + 8 * tj;
-                const double a0 = A[(r0 + g) * ld + jb + t], a1 = A[(r0 + g) * ld + jb + 4 + t];
-                const double b0 = A[(jb + t) * ld + c0 + g], b1 = A[(jb + 4 + t) * ld + c0 + g];
-                double *cp = A + (r0 + g) * ld + c0 + 2 * t;
-                double c0v = cp[0], c1v = cp[1];
-                dmma884(c0v, c1v, a0, b0);
-                dmma884(c0v, c1v, a1, b1);
-                cp[0] = c0v;
-                cp[1] = c1v;
-            }
-        }
-        __syncthreads();
+        if (warp == 0) solve_finish(P, S, m, tl, tg, lane, singular);
     }
-    if (warp != 0) return;
-    solve_finish(P, S, m, tl, tg, lane, singular);
 }
 
-// stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += sum(singular)
+#include "krig_chol.cuh"
+
+// stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += sum(singular),
+// [4] += targets the covariance-form kernel handed to the pivoted LU
 __global__ void stats_kernel(const unsigned *exam_n, const unsigned *cand_n, const int *sel_n,
-                             const unsigned *singular, int n, unsigned long long *stats)
+                             const unsigned *singular, int n, const unsigned *fail_count,
+                             unsigned long long *stats)
 {
+    if (fail_count && blockIdx.x == 0 && threadIdx.x == 0 && *fail_count)
+        atomicAdd(&stats[4], (unsigned long long)*fail_count);
     unsigned long long a = 0, b = 0, c = 0, d = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         a += exam_n[i];
@@ -937,6 +961,55 @@ static int build_model(const KrigModel &km, Model &M)
     return STIF_OK;
 }
 
+__global__ void obs_interleave_kernel(const double *x, const double *y, const double *t,
+                                      const double *r, int64_t n, double4 *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double4(x[i], y[i], t[i], r[i]);
+}
+
+// Host: decide whether the covariance-form (Cholesky) kernel may be tried for this model and
+// fill its constants.  Returns the kernel variant (CHOL_*) or -1 for "pivoted LU only".
+static int chol_plan(const KrigModel &km, const Model &M, int flags, CholParams &X)
+{
+    memset(&X, 0, sizeof(X));
+    if (flags & STIF_KRIG_FORCE_LU) return -1;
+    const bool use_s = km.st_model != STIF_ST_METRIC;
+    const bool use_t = use_s;
+    const bool use_m = km.st_model == STIF_ST_METRIC || km.st_model == STIF_ST_SUM_METRIC;
+    auto ok = [](double r, double c0, double b) {
+        return r > 0.0 && isfinite(r) && c0 >= 0.0 && isfinite(c0) && b >= 0.0 && isfinite(b);
+    };
+    bool valid = (km.st_model == STIF_ST_SUM || km.st_model == STIF_ST_METRIC ||
+                  km.st_model == STIF_ST_SUM_METRIC);
+    if (use_s) valid = valid && ok(M.rs, M.c0s, M.bs);
+    if (use_t) valid = valid && ok(M.rt, M.c0t, M.bt);
+    if (use_m) valid = valid && ok(M.rm, M.c0m, M.bm) && M.ani2 >= 0.0 && isfinite(M.ani2);
+    if (!valid && !(flags & STIF_KRIG_TRY_CHOL)) return -1;
+    const double ss = M.bs + M.c0s, stt = M.bt + M.c0t, sm = M.bm + M.c0m;   // marginal sills
+    double sill, nug;
+    switch (km.st_model) {
+    case STIF_ST_SUM: sill = ss + stt; nug = M.bs + M.bt; break;
+    case STIF_ST_PRODUCT: sill = ss * stt; nug = M.bs * M.bt; break;
+    case STIF_ST_PRODUCT_SUM: sill = M.k * (ss * stt) + ss * stt; nug = M.k * (M.bs * M.bt) + M.bs * M.bt; break;
+    case STIF_ST_METRIC: sill = sm; nug = M.bm; break;
+    default: sill = (ss + stt) + sm; nug = (M.bs + M.bt) + M.bm; break;
+    }
+    if (!(isfinite(sill) && isfinite(nug) && sill - nug > 0.0)) return -1;
+    X.csill = sill;
+    X.cdiag = sill - nug;
+    X.tol = 1e-10 * X.cdiag;
+    const bool sph = valid && (!use_s || M.ks == STIF_M_SPHERICAL) && (!use_t || M.kt == STIF_M_SPHERICAL) &&
+                     (!use_m || M.km == STIF_M_SPHERICAL);
+    if (!sph) return CHOL_GENERIC;
+    X.is = M.is; X.it = M.it; X.im = M.im;
+    X.ncs = -M.c0s; X.nct = -M.c0t; X.ncm = -M.c0m;
+    X.ani2 = M.ani2;
+    X.cb = sill - nug;
+    return km.st_model == STIF_ST_SUM ? CHOL_SUM_SPH
+         : km.st_model == STIF_ST_METRIC ? CHOL_METRIC_SPH : CHOL_SUM_METRIC_SPH;
+}
+
 }  // namespace krig
 }  // namespace stif
 
@@ -947,7 +1020,7 @@ namespace {
 
 enum Scratch {
     S_GRIDHDR = 0, S_OKEYS, S_OIDX, S_OKEYS_S, S_OIDX_S, S_CUB, S_OBS_SORTED, S_CELL_START,
-    S_TKEYS, S_TFLAGS, S_SEL_IDX, S_SEL_GAMMA, S_STAGE, S_EVAL
+    S_TKEYS, S_TFLAGS, S_SEL_IDX, S_SEL_GAMMA, S_STAGE, S_EVAL, S_FAIL
 };
 
 int check_ctx(stif_ctx *c, const char *who)
@@ -1037,6 +1110,12 @@ extern "C" int stif_kriging_set_obs(stif_ctx *c, const double *x, const double *
         STIF_CUDA(cudaMemcpyAsync(d + 2 * n, t, bytes, kind, c->stream));
         STIF_CUDA(cudaMemcpyAsync(d + 3 * n, resid, bytes, kind, c->stream));
     }
+    STIF_TRY(c->k_obs4.reserve(sizeof(double4) * (size_t)(n > 0 ? n : 1)));
+    if (n > 0) {
+        obs_interleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+            d, d + n, d + 2 * n, d + 3 * n, n, c->k_obs4.as<double4>());
+        STIF_CUDA(cudaGetLastError());
+    }
     STIF_CUDA(cudaStreamSynchronize(c->stream));
     c->n_obs = n;
     c->grid_nobs = -1;  // invalidate the grid
@@ -1125,8 +1204,8 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     }
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
     c->last_stream = st;
-    STIF_TRY(c->k_stats.reserve(4 * sizeof(unsigned long long)));
-    STIF_CUDA(cudaMemsetAsync(c->k_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    STIF_TRY(c->k_stats.reserve(8 * sizeof(unsigned long long)));
+    STIF_CUDA(cudaMemsetAsync(c->k_stats.p, 0, 8 * sizeof(unsigned long long), st));
     STIF_CUDA(cudaEventRecord(c->ev[0], st));
     c->n_phase = 3;
     if (n_targets == 0) {
@@ -1145,6 +1224,14 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     const int cta_doubles = nr_pad * ld + 5 * (k + 1) + 1 + 4 + (k + 2) / 2 + 1;
     const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
+    CholParams CX;
+    const int chol_var = chol_plan(c->model, M, flags, CX);
+    CX.obs4 = c->k_obs4.as<double4>();
+    c->k_chol_enabled = chol_var >= 0 ? 1 : 0;
+    const int chol_nt = (k + 2 + 7) / 8, chol_kp = (k + 1) & ~1;
+    const size_t chol_smem = sizeof(double) * ((size_t)chol_nt * (chol_nt + 1) / 2 * 64 + 5 * (size_t)chol_kp) +
+                             sizeof(unsigned) * (size_t)chol_kp;
+
     // chunk so that the selection scratch stays below ~16 GB
     const size_t per_target = (size_t)k * 12 + 32;
     int64_t chunk = (int64_t)((16ull << 30) / per_target);
@@ -1154,6 +1241,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     STIF_TRY(c->k_scratch[S_TFLAGS].reserve(4 * 4 * (size_t)chunk));
     STIF_TRY(c->k_scratch[S_SEL_IDX].reserve(4 * (size_t)chunk * k));
     STIF_TRY(c->k_scratch[S_SEL_GAMMA].reserve(8 * (size_t)chunk * k));
+    STIF_TRY(c->k_scratch[S_FAIL].reserve(4 * (size_t)(chunk + 1)));
     unsigned *tkeys = c->k_scratch[S_TKEYS].as<unsigned>();
     unsigned *tidx = tkeys + chunk, *tkeys_s = tidx + chunk, *tidx_s = tkeys_s + chunk;
     int *sel_n = c->k_scratch[S_TFLAGS].as<int>();
@@ -1222,13 +1310,56 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         QP.idx_out = idx_out;
         QP.nused_out = n_used_out;
         QP.singular = singular;
+        QP.count = nullptr;
+        // ---- covariance-form Cholesky (valid models), then the pivoted LU for the rest ----
+        unsigned *fail_list = c->k_scratch[S_FAIL].as<unsigned>();
+        unsigned *fail_count = fail_list + chunk;
+        if (chol_var >= 0) {
+            STIF_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(unsigned), st));
+            CX.fail_list = fail_list;
+            CX.fail_count = fail_count;
+            QP.count = nullptr;
+#define STIF_CHOL(VAR_, ZR_)                                                                       \
+    do {                                                                                           \
+        auto kern = solve_chol_kernel<VAR_, ZR_>;                                                  \
+        STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                       (int)chol_smem));                                           \
+        int occ = 0;                                                                               \
+        STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, chol_smem));       \
+        if (occ < 1) occ = 1;                                                                      \
+        int64_t gsz = (int64_t)occ * c->sm_count;                                                  \
+        if (gsz > nc) gsz = nc;                                                                    \
+        kern<<<(unsigned)gsz, 32, chol_smem, st>>>(QP, CX);                                        \
+    } while (0)
+#define STIF_CHOL_Z(VAR_)                                                                          \
+    do {                                                                                           \
+        if (k <= 64) STIF_CHOL(VAR_, 2);                                                           \
+        else STIF_CHOL(VAR_, 4);                                                                   \
+    } while (0)
+            switch (chol_var) {
+            case CHOL_SUM_SPH: STIF_CHOL_Z(CHOL_SUM_SPH); break;
+            case CHOL_METRIC_SPH: STIF_CHOL_Z(CHOL_METRIC_SPH); break;
+            case CHOL_SUM_METRIC_SPH: STIF_CHOL_Z(CHOL_SUM_METRIC_SPH); break;
+            default: STIF_CHOL_Z(CHOL_GENERIC); break;
+            }
+#undef STIF_CHOL_Z
+#undef STIF_CHOL
+            STIF_CUDA(cudaGetLastError());
+            QP.order = fail_list;
+            QP.count = fail_count;
+        }
         {
-            const dim3 grid(nc);
 #define STIF_SOLVE(WPT_)                                                                           \
     do {                                                                                           \
-        STIF_CUDA(cudaFuncSetAttribute(solve_blk_kernel<WPT_>,                                     \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem)); \
-        solve_blk_kernel<WPT_><<<grid, WPT_ * 32, solve_smem, st>>>(QP, nr_pad, nc_pad);           \
+        auto kern = solve_blk_kernel<WPT_>;                                                        \
+        STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                       (int)solve_smem));                                          \
+        int occ = 0;                                                                               \
+        STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPT_ * 32, solve_smem)); \
+        if (occ < 1) occ = 1;                                                                      \
+        int64_t gsz = (int64_t)occ * c->sm_count;                                                  \
+        if (gsz > nc) gsz = nc;                                                                    \
+        kern<<<(unsigned)gsz, WPT_ * 32, solve_smem, st>>>(QP, nr_pad, nc_pad);                    \
     } while (0)
             if (k <= 16) STIF_SOLVE(1);
             else if (k <= 32) STIF_SOLVE(2);
@@ -1238,6 +1369,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         }
         STIF_CUDA(cudaGetLastError());
         stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,
+                                                 chol_var >= 0 ? fail_count : nullptr,
                                                  c->k_stats.as<unsigned long long>());
         STIF_CUDA(cudaGetLastError());
     }
@@ -1311,5 +1443,23 @@ extern "C" int stif_kriging_stats(stif_ctx *c, uint64_t out[4])
     unsigned long long h[4];
     STIF_CUDA(cudaMemcpy(h, c->k_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) out[i] = h[i];
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_solver_stats(stif_ctx *c, uint64_t out[2])
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_solver_stats"));
+    if (!out) {
+        set_error("stif_kriging_solver_stats: NULL argument");
+        return STIF_EINVAL;
+    }
+    out[0] = 0;
+    out[1] = (uint64_t)c->k_chol_enabled;
+    if (!c->k_stats.p) return STIF_OK;
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    STIF_CUDA(cudaStreamSynchronize(st));
+    unsigned long long h = 0;
+    STIF_CUDA(cudaMemcpy(&h, c->k_stats.as<unsigned long long>() + 4, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h;
     return STIF_OK;
 }

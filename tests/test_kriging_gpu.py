@@ -30,12 +30,16 @@ def synth(n_obs, n_tgt, seed=20261020, extent=300.0):
     return space, t, z, tsp, tt
 
 
-def gpu_predict(ctx, space, t, z, tsp, tt, models, params, min_pts, k, smax, tmax, leave=None, f32=True):
+SOLVER_FLAGS = {"auto": 0, "lu": _native.KRIG_FORCE_LU, "chol": _native.KRIG_TRY_CHOL}
+
+
+def gpu_predict(ctx, space, t, z, tsp, tt, models, params, min_pts, k, smax, tmax, leave=None, f32=True,
+                solver="auto"):
     x, y = _native.split_space(space)
     ctx.kriging_set_obs(x, y, t, z)
     ctx.kriging_set_model(*models, params)
     tx, ty = _native.split_space(tsp)
-    flags = _native.KRIG_F32_STORAGE if f32 else 0
+    flags = (_native.KRIG_F32_STORAGE if f32 else 0) | SOLVER_FLAGS[solver]
     mean, std, w, g, idx, nused = ctx.kriging_predict_host(tx, ty, tt, min_pts, k, smax, tmax, leave_out=leave,
                                                            flags=flags, want_weights=True)
     return dict(mean=mean, std=std, w=w, gamma=g, idx=idx, n_used=nused)
@@ -75,6 +79,7 @@ def compare(g, o, z, f32):
         assert np.all(dv <= RTOL * vscale[nonsing]), dv.max()
 
 
+@pytest.mark.parametrize("solver", ["auto", "lu", "chol"])
 @pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("models,params,k", [
     (SUM_METRIC, P_SUM_METRIC, 50),
@@ -84,11 +89,37 @@ def compare(g, o, z, f32):
     (("metric", "spherical", "spherical", "spherical"), [500, 1.0, 0.05, 5.0], 33),
     (("product", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 8),
 ])
-def test_models(ctx, models, params, k, f32):
+def test_models(ctx, models, params, k, f32, solver):
     space, t, z, tsp, tt = synth(20000, 400)
-    g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=f32)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=f32, solver=solver)
     o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32_storage=f32)
     compare(g, o, z, f32)
+    ss = ctx.kriging_solver_stats()
+    valid = models[0] in ("sum", "metric", "sum_metric")
+    if solver == "lu":
+        assert not ss["cholesky_enabled"]
+    elif solver == "chol" or valid:
+        assert ss["cholesky_enabled"]
+        if models[0] in ("metric", "sum_metric"):
+            # valid variogram, distinct points: positive definite, nothing handed to the LU
+            assert ss["cholesky_to_lu"] == 0
+    else:
+        assert not ss["cholesky_enabled"]       # product / product_sum: pivoted LU only
+
+
+def test_cholesky_hands_indefinite_systems_to_lu(ctx):
+    """product_sum is not a valid variogram: forcing the covariance-form kernel must detect the
+    non-positive pivots and give the same answers through the LU."""
+    space, t, z, tsp, tt = synth(20000, 300, seed=21)
+    g1 = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 30.0, 30.0, f32=False,
+                     solver="chol")
+    ss = ctx.kriging_solver_stats()
+    assert ss["cholesky_enabled"] and ss["cholesky_to_lu"] > 0
+    g2 = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 30.0, 30.0, f32=False,
+                     solver="lu")
+    o = ok.predict(space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 30.0, 30.0, f32_storage=False)
+    compare(g1, o, z, False)
+    compare(g2, o, z, False)
 
 
 def test_k100_many_candidates(ctx):
@@ -178,15 +209,19 @@ def test_errors(ctx):
     c2.close()
 
 
-@pytest.mark.parametrize("k", [1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, 55, 63, 64, 65, 96, 127, 128])
-def test_every_kernel_variant(ctx, k):
+@pytest.mark.parametrize("solver", ["auto", "lu"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 46, 47, 48, 55, 62, 63, 64, 65, 96, 127,
+                               128])
+def test_every_kernel_variant(ctx, k, solver):
     """max_kriging_points selects the (warps per target, panel count) variant of the solve
     kernel and the padding of the system; sweep the boundaries."""
     space, t, z, tsp, tt = synth(30000, 96, seed=100 + k, extent=200.0)
-    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, k, 40.0, 40.0, f32=False)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, k, 40.0, 40.0, f32=False,
+                    solver=solver)
     o = ok.predict(space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, k, 40.0, 40.0, f32_storage=False)
     assert o["n_cand"].max() > k
     compare(g, o, z, False)
+    assert ctx.kriging_solver_stats()["cholesky_enabled"] == (solver == "auto")
 
 
 def test_fewer_observations_than_k(ctx):
@@ -208,6 +243,7 @@ def test_duplicate_observations_are_flagged_not_fatal(ctx):
     g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 20, 30.0, 30.0, f32=False)
     st = ctx.kriging_stats()
     assert st["targets_singular"] > 0
+    assert ctx.kriging_solver_stats()["cholesky_to_lu"] >= st["targets_singular"]
     used = g["n_used"] > 0
     assert np.all(np.isfinite(g["mean"][used]))
     assert np.allclose(g["w"][used].sum(axis=1), 1.0, atol=1e-4)

@@ -34,6 +34,7 @@ struct CholParams {
     double tol;              // pivot tolerance
     // all-spherical fast path: C = cb + ncs q(h is) + nct q(t it) + ncm q(d im)
     double is, it, im, ncs, nct, ncm, cb, ani2;
+    int clamp;               // 1: a neighbour pair can lie beyond a marginal's range
     unsigned *fail_list;     // targets (chunk-local ids) that need the pivoted LU
     unsigned *fail_count;
 };
@@ -58,10 +59,11 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     return __fma_rn(y, q, y);
 }
 
-// sqrt(x) to <= 1 ulp for x >= 0 (coupled Newton on g ~ sqrt x, h ~ 1/(2 sqrt x)); 0 -> ~1e-140.
+// sqrt(x) to <= 1 ulp for x >= 0 (coupled Newton on g ~ sqrt x, h ~ 1/(2 sqrt x)); the tiny
+// offset keeps x = 0 (coincident stations) away from 0 * inf: sqrt(0) -> 1e-145.
 __device__ __forceinline__ double sqrt_fast(double x)
 {
-    x = fmax(x, 1e-280);
+    x = x + 1e-290;
     const double y = rsqrt_approx(x);
     double g = x * y;
     double h = 0.5 * y;
@@ -72,34 +74,36 @@ __device__ __forceinline__ double sqrt_fast(double x)
     return __fma_rn(d, h, g);
 }
 
-// spherical shape q(u) = 1.5 u - 0.5 u^3 for u <= 1, 1 beyond (variogram_models.py:40-44, r > 0)
+// spherical shape q(u) = 1.5 u - 0.5 u^3 for u <= 1, 1 beyond (variogram_models.py:40-44, r > 0).
+// CLAMP = false when the search radii guarantee u <= 1 for every neighbour pair.
+template <bool CLAMP>
 __device__ __forceinline__ double sph_q(double u)
 {
-    u = fmin(u, 1.0);
+    if (CLAMP) u = (u < 1.0) ? u : 1.0;
     return u * __fma_rn(-0.5, u * u, 1.5);
 }
 
-template <int VAR>
+template <int VAR, bool CLAMP>
 __device__ __forceinline__ double cov_entry(const Model &M, const CholParams &X, double d2, double lt)
 {
     if (VAR == CHOL_SUM_SPH) {
         const double h = sqrt_fast(d2);
-        return __fma_rn(X.nct, sph_q(lt * X.it), __fma_rn(X.ncs, sph_q(h * X.is), X.cb));
+        return __fma_rn(X.nct, sph_q<CLAMP>(lt * X.it), __fma_rn(X.ncs, sph_q<CLAMP>(h * X.is), X.cb));
     } else if (VAR == CHOL_METRIC_SPH) {
         const double dm = sqrt_fast(__fma_rn(X.ani2 * lt, lt, d2));
-        return __fma_rn(X.ncm, sph_q(dm * X.im), X.cb);
+        return __fma_rn(X.ncm, sph_q<CLAMP>(dm * X.im), X.cb);
     } else if (VAR == CHOL_SUM_METRIC_SPH) {
         const double h = sqrt_fast(d2);
         const double dm = sqrt_fast(__fma_rn(X.ani2 * lt, lt, d2));
-        double c = __fma_rn(X.ncs, sph_q(h * X.is), X.cb);
-        c = __fma_rn(X.nct, sph_q(lt * X.it), c);
-        return __fma_rn(X.ncm, sph_q(dm * X.im), c);
+        double c = __fma_rn(X.ncs, sph_q<CLAMP>(h * X.is), X.cb);
+        c = __fma_rn(X.nct, sph_q<CLAMP>(lt * X.it), c);
+        return __fma_rn(X.ncm, sph_q<CLAMP>(dm * X.im), c);
     } else {
         return X.csill - gamma_st(M, sqrt(d2), lt);
     }
 }
 
-__device__ __forceinline__ int chol_swz(int r) { return (((r >> 1) & 1) << 1) | ((r >> 2) & 1); }
+__host__ __device__ constexpr int chol_swz(int r) { return (((r >> 1) & 1) << 1) | ((r >> 2) & 1); }
 __device__ __forceinline__ int chol_tri(int I) { return (I * (I + 1)) >> 1; }
 // offset (in doubles) of entry (r, c), c <= r (or any entry of a stored tile)
 __device__ __forceinline__ int chol_off(int r, int c)
@@ -107,30 +111,70 @@ __device__ __forceinline__ int chol_off(int r, int c)
     const int ri = r & 7, ci = c & 7;
     return (chol_tri(r >> 3) + (c >> 3)) * 64 + ri * 8 + ((((ci >> 1) ^ chol_swz(ri)) << 1) | (ci & 1));
 }
-// 16-byte chunk ch (0..3) of row ri of a tile
-__device__ __forceinline__ double2 *chol_chunk(double *tile, int ri, int ch)
+
+// per-lane constants (computed once per kernel)
+struct CholLane {
+    int lane;
+    int q8, l8, ls;     // row ownership: rows lane + 32 slot; q8 = lane >> 3, l8 = (lane & 7) * 8, ls = swz(lane & 7)
+    int foA, foB;       // mma fragment element (row g, column t) / (row g, column 4 + t) of a tile
+    int co;             // C fragment (row g, columns 2t, 2t+1)
+    int t;
+};
+
+// ---- C = c - gamma(D_s, D_t), strictly lower triangle; pair e = a(a-1)/2 + b, b < a ----
+template <int VAR, bool CLAMP>
+__device__ __forceinline__ void chol_assemble(double *T, const double2 *pxy, const double *pt, int m,
+                                              const Model &M, const CholParams &X, int lane)
 {
-    return reinterpret_cast<double2 *>(tile + ri * 8 + ((ch ^ chol_swz(ri)) << 1));
+    const int npairs = (m * (m - 1)) >> 1;
+    int a = 1, b = lane;
+    int rowoff = 8, sa = chol_swz(1);
+    double2 pa = pxy[1];
+    double ta = pt[1];
+    for (int e = lane; e < npairs; e += 32) {
+        if (b >= a) {
+            do {
+                b -= a;
+                ++a;
+            } while (b >= a);
+            rowoff = chol_tri(a >> 3) * 64 + (a & 7) * 8;
+            sa = chol_swz(a & 7);
+            pa = pxy[a];
+            ta = pt[a];
+        }
+        const double2 pb = pxy[b];
+        const double dx = pa.x - pb.x, dy = pa.y - pb.y;
+        const double d2 = __fma_rn(dy, dy, dx * dx);
+        const double lt = fabs(ta - pt[b]);
+        T[rowoff + ((b >> 3) << 6) + ((((b >> 1) & 3) ^ sa) << 1) + (b & 1)] = cov_entry<VAR, CLAMP>(M, X, d2, lt);
+        b += 32;
+    }
 }
 
-// Factor the 4-column panel starting at column c0 (tile column Pt, half h) and forward-substitute
-// the rows below.  Returns true if a pivot failed.
-__device__ __forceinline__ bool chol_panel(double *T, int c0, int m, int nrow, double tol, int lane)
+// Factor the 4-column panel at columns 8 Pt + 4 H .. +3 and forward-substitute the rows below.
+// Every lane factors the 4x4 diagonal block redundantly in registers; lane 0 writes it back
+// (1/L_ii on the diagonal); lanes own rows lane + 32 slot.  Returns true if a pivot failed.
+template <int H>
+__device__ __forceinline__ bool chol_panel(double *T, int Pt, int m, int nrow, double tol, const CholLane &L)
 {
-    const int Pt = c0 >> 3, h = (c0 >> 2) & 1;
+    const int c0 = 8 * Pt + 4 * H;
     double *Td = T + (chol_tri(Pt) + Pt) * 64;
-    const int r0 = 4 * h;
-    const double2 u0 = *chol_chunk(Td, r0 + 0, 2 * h);
-    const double2 u1 = *chol_chunk(Td, r0 + 1, 2 * h);
-    const double2 u2 = *chol_chunk(Td, r0 + 2, 2 * h), v2 = *chol_chunk(Td, r0 + 2, 2 * h + 1);
-    const double2 u3 = *chol_chunk(Td, r0 + 3, 2 * h), v3 = *chol_chunk(Td, r0 + 3, 2 * h + 1);
+    constexpr int r0 = 4 * H;
+    // 16-byte chunk ch of row ri of the tile (swizzle is a compile-time constant here)
+#define CHUNK(ri, ch) reinterpret_cast<double2 *>(Td + (ri) * 8 + ((((ch)) ^ chol_swz(ri)) << 1))
+    const double2 u0 = *CHUNK(r0 + 0, 2 * H);
+    const double2 u1 = *CHUNK(r0 + 1, 2 * H);
+    const double2 u2 = *CHUNK(r0 + 2, 2 * H), v2 = *CHUNK(r0 + 2, 2 * H + 1);
+    const double2 u3 = *CHUNK(r0 + 3, 2 * H), v3 = *CHUNK(r0 + 3, 2 * H + 1);
     double d00 = u0.x, d10 = u1.x, d11 = u1.y, d20 = u2.x, d21 = u2.y, d22 = v2.x;
     double d30 = u3.x, d31 = u3.y, d32 = v3.x, d33 = v3.y;
-    __syncwarp();              // every lane holds the block before its rows are overwritten
+    __syncwarp();              // every lane holds the block before it is overwritten
     const int ncol = m - c0;   // real columns in this panel (>= 1); the others pass through
-    if (ncol < 4) { d30 = 0.0; d31 = 0.0; d32 = 0.0; d33 = 1.0; }
-    if (ncol < 3) { d20 = 0.0; d21 = 0.0; d22 = 1.0; }
-    if (ncol < 2) { d10 = 0.0; d11 = 1.0; }
+    if (ncol < 4) {
+        d30 = 0.0; d31 = 0.0; d32 = 0.0; d33 = 1.0;
+        if (ncol < 3) { d20 = 0.0; d21 = 0.0; d22 = 1.0; }
+        if (ncol < 2) { d10 = 0.0; d11 = 1.0; }
+    }
     bool fail = !(d00 > tol);
     const double i0 = rsqrt_fast(d00);
     const double l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
@@ -153,29 +197,148 @@ __device__ __forceinline__ bool chol_panel(double *T, int c0, int m, int nrow, d
     fail |= !(d33 > tol);
     const double i3 = rsqrt_fast(d33);
     if (fail) return true;
-
-    for (int r = c0 + lane; r < nrow; r += 32) {
-        double *tile = T + (chol_tri(r >> 3) + Pt) * 64;
-        double2 *p0 = chol_chunk(tile, r & 7, 2 * h), *p1 = chol_chunk(tile, r & 7, 2 * h + 1);
-        const double2 q0 = *p0, q1 = *p1;
-        double x0 = q0.x * i0;
-        double x1 = __fma_rn(-x0, l10, q0.y) * i1;
-        double x2 = __fma_rn(-x1, l21, __fma_rn(-x0, l20, q1.x)) * i2;
-        double x3 = __fma_rn(-x2, l32, __fma_rn(-x1, l31, __fma_rn(-x0, l30, q1.y))) * i3;
-        const int i = r - c0;
-        if (i < 4) {   // rows of the diagonal block: 1/L_ii on the diagonal, upper part untouched
-            if (i == 0) { x0 = i0; x1 = q0.y; x2 = q1.x; x3 = q1.y; }
-            if (i == 1) { x1 = i1; x2 = q1.x; x3 = q1.y; }
-            if (i == 2) { x2 = i2; x3 = q1.y; }
-            if (i == 3) { x3 = i3; }
+    if (L.lane == 0) {         // the real rows of the diagonal block
+        CHUNK(r0 + 0, 2 * H)->x = i0;
+        if (ncol >= 2) *CHUNK(r0 + 1, 2 * H) = make_double2(l10, i1);
+        if (ncol >= 3) {
+            *CHUNK(r0 + 2, 2 * H) = make_double2(l20, l21);
+            CHUNK(r0 + 2, 2 * H + 1)->x = i2;
         }
-        *p0 = make_double2(x0, x1);
-        *p1 = make_double2(x2, x3);
+        if (ncol >= 4) {
+            *CHUNK(r0 + 3, 2 * H) = make_double2(l30, l31);
+            *CHUNK(r0 + 3, 2 * H + 1) = make_double2(l32, i3);
+        }
+    }
+#undef CHUNK
+    // rows below the real part of the block (pass-through columns have i = 1, l = 0)
+    const int rstart = c0 + (ncol < 4 ? ncol : 4);
+    const int chA = ((2 * H) ^ L.ls) << 1, chB = ((2 * H + 1) ^ L.ls) << 1;
+    for (int slot = rstart >> 5; slot <= ((nrow - 1) >> 5); ++slot) {
+        const int r = L.lane + 32 * slot;
+        if (r >= rstart && r < nrow) {
+            double *row = T + (chol_tri(L.q8 + 4 * slot) + Pt) * 64 + L.l8;
+            double2 *p0 = reinterpret_cast<double2 *>(row + chA), *p1 = reinterpret_cast<double2 *>(row + chB);
+            const double2 q0 = *p0, q1 = *p1;
+            const double x0 = q0.x * i0;
+            const double x1 = __fma_rn(-x0, l10, q0.y) * i1;
+            const double x2 = __fma_rn(-x1, l21, __fma_rn(-x0, l20, q1.x)) * i2;
+            const double x3 = __fma_rn(-x2, l32, __fma_rn(-x1, l31, __fma_rn(-x0, l30, q1.y))) * i3;
+            *p0 = make_double2(x0, x1);
+            *p1 = make_double2(x2, x3);
+        }
     }
     return false;
 }
 
+// tiles (I0 .. I0+NTI-1, Jc) -= sum over the 2 Jc earlier panels of L(I, q) L(Jc, q)^T
+template <int NTI>
+__device__ __forceinline__ void chol_update_group(double *T, int I0, int Jc, const CholLane &L)
+{
+    double2 acc[NTI];
+    const double *pa[NTI];
+#pragma unroll
+    for (int u = 0; u < NTI; ++u) {
+        acc[u] = make_double2(0.0, 0.0);
+        pa[u] = T + chol_tri(I0 + u) * 64;
+    }
+    const double *pb = T + chol_tri(Jc) * 64;
+    for (int qq = 0; qq < Jc; ++qq) {
+        const double bA = pb[L.foA], bB = pb[L.foB];
+#pragma unroll
+        for (int u = 0; u < NTI; ++u) {
+            const double aA = pa[u][L.foA], aB = pa[u][L.foB];
+            dmma884(acc[u].x, acc[u].y, aA, bA);
+            dmma884(acc[u].x, acc[u].y, aB, bB);
+            pa[u] += 64;
+        }
+        pb += 64;
+    }
+#pragma unroll
+    for (int u = 0; u < NTI; ++u) {     // pa[u] now points at tile (I0 + u, Jc)
+        double2 *cp = reinterpret_cast<double2 *>(const_cast<double *>(pa[u]) + L.co);
+        double2 cv = *cp;
+        cv.x -= acc[u].x;
+        cv.y -= acc[u].y;
+        *cp = cv;
+    }
+}
+
+// columns 4..7 of tiles (I0 .. I0+NTI-1, Jc) -= left panel of the same tile column
+template <int NTI>
+__device__ __forceinline__ void chol_half_group(double *T, int I0, int Jc, const CholLane &L)
+{
+    const double bA = T[(chol_tri(Jc) + Jc) * 64 + L.foA];
+    double2 acc[NTI];
+    double *pc[NTI];
+#pragma unroll
+    for (int u = 0; u < NTI; ++u) {
+        pc[u] = T + (chol_tri(I0 + u) + Jc) * 64;
+        acc[u] = make_double2(0.0, 0.0);
+        dmma884(acc[u].x, acc[u].y, pc[u][L.foA], bA);
+    }
+    if (L.t >= 2) {
+#pragma unroll
+        for (int u = 0; u < NTI; ++u) {
+            double2 *cp = reinterpret_cast<double2 *>(pc[u] + L.co);
+            double2 cv = *cp;
+            cv.x -= acc[u].x;
+            cv.y -= acc[u].y;
+            *cp = cv;
+        }
+    }
+}
+
 constexpr int CHOL_G = 8;   // tiles of one tile column updated together (accumulators in registers)
+
+#define CHOL_DISPATCH_NTI(FN, n_, ...)                                                             \
+    switch (n_) {                                                                                  \
+    case 1: FN<1>(__VA_ARGS__); break;                                                             \
+    case 2: FN<2>(__VA_ARGS__); break;                                                             \
+    case 3: FN<3>(__VA_ARGS__); break;                                                             \
+    case 4: FN<4>(__VA_ARGS__); break;                                                             \
+    case 5: FN<5>(__VA_ARGS__); break;                                                             \
+    case 6: FN<6>(__VA_ARGS__); break;                                                             \
+    case 7: FN<7>(__VA_ARGS__); break;                                                             \
+    default: FN<8>(__VA_ARGS__); break;                                                            \
+    }
+
+// One tile row (8 steps) of the back substitution L' w = z; NS = column slots that can still be
+// below the diagonal.  z[i] belongs to column lane + 32 i; w_j goes to sol[j].
+template <int ZR, int NS>
+__device__ __forceinline__ void chol_backsub_row(const double *T, double *sol, double (&z)[ZR], int J,
+                                                 int m, const CholLane &L)
+{
+    const double *rowT = T + chol_tri(J) * 64;
+    // lane's column offsets for the 4 possible row swizzles
+    int lo[NS][4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int c = L.lane + 32 * i;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) lo[i][s] = (c >> 3) * 64 + (((((c & 7) >> 1) ^ s) << 1) | (c & 1));
+    }
+    const int zi = (8 * J) >> 5;          // slot that owns this tile row's columns
+    const int src0 = (8 * J) & 31;
+#pragma unroll
+    for (int jj = 7; jj >= 0; --jj) {
+        const int j = 8 * J + jj;
+        if (j >= m) continue;             // padding / right-hand-side rows of the last tile row
+        const int sj = chol_swz(jj);
+        const double dinv = rowT[J * 64 + jj * 8 + ((((jj >> 1) ^ sj) << 1) | (jj & 1))];
+        double zj = z[0];
+#pragma unroll
+        for (int i = 1; i < NS; ++i)
+            if (zi == i) zj = z[i];
+        zj = __shfl_sync(FULL, zj, src0 + jj);
+        const double wj = zj * dinv;
+        if (L.lane == 0) sol[j] = wj;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int c = L.lane + 32 * i;
+            if (c < j) z[i] = __fma_rn(-rowT[jj * 8 + lo[i][sj]], wj, z[i]);
+        }
+    }
+}
 
 template <int VAR, int ZR>
 __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParams X)
@@ -191,8 +354,18 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
     double *g0 = pt + kp, *rs = g0 + kp;
     unsigned *ids = reinterpret_cast<unsigned *>(rs + kp);
     double *sol = pt;                                   // pt is dead after the assembly
-    const int g = lane >> 2, t = lane & 3, sg = chol_swz(g);
-    const int co = g * 8 + ((t ^ sg) << 1);             // C fragment: row g, columns 2t, 2t+1
+    CholLane L;
+    {
+        const int g = lane >> 2, t = lane & 3, sg = chol_swz(g);
+        L.lane = lane;
+        L.q8 = lane >> 3;
+        L.l8 = (lane & 7) * 8;
+        L.ls = chol_swz(lane & 7);
+        L.foA = g * 8 + ((((t >> 1) ^ sg) << 1) | (t & 1));
+        L.foB = g * 8 + ((((2 + (t >> 1)) ^ sg) << 1) | (t & 1));
+        L.co = g * 8 + ((t ^ sg) << 1);
+        L.t = t;
+    }
 
     for (int slot = blockIdx.x; slot < P.n; slot += gridDim.x) {
         const unsigned tl = P.order[slot];
@@ -228,86 +401,31 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
             T[chol_off(m + 1, e)] = 1.0;
         }
         __syncwarp();
-        // ---- C = c - gamma(D_s, D_t), strictly lower triangle; pair e = a(a-1)/2 + b, b < a ----
-        {
-            const int npairs = (m * (m - 1)) >> 1;
-            int a = 1, b = lane;
-            for (int e = lane; e < npairs; e += 32) {
-                while (b >= a) {
-                    b -= a;
-                    ++a;
-                }
-                const double2 pa = pxy[a], pb = pxy[b];
-                const double dx = pa.x - pb.x, dy = pa.y - pb.y;
-                const double d2 = __fma_rn(dy, dy, dx * dx);
-                const double lt = fabs(pt[a] - pt[b]);
-                T[chol_off(a, b)] = cov_entry<VAR>(P.M, X, d2, lt);
-                b += 32;
-            }
+        if (m > 1) {
+            if (X.clamp) chol_assemble<VAR, true>(T, pxy, pt, m, P.M, X, lane);
+            else chol_assemble<VAR, false>(T, pxy, pt, m, P.M, X, lane);
         }
         __syncwarp();
         // ---- left-looking tiled Cholesky ----
         bool fail = false;
         const int ntc = (m + 7) >> 3;       // tile columns that hold real columns
-        for (int Jc = 0; Jc < ntc && !fail; ++Jc) {
+        for (int Jc = 0; Jc < ntc; ++Jc) {
             if (Jc > 0) {
-                // 1. tiles (I, Jc) -= sum_q L(I, q) L(Jc, q)^T over the 2 Jc earlier panels
-                const double *rowJ = T + chol_tri(Jc) * 64;
                 for (int I0 = Jc; I0 < nt; I0 += CHOL_G) {
-                    double2 acc[CHOL_G];
-#pragma unroll
-                    for (int u = 0; u < CHOL_G; ++u) acc[u] = make_double2(0.0, 0.0);
-                    for (int q = 0; q < 2 * Jc; ++q) {
-                        // fragment element (row g, column 4 (q & 1) + t) of tile (., q >> 1)
-                        const int fo = (q >> 1) * 64 + g * 8 +
-                                       ((((2 * (q & 1) + (t >> 1)) ^ sg) << 1) | (t & 1));
-                        const double bf = rowJ[fo];
-#pragma unroll
-                        for (int u = 0; u < CHOL_G; ++u) {
-                            if (I0 + u < nt) {
-                                const double af = T[chol_tri(I0 + u) * 64 + fo];
-                                dmma884(acc[u].x, acc[u].y, af, bf);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < CHOL_G; ++u) {
-                        if (I0 + u < nt) {
-                            double2 *cp = reinterpret_cast<double2 *>(T + (chol_tri(I0 + u) + Jc) * 64 + co);
-                            double2 cv = *cp;
-                            cv.x -= acc[u].x;
-                            cv.y -= acc[u].y;
-                            *cp = cv;
-                        }
-                    }
+                    CHOL_DISPATCH_NTI(chol_update_group, nt - I0, T, I0, Jc, L);
                 }
                 __syncwarp();
             }
-            // 2. left panel
-            fail = chol_panel(T, 8 * Jc, m, nrow, X.tol, lane);
+            fail = chol_panel<0>(T, Jc, m, nrow, X.tol, L);
             __syncwarp();
             if (fail || 8 * Jc + 4 >= m) break;
-            // 3. right half of the tile column -= left panel
-            {
-                const int fo = Jc * 64 + g * 8 + ((((t >> 1) ^ sg) << 1) | (t & 1));
-                const double bf = T[chol_tri(Jc) * 64 + fo];
-                for (int I = Jc; I < nt; ++I) {
-                    const double af = T[chol_tri(I) * 64 + fo];
-                    double c0v = 0.0, c1v = 0.0;
-                    dmma884(c0v, c1v, af, bf);
-                    if (t >= 2) {
-                        double2 *cp = reinterpret_cast<double2 *>(T + (chol_tri(I) + Jc) * 64 + co);
-                        double2 cv = *cp;
-                        cv.x -= c0v;
-                        cv.y -= c1v;
-                        *cp = cv;
-                    }
-                }
+            for (int I0 = Jc; I0 < nt; I0 += CHOL_G) {
+                CHOL_DISPATCH_NTI(chol_half_group, nt - I0, T, I0, Jc, L);
             }
             __syncwarp();
-            // 4. right panel
-            fail = chol_panel(T, 8 * Jc + 4, m, nrow, X.tol, lane);
+            fail = chol_panel<1>(T, Jc, m, nrow, X.tol, L);
             __syncwarp();
+            if (fail) break;
         }
         if (fail) {   // not positive definite / singular: the pivoted LU takes this target
             if (lane == 0) X.fail_list[atomicAdd(X.fail_count, 1u)] = tl;
@@ -338,37 +456,20 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
 #pragma unroll
             for (int i = 0; i < ZR; ++i) z[i] = __fma_rn(lam, yu[i], z[i]);
         }
-        // ---- back substitution L' w = z, column oriented; lane owns columns lane + 32 i ----
-        {
-            int cofs[ZR], cch[ZR];
-#pragma unroll
-            for (int i = 0; i < ZR; ++i) {
-                const int c = lane + 32 * i;
-                cofs[i] = (c >> 3) * 64 + (c & 1);
-                cch[i] = (c & 7) >> 1;
+        __syncwarp();          // pt (aliased by sol) is dead, rows m / m+1 have been read
+        // ---- back substitution L' w = z by tile rows (padding columns of the last one: z = 0,
+        //      their dinv entries are finite garbage-free pass-through values or unused) ----
+        for (int J = ntc - 1; J >= 0; --J) {
+            const int ns = ((8 * J + 7) >> 5) + 1;
+            if (ZR == 2) {
+                if (ns == 1) chol_backsub_row<ZR, 1>(T, sol, z, J, m, L);
+                else chol_backsub_row<ZR, 2>(T, sol, z, J, m, L);
+            } else {
+                if (ns == 1) chol_backsub_row<ZR, 1>(T, sol, z, J, m, L);
+                else if (ns == 2) chol_backsub_row<ZR, 2>(T, sol, z, J, m, L);
+                else if (ns == 3) chol_backsub_row<ZR, 3>(T, sol, z, J, m, L);
+                else chol_backsub_row<ZR, 4>(T, sol, z, J, m, L);
             }
-            for (int j = m - 1; j >= 0; --j) {
-                const int rowb = chol_tri(j >> 3) * 64 + (j & 7) * 8, sj = chol_swz(j & 7);
-                const double dinv = T[chol_off(j, j)];
-                double zj = z[0];
-#pragma unroll
-                for (int i = 1; i < ZR; ++i)
-                    if ((j >> 5) == i) zj = z[i];
-                zj = __shfl_sync(FULL, zj, j & 31);
-                const double wj = zj * dinv;
-#pragma unroll
-                for (int i = 0; i < ZR; ++i) {
-                    const int c = lane + 32 * i;
-                    if (c < j) z[i] = __fma_rn(-T[rowb + cofs[i] + ((cch[i] ^ sj) << 1)], wj, z[i]);
-                    else if (c == j) z[i] = wj;
-                }
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < ZR; ++i) {
-            const int c = lane + 32 * i;
-            if (c < m) sol[c] = z[i];
         }
         __syncwarp();
         solve_epilogue(P, sol, g0, ids, rs, reinterpret_cast<double *>(pxy),

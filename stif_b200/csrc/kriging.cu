@@ -970,7 +970,8 @@ __global__ void obs_interleave_kernel(const double *x, const double *y, const do
 
 // Host: decide whether the covariance-form (Cholesky) kernel may be tried for this model and
 // fill its constants.  Returns the kernel variant (CHOL_*) or -1 for "pivoted LU only".
-static int chol_plan(const KrigModel &km, const Model &M, int flags, CholParams &X)
+static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax, double tmax,
+                     CholParams &X)
 {
     memset(&X, 0, sizeof(X));
     if (flags & STIF_KRIG_FORCE_LU) return -1;
@@ -1006,6 +1007,16 @@ static int chol_plan(const KrigModel &km, const Model &M, int flags, CholParams 
     X.ncs = -M.c0s; X.nct = -M.c0t; X.ncm = -M.c0m;
     X.ani2 = M.ani2;
     X.cb = sill - nug;
+    // neighbour pairs are at most 2 smax apart in space and tmax in time (both inside the
+    // target's causal window); if every marginal's range covers that, q(u) needs no clamp
+    {
+        const double hmax = 2.0 * smax, dmax = sqrt(4.0 * smax * smax + M.ani2 * tmax * tmax);
+        bool noclamp = true;
+        if (use_s) noclamp = noclamp && hmax * (1.0 + 1e-9) <= M.rs;
+        if (use_t) noclamp = noclamp && tmax * (1.0 + 1e-9) <= M.rt;
+        if (use_m) noclamp = noclamp && dmax * (1.0 + 1e-9) <= M.rm;
+        X.clamp = noclamp ? 0 : 1;     // NaN / inf radii compare false -> clamp
+    }
     return km.st_model == STIF_ST_SUM ? CHOL_SUM_SPH
          : km.st_model == STIF_ST_METRIC ? CHOL_METRIC_SPH : CHOL_SUM_METRIC_SPH;
 }
@@ -1225,7 +1236,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
     CholParams CX;
-    const int chol_var = chol_plan(c->model, M, flags, CX);
+    const int chol_var = chol_plan(c->model, M, flags, smax, tmax, CX);
     CX.obs4 = c->k_obs4.as<double4>();
     c->k_chol_enabled = chol_var >= 0 ? 1 : 0;
     const int chol_nt = (k + 2 + 7) / 8, chol_kp = (k + 1) & ~1;

@@ -91,6 +91,7 @@ struct stif_ctx {
     // ---- kriging state ----
     int64_t n_obs = 0;
     stif::DevBuf k_obs;        // obs SoA (x, y, t, resid) as given
+    stif::DevBuf k_pairtab;    // assembly pair table of the Cholesky kernel
     stif::DevBuf k_obs4;       // obs AoS {x, y, t, resid}, original order (neighbour gathers)
     stif::KrigModel model;
     stif::DevBuf k_scratch[16];

@@ -98,6 +98,7 @@ int stif_ctx_destroy(stif_ctx *c)
     c->v_thr.release();
     c->k_obs.release();
     c->k_obs4.release();
+    c->k_pairtab.release();
     c->k_stats.release();
     for (auto &b : c->k_scratch) b.release();
     for (int i = 0; i < 6; ++i)

@@ -34,7 +34,11 @@ struct CholParams {
     double tol;              // pivot tolerance
     // all-spherical fast path: C = cb + ncs q(h is) + nct q(t it) + ncm q(d im)
     double is, it, im, ncs, nct, ncm, cb, ani2;
+    // the same without clamps (every neighbour pair inside every range):
+    //   C = cb + h (as - bs h^2) + t (at - bt t^2) + d (am - bm d^2),  a = -c0 1.5 / r,  b = -c0 0.5 / r^3
+    double pas, pbs, pat, pbt, pam, pbm;
     int clamp;               // 1: a neighbour pair can lie beyond a marginal's range
+    const unsigned *pairtab; // pair e = a(a-1)/2 + b (b < a)  ->  a | b << 8 | chol_off(a, b) << 16
     unsigned *fail_list;     // targets (chunk-local ids) that need the pivoted LU
     unsigned *fail_count;
 };
@@ -72,6 +76,38 @@ __device__ __forceinline__ double sqrt_fast(double x)
     h = __fma_rn(h, r, h);
     const double d = __fma_rn(-g, g, x);
     return __fma_rn(d, h, g);
+}
+
+// sqrt(x) for x > 0 (caller adds the guard): MUFU.RSQ64H + one cubic correction of
+// t = x y ~ sqrt(x): t (1 + e/2 + 3 e^2/8), e = 1 - t y  ->  relative error ~ e^3 (2^-66) + rounding.
+__device__ __forceinline__ double sqrt_cubic(double x)
+{
+    const double y = rsqrt_approx(x);
+    const double t = x * y;
+    const double e = __fma_rn(-t, y, 1.0);
+    const double p = __fma_rn(0.375, e, 0.5);
+    const double te = t * e;
+    return __fma_rn(te, p, t);
+}
+
+// Covariance entry without clamps, polynomial form (see CholParams).
+template <int VAR>
+__device__ __forceinline__ double cov_entry_poly(const CholParams &X, double d2, double lt)
+{
+    d2 = d2 + 1e-290;                 // coincident stations: sqrt(0) -> 1e-145, no 0 * inf
+    const double lt2 = lt * lt;
+    double c = X.cb;
+    if (VAR == CHOL_SUM_SPH || VAR == CHOL_SUM_METRIC_SPH) {
+        const double h = sqrt_cubic(d2);
+        c = __fma_rn(h, __fma_rn(-X.pbs, d2, X.pas), c);
+        c = __fma_rn(lt, __fma_rn(-X.pbt, lt2, X.pat), c);
+    }
+    if (VAR == CHOL_METRIC_SPH || VAR == CHOL_SUM_METRIC_SPH) {
+        const double dm2 = __fma_rn(X.ani2, lt2, d2);
+        const double dm = sqrt_cubic(dm2);
+        c = __fma_rn(dm, __fma_rn(-X.pbm, dm2, X.pam), c);
+    }
+    return c;
 }
 
 // spherical shape q(u) = 1.5 u - 0.5 u^3 for u <= 1, 1 beyond (variogram_models.py:40-44, r > 0).
@@ -122,32 +158,37 @@ struct CholLane {
 };
 
 // ---- C = c - gamma(D_s, D_t), strictly lower triangle; pair e = a(a-1)/2 + b, b < a ----
+// Two pairs per lane and iteration (independent dependency chains); (a, b) and the tile offset
+// come from a precomputed table (L1-resident, coalesced) instead of a divergent decode loop.
+template <int VAR, bool CLAMP>
+__device__ __forceinline__ double chol_cov(const Model &M, const CholParams &X, double2 pa, double ta,
+                                           double2 pb, double tb)
+{
+    const double dx = pa.x - pb.x, dy = pa.y - pb.y;
+    const double d2 = __fma_rn(dy, dy, dx * dx);
+    const double lt = fabs(ta - tb);
+    if (VAR != CHOL_GENERIC && !CLAMP) return cov_entry_poly<VAR>(X, d2, lt);
+    return cov_entry<VAR, CLAMP>(M, X, d2, lt);
+}
+
 template <int VAR, bool CLAMP>
 __device__ __forceinline__ void chol_assemble(double *T, const double2 *pxy, const double *pt, int m,
                                               const Model &M, const CholParams &X, int lane)
 {
     const int npairs = (m * (m - 1)) >> 1;
-    int a = 1, b = lane;
-    int rowoff = 8, sa = chol_swz(1);
-    double2 pa = pxy[1];
-    double ta = pt[1];
-    for (int e = lane; e < npairs; e += 32) {
-        if (b >= a) {
-            do {
-                b -= a;
-                ++a;
-            } while (b >= a);
-            rowoff = chol_tri(a >> 3) * 64 + (a & 7) * 8;
-            sa = chol_swz(a & 7);
-            pa = pxy[a];
-            ta = pt[a];
-        }
-        const double2 pb = pxy[b];
-        const double dx = pa.x - pb.x, dy = pa.y - pb.y;
-        const double d2 = __fma_rn(dy, dy, dx * dx);
-        const double lt = fabs(ta - pt[b]);
-        T[rowoff + ((b >> 3) << 6) + ((((b >> 1) & 3) ^ sa) << 1) + (b & 1)] = cov_entry<VAR, CLAMP>(M, X, d2, lt);
-        b += 32;
+    const unsigned *tab = X.pairtab + lane;
+#pragma unroll 1
+    for (int e = lane; e < npairs; e += 64) {
+        const bool two = e + 32 < npairs;
+        const unsigned w0 = __ldg(tab), w1 = two ? __ldg(tab + 32) : w0;
+        tab += 64;
+        const int a0 = w0 & 0xff, b0 = (w0 >> 8) & 0xff, a1 = w1 & 0xff, b1 = (w1 >> 8) & 0xff;
+        const double2 pa0 = pxy[a0], pb0 = pxy[b0], pa1 = pxy[a1], pb1 = pxy[b1];
+        const double ta0 = pt[a0], tb0 = pt[b0], ta1 = pt[a1], tb1 = pt[b1];
+        const double c0 = chol_cov<VAR, CLAMP>(M, X, pa0, ta0, pb0, tb0);
+        const double c1 = chol_cov<VAR, CLAMP>(M, X, pa1, ta1, pb1, tb1);
+        T[w0 >> 16] = c0;
+        if (two) T[w1 >> 16] = c1;
     }
 }
 
@@ -213,6 +254,7 @@ __device__ __forceinline__ bool chol_panel(double *T, int Pt, int m, int nrow, d
     // rows below the real part of the block (pass-through columns have i = 1, l = 0)
     const int rstart = c0 + (ncol < 4 ? ncol : 4);
     const int chA = ((2 * H) ^ L.ls) << 1, chB = ((2 * H + 1) ^ L.ls) << 1;
+#pragma unroll 1
     for (int slot = rstart >> 5; slot <= ((nrow - 1) >> 5); ++slot) {
         const int r = L.lane + 32 * slot;
         if (r >= rstart && r < nrow) {
@@ -242,6 +284,7 @@ __device__ __forceinline__ void chol_update_group(double *T, int I0, int Jc, con
         pa[u] = T + chol_tri(I0 + u) * 64;
     }
     const double *pb = T + chol_tri(Jc) * 64;
+#pragma unroll 1
     for (int qq = 0; qq < Jc; ++qq) {
         const double bA = pb[L.foA], bB = pb[L.foB];
 #pragma unroll
@@ -340,7 +383,7 @@ __device__ __forceinline__ void chol_backsub_row(const double *T, double *sol, d
     }
 }
 
-template <int VAR, int ZR>
+template <int VAR, int ZR, bool CLAMP>
 __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParams X)
 {
     extern __shared__ __align__(16) double smem_d[];
@@ -401,10 +444,7 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
             T[chol_off(m + 1, e)] = 1.0;
         }
         __syncwarp();
-        if (m > 1) {
-            if (X.clamp) chol_assemble<VAR, true>(T, pxy, pt, m, P.M, X, lane);
-            else chol_assemble<VAR, false>(T, pxy, pt, m, P.M, X, lane);
-        }
+        if (m > 1) chol_assemble<VAR, CLAMP>(T, pxy, pt, m, P.M, X, lane);
         __syncwarp();
         // ---- left-looking tiled Cholesky ----
         bool fail = false;

@@ -968,6 +968,21 @@ __global__ void obs_interleave_kernel(const double *x, const double *y, const do
     if (i < n) out[i] = make_double4(x[i], y[i], t[i], r[i]);
 }
 
+// Host: pair table of the assembly loop (see CholParams::pairtab) for up to KMAX neighbours.
+static void build_pair_table(std::vector<unsigned> &tab)
+{
+    tab.resize((size_t)KMAX * (KMAX - 1) / 2);
+    size_t e = 0;
+    for (int a = 1; a < KMAX; ++a) {
+        for (int b = 0; b < a; ++b) {
+            const int I = a >> 3, ri = a & 7, ci = b & 7;
+            const int off = (I * (I + 1) / 2 + (b >> 3)) * 64 + ri * 8 +
+                            ((((ci >> 1) ^ chol_swz(ri)) << 1) | (ci & 1));
+            tab[e++] = (unsigned)a | ((unsigned)b << 8) | ((unsigned)off << 16);
+        }
+    }
+}
+
 // Host: decide whether the covariance-form (Cholesky) kernel may be tried for this model and
 // fill its constants.  Returns the kernel variant (CHOL_*) or -1 for "pivoted LU only".
 static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax, double tmax,
@@ -1016,6 +1031,13 @@ static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax
         if (use_t) noclamp = noclamp && tmax * (1.0 + 1e-9) <= M.rt;
         if (use_m) noclamp = noclamp && dmax * (1.0 + 1e-9) <= M.rm;
         X.clamp = noclamp ? 0 : 1;     // NaN / inf radii compare false -> clamp
+    }
+    {
+        auto pa = [](double c0, double inv_r) { return -c0 * 1.5 * inv_r; };
+        auto pb = [](double c0, double inv_r) { return -c0 * 0.5 * inv_r * inv_r * inv_r; };
+        X.pas = pa(M.c0s, M.is); X.pbs = pb(M.c0s, M.is);
+        X.pat = pa(M.c0t, M.it); X.pbt = pb(M.c0t, M.it);
+        X.pam = pa(M.c0m, M.im); X.pbm = pb(M.c0m, M.im);
     }
     return km.st_model == STIF_ST_SUM ? CHOL_SUM_SPH
          : km.st_model == STIF_ST_METRIC ? CHOL_METRIC_SPH : CHOL_SUM_METRIC_SPH;
@@ -1238,6 +1260,13 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     CholParams CX;
     const int chol_var = chol_plan(c->model, M, flags, smax, tmax, CX);
     CX.obs4 = c->k_obs4.as<double4>();
+    if (!c->k_pairtab.p) {
+        std::vector<unsigned> tab;
+        build_pair_table(tab);
+        STIF_TRY(c->k_pairtab.reserve(tab.size() * sizeof(unsigned)));
+        STIF_CUDA(cudaMemcpy(c->k_pairtab.p, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    }
+    CX.pairtab = c->k_pairtab.as<unsigned>();
     c->k_chol_enabled = chol_var >= 0 ? 1 : 0;
     const int chol_nt = (k + 2 + 7) / 8, chol_kp = (k + 1) & ~1;
     const size_t chol_smem = sizeof(double) * ((size_t)chol_nt * (chol_nt + 1) / 2 * 64 + 5 * (size_t)chol_kp) +
@@ -1330,9 +1359,9 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             CX.fail_list = fail_list;
             CX.fail_count = fail_count;
             QP.count = nullptr;
-#define STIF_CHOL(VAR_, ZR_)                                                                       \
+#define STIF_CHOL(VAR_, ZR_, CL_)                                                                  \
     do {                                                                                           \
-        auto kern = solve_chol_kernel<VAR_, ZR_>;                                                  \
+        auto kern = solve_chol_kernel<VAR_, ZR_, CL_>;                                                \
         STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        (int)chol_smem));                                           \
         int occ = 0;                                                                               \
@@ -1344,14 +1373,19 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     } while (0)
 #define STIF_CHOL_Z(VAR_)                                                                          \
     do {                                                                                           \
-        if (k <= 64) STIF_CHOL(VAR_, 2);                                                           \
-        else STIF_CHOL(VAR_, 4);                                                                   \
+        if (k <= 64) {                                                                             \
+            if (CX.clamp) STIF_CHOL(VAR_, 2, true);                                                \
+            else STIF_CHOL(VAR_, 2, false);                                                        \
+        } else {                                                                                   \
+            if (CX.clamp) STIF_CHOL(VAR_, 4, true);                                                \
+            else STIF_CHOL(VAR_, 4, false);                                                        \
+        }                                                                                          \
     } while (0)
             switch (chol_var) {
             case CHOL_SUM_SPH: STIF_CHOL_Z(CHOL_SUM_SPH); break;
             case CHOL_METRIC_SPH: STIF_CHOL_Z(CHOL_METRIC_SPH); break;
             case CHOL_SUM_METRIC_SPH: STIF_CHOL_Z(CHOL_SUM_METRIC_SPH); break;
-            default: STIF_CHOL_Z(CHOL_GENERIC); break;
+            default: CX.clamp = 1; STIF_CHOL_Z(CHOL_GENERIC); break;
             }
 #undef STIF_CHOL_Z
 #undef STIF_CHOL

@@ -58,9 +58,9 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     const double y = rsqrt_approx(x);
     const double t = x * y;
     const double e = __fma_rn(-t, y, 1.0);
-    const double p = __fma_rn(0.375, e, 0.5);
-    const double q = e * p;
-    return __fma_rn(y, q, y);
+    const double p = __fma_rn(0.375, e, 0.5);     // p and ye are independent: chain = 4 ops
+    const double ye = y * e;
+    return __fma_rn(ye, p, y);
 }
 
 // sqrt(x) to <= 1 ulp for x >= 0 (coupled Newton on g ~ sqrt x, h ~ 1/(2 sqrt x)); the tiny
@@ -158,8 +158,9 @@ struct CholLane {
 };
 
 // ---- C = c - gamma(D_s, D_t), strictly lower triangle; pair e = a(a-1)/2 + b, b < a ----
-// Two pairs per lane and iteration (independent dependency chains); (a, b) and the tile offset
-// come from a precomputed table (L1-resident, coalesced) instead of a divergent decode loop.
+// Four pairs per lane and iteration (independent dependency chains); (a, b) and the tile offset
+// come from a precomputed table (coalesced, prefetched one iteration ahead) instead of a
+// divergent decode loop.
 template <int VAR, bool CLAMP>
 __device__ __forceinline__ double chol_cov(const Model &M, const CholParams &X, double2 pa, double ta,
                                            double2 pb, double tb)
@@ -175,32 +176,69 @@ template <int VAR, bool CLAMP>
 __device__ __forceinline__ void chol_assemble(double *T, const double2 *pxy, const double *pt, int m,
                                               const Model &M, const CholParams &X, int lane)
 {
+    constexpr int U = 4;                       // pairs per lane and iteration
     const int npairs = (m * (m - 1)) >> 1;
     const unsigned *tab = X.pairtab + lane;
+    unsigned w[U], wn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) w[u] = (lane + 32 * u < npairs) ? __ldg(tab + 32 * u) : 0x00000100u;
 #pragma unroll 1
-    for (int e = lane; e < npairs; e += 64) {
-        const bool two = e + 32 < npairs;
-        const unsigned w0 = __ldg(tab), w1 = two ? __ldg(tab + 32) : w0;
-        tab += 64;
-        const int a0 = w0 & 0xff, b0 = (w0 >> 8) & 0xff, a1 = w1 & 0xff, b1 = (w1 >> 8) & 0xff;
-        const double2 pa0 = pxy[a0], pb0 = pxy[b0], pa1 = pxy[a1], pb1 = pxy[b1];
-        const double ta0 = pt[a0], tb0 = pt[b0], ta1 = pt[a1], tb1 = pt[b1];
-        const double c0 = chol_cov<VAR, CLAMP>(M, X, pa0, ta0, pb0, tb0);
-        const double c1 = chol_cov<VAR, CLAMP>(M, X, pa1, ta1, pb1, tb1);
-        T[w0 >> 16] = c0;
-        if (two) T[w1 >> 16] = c1;
+    for (int e = lane; e < npairs; e += 32 * U) {
+        tab += 32 * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u)            // next iteration's table words (pair (1,0) = harmless filler)
+            wn[u] = (e + 32 * (U + u) < npairs) ? __ldg(tab + 32 * u) : 0x00000100u;
+        double2 pa[U], pb[U];
+        double ta[U], tb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int a = w[u] & 0xff, b = (w[u] >> 8) & 0xff;
+            pa[u] = pxy[a];
+            pb[u] = pxy[b];
+            ta[u] = pt[a];
+            tb[u] = pt[b];
+        }
+        double c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = chol_cov<VAR, CLAMP>(M, X, pa[u], ta[u], pb[u], tb[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e + 32 * u < npairs) T[w[u] >> 16] = c[u];
+            w[u] = wn[u];
+        }
     }
 }
 
 // Factor the 4-column panel at columns 8 Pt + 4 H .. +3 and forward-substitute the rows below.
 // Every lane factors the 4x4 diagonal block redundantly in registers; lane 0 writes it back
 // (1/L_ii on the diagonal); lanes own rows lane + 32 slot.  Returns true if a pivot failed.
-template <int H>
+template <int H, int NSLOT>
 __device__ __forceinline__ bool chol_panel(double *T, int Pt, int m, int nrow, double tol, const CholLane &L)
 {
     const int c0 = 8 * Pt + 4 * H;
     double *Td = T + (chol_tri(Pt) + Pt) * 64;
     constexpr int r0 = 4 * H;
+    const int ncol = m - c0;   // real columns in this panel (>= 1); the others pass through
+    const int rstart = c0 + (ncol < 4 ? ncol : 4);
+    // own rows (lane + 32 s) below the real part of the block: loaded up front so that their
+    // latency hides behind the serial 4x4 factorisation
+    const int chA = ((2 * H) ^ L.ls) << 1, chB = ((2 * H + 1) ^ L.ls) << 1;
+    double2 q0[NSLOT], q1[NSLOT];
+    double2 *p0[NSLOT];
+    bool act[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int r = L.lane + 32 * s;
+        act[s] = r >= rstart && r < nrow;
+        double *row = T + (chol_tri(L.q8 + 4 * s) + Pt) * 64 + L.l8;
+        p0[s] = reinterpret_cast<double2 *>(row + chA);
+        if (32 * s + 31 >= rstart && 32 * s < nrow) {      // warp-uniform: slot has rows to do
+            if (act[s]) {
+                q0[s] = *p0[s];
+                q1[s] = *reinterpret_cast<double2 *>(row + chB);
+            }
+        }
+    }
     // 16-byte chunk ch of row ri of the tile (swizzle is a compile-time constant here)
 #define CHUNK(ri, ch) reinterpret_cast<double2 *>(Td + (ri) * 8 + ((((ch)) ^ chol_swz(ri)) << 1))
     const double2 u0 = *CHUNK(r0 + 0, 2 * H);
@@ -210,7 +248,6 @@ __device__ __forceinline__ bool chol_panel(double *T, int Pt, int m, int nrow, d
     double d00 = u0.x, d10 = u1.x, d11 = u1.y, d20 = u2.x, d21 = u2.y, d22 = v2.x;
     double d30 = u3.x, d31 = u3.y, d32 = v3.x, d33 = v3.y;
     __syncwarp();              // every lane holds the block before it is overwritten
-    const int ncol = m - c0;   // real columns in this panel (>= 1); the others pass through
     if (ncol < 4) {
         d30 = 0.0; d31 = 0.0; d32 = 0.0; d33 = 1.0;
         if (ncol < 3) { d20 = 0.0; d21 = 0.0; d22 = 1.0; }
@@ -251,22 +288,18 @@ __device__ __forceinline__ bool chol_panel(double *T, int Pt, int m, int nrow, d
         }
     }
 #undef CHUNK
-    // rows below the real part of the block (pass-through columns have i = 1, l = 0)
-    const int rstart = c0 + (ncol < 4 ? ncol : 4);
-    const int chA = ((2 * H) ^ L.ls) << 1, chB = ((2 * H + 1) ^ L.ls) << 1;
-#pragma unroll 1
-    for (int slot = rstart >> 5; slot <= ((nrow - 1) >> 5); ++slot) {
-        const int r = L.lane + 32 * slot;
-        if (r >= rstart && r < nrow) {
-            double *row = T + (chol_tri(L.q8 + 4 * slot) + Pt) * 64 + L.l8;
-            double2 *p0 = reinterpret_cast<double2 *>(row + chA), *p1 = reinterpret_cast<double2 *>(row + chB);
-            const double2 q0 = *p0, q1 = *p1;
-            const double x0 = q0.x * i0;
-            const double x1 = __fma_rn(-x0, l10, q0.y) * i1;
-            const double x2 = __fma_rn(-x1, l21, __fma_rn(-x0, l20, q1.x)) * i2;
-            const double x3 = __fma_rn(-x2, l32, __fma_rn(-x1, l31, __fma_rn(-x0, l30, q1.y))) * i3;
-            *p0 = make_double2(x0, x1);
-            *p1 = make_double2(x2, x3);
+    // forward substitution of the preloaded rows (pass-through columns have i = 1, l = 0)
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        if (32 * s + 31 >= rstart && 32 * s < nrow) {
+            if (act[s]) {
+                const double x0 = q0[s].x * i0;
+                const double x1 = __fma_rn(-x0, l10, q0[s].y) * i1;
+                const double x2 = __fma_rn(-x1, l21, __fma_rn(-x0, l20, q1[s].x)) * i2;
+                const double x3 = __fma_rn(-x2, l32, __fma_rn(-x1, l31, __fma_rn(-x0, l30, q1[s].y))) * i3;
+                *p0[s] = make_double2(x0, x1);
+                *reinterpret_cast<double2 *>(reinterpret_cast<double *>(p0[s]) - chA + chB) = make_double2(x2, x3);
+            }
         }
     }
     return false;
@@ -362,6 +395,7 @@ __device__ __forceinline__ void chol_backsub_row(const double *T, double *sol, d
     }
     const int zi = (8 * J) >> 5;          // slot that owns this tile row's columns
     const int src0 = (8 * J) & 31;
+    double wkeep = 0.0;                   // lane jj keeps w_{8J+jj}; stored once after the 8 steps
 #pragma unroll
     for (int jj = 7; jj >= 0; --jj) {
         const int j = 8 * J + jj;
@@ -374,17 +408,18 @@ __device__ __forceinline__ void chol_backsub_row(const double *T, double *sol, d
             if (zi == i) zj = z[i];
         zj = __shfl_sync(FULL, zj, src0 + jj);
         const double wj = zj * dinv;
-        if (L.lane == 0) sol[j] = wj;
+        if (L.lane == jj) wkeep = wj;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int c = L.lane + 32 * i;
             if (c < j) z[i] = __fma_rn(-rowT[jj * 8 + lo[i][sj]], wj, z[i]);
         }
     }
+    if (L.lane < 8 && 8 * J + L.lane < m) sol[8 * J + L.lane] = wkeep;
 }
 
 template <int VAR, int ZR, bool CLAMP>
-__global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParams X)
+__global__ void __maxnreg__(ZR == 2 ? 152 : 240) solve_chol_kernel(SolveParams P, CholParams X)
 {
     extern __shared__ __align__(16) double smem_d[];
     const int lane = threadIdx.x;
@@ -410,12 +445,70 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
         L.t = t;
     }
 
-    for (int slot = blockIdx.x; slot < P.n; slot += gridDim.x) {
-        const unsigned tl = P.order[slot];
+    // The next target's selection (indices, then coordinates) is fetched into registers while
+    // the current one is being factorised: no dependent global-load chain at the loop top.
+    unsigned tl = 0, ntl = 0, nid[ZR];
+    int m = 0, nm = 0;
+    double4 no[ZR];
+    double ng[ZR];
+#pragma unroll
+    for (int i = 0; i < ZR; ++i) {
+        nid[i] = 0u;
+        no[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+        ng[i] = 0.0;
+    }
+    bool has_next = false;
+    auto fetch_ids = [&]() {              // stage B: needs ntl
+        nm = has_next ? P.sel_n[ntl] : 0;
+#pragma unroll
+        for (int i = 0; i < ZR; ++i) {
+            const int e = lane + 32 * i;
+            if (has_next && e < k) nid[i] = P.sel_idx[(size_t)ntl * k + e];
+        }
+    };
+    auto fetch_obs = [&]() {              // stage C: needs nm and nid
+#pragma unroll
+        for (int i = 0; i < ZR; ++i) {
+            const int e = lane + 32 * i;
+            if (e < nm) {
+                no[i] = X.obs4[nid[i]];
+                ng[i] = P.sel_gamma[(size_t)ntl * k + e];
+            }
+        }
+    };
+    if ((int)blockIdx.x < P.n) {
+        has_next = true;
+        ntl = P.order[blockIdx.x];
+        fetch_ids();
+        fetch_obs();
+        tl = ntl;
+        m = nm;
+    }
+    for (int slot = blockIdx.x; slot < P.n; slot += gridDim.x, tl = ntl, m = nm) {
         const int64_t tg = P.c0 + tl;
-        const int m = P.sel_n[tl];
         __syncwarp();
+        // ---- neighbours (prefetched), diagonal, the two right-hand-side rows ----
+        if (m > 0) {
+#pragma unroll
+            for (int i = 0; i < ZR; ++i) {
+                const int e = lane + 32 * i;
+                if (e < m) {
+                    ids[e] = nid[i];
+                    pxy[e] = make_double2(no[i].x, no[i].y);
+                    pt[e] = no[i].z;
+                    rs[e] = no[i].w;
+                    g0[e] = ng[i];
+                    T[chol_off(e, e)] = X.cdiag;
+                    T[chol_off(m, e)] = X.csill - ng[i];
+                    T[chol_off(m + 1, e)] = 1.0;
+                }
+            }
+        }
+        has_next = slot + (int)gridDim.x < P.n;
+        if (has_next) ntl = P.order[slot + gridDim.x];       // stage A
         if (m <= 0) {
+            fetch_ids();
+            fetch_obs();
             if (lane == 0) {
                 P.mean[tg] = 0.0;
                 P.std[tg] = 0.0;
@@ -429,23 +522,10 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
             continue;
         }
         const int nrow = m + 2, nt = (nrow + 7) >> 3;
-        // ---- neighbours, diagonal, the two right-hand-side rows ----
-        for (int e = lane; e < m; e += 32) {
-            const unsigned id = P.sel_idx[(size_t)tl * k + e];
-            const double4 o = X.obs4[id];
-            ids[e] = id;
-            pxy[e] = make_double2(o.x, o.y);
-            pt[e] = o.z;
-            rs[e] = o.w;
-            const double gv = P.sel_gamma[(size_t)tl * k + e];
-            g0[e] = gv;
-            T[chol_off(e, e)] = X.cdiag;
-            T[chol_off(m, e)] = X.csill - gv;
-            T[chol_off(m + 1, e)] = 1.0;
-        }
         __syncwarp();
         if (m > 1) chol_assemble<VAR, CLAMP>(T, pxy, pt, m, P.M, X, lane);
         __syncwarp();
+        fetch_ids();
         // ---- left-looking tiled Cholesky ----
         bool fail = false;
         const int ntc = (m + 7) >> 3;       // tile columns that hold real columns
@@ -456,17 +536,18 @@ __global__ void __launch_bounds__(32) solve_chol_kernel(SolveParams P, CholParam
                 }
                 __syncwarp();
             }
-            fail = chol_panel<0>(T, Jc, m, nrow, X.tol, L);
+            fail = chol_panel<0, ZR + 1>(T, Jc, m, nrow, X.tol, L);
             __syncwarp();
             if (fail || 8 * Jc + 4 >= m) break;
             for (int I0 = Jc; I0 < nt; I0 += CHOL_G) {
                 CHOL_DISPATCH_NTI(chol_half_group, nt - I0, T, I0, Jc, L);
             }
             __syncwarp();
-            fail = chol_panel<1>(T, Jc, m, nrow, X.tol, L);
+            fail = chol_panel<1, ZR + 1>(T, Jc, m, nrow, X.tol, L);
             __syncwarp();
             if (fail) break;
         }
+        fetch_obs();
         if (fail) {   // not positive definite / singular: the pivoted LU takes this target
             if (lane == 0) X.fail_list[atomicAdd(X.fail_count, 1u)] = tl;
             continue;

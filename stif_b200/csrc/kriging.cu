@@ -33,8 +33,9 @@ namespace krig {
 
 constexpr int KMAX = 128;        // max_kriging_points limit
 constexpr int SEARCH_WARPS = 4;  // warps per block in the search kernel
-constexpr int PEND_CAP = 256;    // pending candidate positions per warp
-constexpr int BUF_CAP = 512;     // (gamma, idx) buffer per warp; >= KMAX + PEND_CAP
+constexpr int SCAN_U = 4;        // independent 32-candidate loads in flight per warp
+constexpr int PEND_CAP = 160;    // pending in-window candidates per warp; >= 31 + 32 * SCAN_U
+constexpr int BUF_CAP = 320;     // (gamma, idx) buffer per warp; >= KMAX + PEND_CAP
 constexpr unsigned FULL = 0xffffffffu;
 
 struct Model {
@@ -72,29 +73,49 @@ __device__ __forceinline__ double marginal(int kind, double h, double r, double 
     return b + c0 * (1.0 - exp(-((h * h) * inv)));
 }
 
-__device__ __forceinline__ double gamma_st(const Model &M, double h, double t)
+// ST / KS / KT / KM < 0: read the id from the model at run time; >= 0: compile-time constant
+// (same arithmetic, the warp-uniform branches disappear).
+template <int ST, int KS, int KT, int KM>
+__device__ __forceinline__ double gamma_tpl(const Model &M, double h, double t)
 {
-    switch (M.st) {
+    const int st = ST < 0 ? M.st : ST;
+    const int ks = KS < 0 ? M.ks : KS, kt = KT < 0 ? M.kt : KT, km = KM < 0 ? M.km : KM;
+    switch (st) {
     case STIF_ST_SUM:  // :98-99
-        return marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) + marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it);
+        return marginal(ks, h, M.rs, M.c0s, M.bs, M.is) + marginal(kt, t, M.rt, M.c0t, M.bt, M.it);
     case STIF_ST_PRODUCT:  // :126-127
-        return marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) * marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it);
+        return marginal(ks, h, M.rs, M.c0s, M.bs, M.is) * marginal(kt, t, M.rt, M.c0t, M.bt, M.it);
     case STIF_ST_PRODUCT_SUM: {  // :155-157  k*prod + prod
-        const double p = marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) *
-                         marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it);
+        const double p = marginal(ks, h, M.rs, M.c0s, M.bs, M.is) *
+                         marginal(kt, t, M.rt, M.c0t, M.bt, M.it);
         return M.k * p + p;
     }
     case STIF_ST_METRIC: {  // :184-186
         const double d = sqrt(h * h + (M.ani2 * t) * t);
-        return marginal(M.km, d, M.rm, M.c0m, M.bm, M.im);
+        return marginal(km, d, M.rm, M.c0m, M.bm, M.im);
     }
     default: {  // sum_metric :213-218
         const double d = sqrt(h * h + (M.ani2 * t) * t);
-        return (marginal(M.ks, h, M.rs, M.c0s, M.bs, M.is) +
-                marginal(M.kt, t, M.rt, M.c0t, M.bt, M.it)) +
-               marginal(M.km, d, M.rm, M.c0m, M.bm, M.im);
+        return (marginal(ks, h, M.rs, M.c0s, M.bs, M.is) +
+                marginal(kt, t, M.rt, M.c0t, M.bt, M.it)) +
+               marginal(km, d, M.rm, M.c0m, M.bm, M.im);
     }
     }
+}
+
+__device__ __forceinline__ double gamma_st(const Model &M, double h, double t)
+{
+    return gamma_tpl<-1, -1, -1, -1>(M, h, t);
+}
+
+// search-kernel variants: 0 = any model (run-time ids), 1 = sum_metric, 2 = product_sum, both
+// with three spherical marginals (the reference's defaults, predictor.py:662-666)
+template <int GV>
+__device__ __forceinline__ double gamma_search(const Model &M, double h, double t)
+{
+    if (GV == 1) return gamma_tpl<STIF_ST_SUM_METRIC, STIF_M_SPHERICAL, STIF_M_SPHERICAL, STIF_M_SPHERICAL>(M, h, t);
+    if (GV == 2) return gamma_tpl<STIF_ST_PRODUCT_SUM, STIF_M_SPHERICAL, STIF_M_SPHERICAL, STIF_M_SPHERICAL>(M, h, t);
+    return gamma_st(M, h, t);
 }
 
 __global__ void model_eval_kernel(Model M, const double *h, const double *t, int64_t n, double *out)
@@ -261,10 +282,18 @@ __device__ __forceinline__ unsigned long long gamma_key(double g)
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+__device__ __forceinline__ double key_gamma(unsigned long long kb)
+{
+    kb = (kb & 0x8000000000000000ull) ? (kb & 0x7fffffffffffffffull) : ~kb;
+    return __longlong_as_double((long long)kb);
+}
+
 struct WarpBuf {
     unsigned long long *key;  // [BUF_CAP]
     unsigned *idx;            // [BUF_CAP]
-    unsigned *pend;           // [PEND_CAP]
+    double *pend_d2;          // [PEND_CAP] squared spatial distance of a pending candidate
+    double *pend_lt;          // [PEND_CAP] |dt|
+    unsigned *pend_idx;       // [PEND_CAP] observation index
 };
 
 __device__ __forceinline__ int warp_count_le(const unsigned long long *key, int m, int lane,
@@ -290,18 +319,38 @@ __device__ void select_k(const WarpBuf &B, int &m, int k, int lane)
         lo = a < lo ? a : lo;
         hi = b > hi ? b : hi;
     }
-    // bisection for the k-th smallest key; early exit when a threshold splits exactly k
+    // k-th smallest key: regula falsi on the gamma values (the counts are a smooth function of
+    // the threshold, so the interpolated guess lands within a few candidates) alternating with
+    // plain bisection of the key range (guaranteed progress); early exit when a threshold
+    // splits exactly k.  Invariant: the k-th smallest key is in [lo, hi],
+    // c_lo = count(key < lo) < k <= c_hi = count(key <= hi).
     unsigned long long thr = hi;
     bool exact = false;
-    while (lo < hi) {
-        const unsigned long long mid = lo + ((hi - lo) >> 1);
+    int c_lo = 0, c_hi = m;
+    for (int it = 0; lo < hi; ++it) {
+        unsigned long long mid = lo + ((hi - lo) >> 1);
+        if ((it & 1) == 0) {
+            const double dlo = key_gamma(lo), dhi = key_gamma(hi);
+            const double frac = ((double)(k - c_lo) - 0.5) / (double)(c_hi - c_lo);
+            const double g = dlo + (dhi - dlo) * frac;
+            if (g >= dlo && g < dhi) {          // finite, inside the bracket
+                const unsigned long long gk = gamma_key(g);
+                if (gk >= lo && gk < hi) mid = gk;
+            }
+        }
         const int c = warp_count_le(B.key, m, lane, mid);
         if (c == k) {
             thr = mid;
             exact = true;
             break;
         }
-        if (c > k) hi = mid; else lo = mid + 1;
+        if (c > k) {
+            hi = mid;
+            c_hi = c;
+        } else {
+            lo = mid + 1;
+            c_lo = c;
+        }
     }
     unsigned ithr = 0xffffffffu;
     if (!exact) {
@@ -352,21 +401,95 @@ __device__ void select_k(const WarpBuf &B, int &m, int k, int lane)
     m = out;  // == k
 }
 
-// Bitonic sort of buf[0..m) by (use_key ? key : 0, idx) ascending; m <= KMAX.
-// Padding entries carry idx 0xffffffff (never a real observation index) and sort last.
+// Sort buf[0..m) by (use_key ? key : 0, idx) ascending; m <= KMAX.
+// m <= 64: bitonic network in registers (two entries per lane, partner exchange by shuffle);
+// larger: bitonic network in shared memory.  Padding entries sort last.
 __device__ void sort_buf(const WarpBuf &B, int m, bool use_key, int lane)
 {
-    int p2 = 1;
+    int p2 = 2;
     while (p2 < m) p2 <<= 1;
+    if (p2 <= 64) {
+        // sort key K (64 bit) with tie-breaker / payload I: by gamma -> (key, idx); by index ->
+        // (idx, position) and the gamma keys are gathered afterwards
+        unsigned long long K[2];
+        unsigned I[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int e = 2 * lane + r;
+            if (e < m) {
+                const unsigned id = B.idx[e];
+                K[r] = use_key ? B.key[e] : (unsigned long long)id;
+                I[r] = use_key ? id : (unsigned)e;
+            } else {
+                K[r] = ~0ull;
+                I[r] = 0xffffffffu;
+            }
+        }
+        for (int size = 2; size <= p2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                if (stride == 1) {            // partner is the lane's other entry
+                    const bool up = (((2 * lane) & size) == 0);
+                    const bool gt = (K[0] > K[1]) || (K[0] == K[1] && I[0] > I[1]);
+                    if (gt == up) {
+                        const unsigned long long tk = K[0];
+                        const unsigned ti = I[0];
+                        K[0] = K[1];
+                        I[0] = I[1];
+                        K[1] = tk;
+                        I[1] = ti;
+                    }
+                } else {
+                    const int d = stride >> 1;             // partner lane distance
+                    const bool lower = (lane & d) == 0;
+                    const bool up = (((2 * lane) & size) == 0);
+                    const bool keep_min = (lower == up);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const unsigned long long ok = __shfl_xor_sync(FULL, K[r], d);
+                        const unsigned oi = __shfl_xor_sync(FULL, I[r], d);
+                        const bool other_less = (ok < K[r]) || (ok == K[r] && oi < I[r]);
+                        if (other_less == keep_min) {
+                            K[r] = ok;
+                            I[r] = oi;
+                        }
+                    }
+                }
+            }
+        }
+        unsigned long long kout[2];
+        unsigned iout[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int e = 2 * lane + r;
+            kout[r] = K[r];
+            iout[r] = I[r];
+            if (!use_key && e < m) {
+                kout[r] = B.key[I[r]];
+                iout[r] = (unsigned)K[r];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int e = 2 * lane + r;
+            if (e < m) {
+                B.key[e] = kout[r];
+                B.idx[e] = iout[r];
+            }
+        }
+        __syncwarp();
+        return;
+    }
     for (int e = m + lane; e < p2; e += 32) {
         B.key[e] = ~0ull;
         B.idx[e] = 0xffffffffu;
     }
     __syncwarp();
     for (int size = 2; size <= p2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int ls = 31 - __clz(size >> 1); ls >= 0; --ls) {
+            const int stride = 1 << ls;
             for (int tsk = lane; tsk < (p2 >> 1); tsk += 32) {
-                const int i = ((tsk / stride) * (stride << 1)) + (tsk % stride);
+                const int i = ((tsk >> ls) << (ls + 1)) + (tsk & (stride - 1));
                 const int j = i + stride;
                 const bool up = ((i & size) == 0);
                 const unsigned long long ki = B.key[i], kj = B.key[j];
@@ -406,9 +529,10 @@ struct SearchParams {
     unsigned *exam_n;      // [n] candidates examined
 };
 
+// gamma of the pending candidates -> (key, idx) buffer; all lanes busy
+template <int GV>
 __device__ __forceinline__ void flush_pending(const WarpBuf &B, const SearchParams &P, int &pend_n,
-                                              int &m, bool &truncated, double x, double y, double t,
-                                              int lane)
+                                              int &m, bool &truncated, int lane)
 {
     __syncwarp();
     if (m + pend_n > BUF_CAP) {
@@ -416,27 +540,27 @@ __device__ __forceinline__ void flush_pending(const WarpBuf &B, const SearchPara
         truncated = true;
     }
     for (int e = lane; e < pend_n; e += 32) {
-        const double4 o = P.obs[B.pend[e]];
-        const double dx = o.x - x, dy = o.y - y;
-        const double h = sqrt(dx * dx + dy * dy);     // predictor.py:627-634
-        const double lag_t = fabs(o.z - t);           // predictor.py:635
-        B.key[m + e] = gamma_key(gamma_st(P.M, h, lag_t));
-        B.idx[m + e] = (unsigned)__double_as_longlong(o.w);
+        const double h = sqrt(B.pend_d2[e]);              // predictor.py:627-634
+        B.key[m + e] = gamma_key(gamma_search<GV>(P.M, h, B.pend_lt[e]));   // lag_t: predictor.py:635
+        B.idx[m + e] = B.pend_idx[e];
     }
     m += pend_n;
     pend_n = 0;
     __syncwarp();
 }
 
+template <int GV>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams P)
 {
     __shared__ unsigned long long s_key[SEARCH_WARPS][BUF_CAP];
+    __shared__ double s_pd2[SEARCH_WARPS][PEND_CAP];
+    __shared__ double s_plt[SEARCH_WARPS][PEND_CAP];
     __shared__ unsigned s_idx[SEARCH_WARPS][BUF_CAP];
-    __shared__ unsigned s_pend[SEARCH_WARPS][PEND_CAP];
+    __shared__ unsigned s_pidx[SEARCH_WARPS][PEND_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SEARCH_WARPS + warp;
     if (slot >= P.n) return;
-    WarpBuf B{s_key[warp], s_idx[warp], s_pend[warp]};
+    WarpBuf B{s_key[warp], s_idx[warp], s_pd2[warp], s_plt[warp], s_pidx[warp]};
     const unsigned tl = P.order[slot];
     const int64_t tg = P.c0 + tl;
     const double x = P.tx[tg], y = P.ty[tg], t = P.tt[tg];
@@ -453,6 +577,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams 
     int pend_n = 0, m = 0;
     bool truncated = false;
     unsigned examined = 0, in_window = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (cx_lo <= cx_hi) {
         for (int ct = ct_lo; ct <= ct_hi; ++ct) {
             for (int cy = cy_lo; cy <= cy_hi; ++cy) {
@@ -460,32 +585,41 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams 
                 const unsigned beg = P.cell_start[row + cx_lo];
                 const unsigned end = P.cell_start[row + cx_hi + 1];
                 examined += end - beg;
-                for (unsigned p0 = beg; p0 < end; p0 += 32) {
-                    const unsigned p = p0 + lane;
-                    bool pass = false;
-                    if (p < end) {
-                        const double4 o = P.obs[p];
-                        const double dx = o.x - x, dy = o.y - y;
-                        const double d2 = dx * dx + dy * dy;      // cdist sqeuclidean, data.py:195-199
-                        const double dt = o.z - t;
-                        pass = (d2 < P.smax2) && (fabs(dt) < P.tmax) && (o.z <= t) &&   // data.py:206-211
-                               ((long long)(unsigned)__double_as_longlong(o.w) != leave);
+                for (unsigned p0 = beg; p0 < end; p0 += 32 * SCAN_U) {
+                    double4 o[SCAN_U];
+#pragma unroll
+                    for (int u = 0; u < SCAN_U; ++u) {     // loads first: SCAN_U requests in flight
+                        const unsigned p = p0 + 32 * u + lane;
+                        o[u] = make_double4(0.0, 0.0, INFINITY, 0.0);     // t_obs = inf fails the filter
+                        if (p < end) o[u] = P.obs[p];
                     }
-                    const unsigned bal = __ballot_sync(FULL, pass);
-                    if (bal) {
-                        if (pass) B.pend[pend_n + __popc(bal & ((1u << lane) - 1u))] = p;
-                        pend_n += __popc(bal);
-                        if (pend_n > PEND_CAP - 32) {
-                            in_window += pend_n;
-                            flush_pending(B, P, pend_n, m, truncated, x, y, t, lane);
+#pragma unroll
+                    for (int u = 0; u < SCAN_U; ++u) {
+                        const double dx = o[u].x - x, dy = o[u].y - y;
+                        const double d2 = dx * dx + dy * dy;      // cdist sqeuclidean, data.py:195-199
+                        const double dt = o[u].z - t;
+                        const unsigned oi = (unsigned)__double_as_longlong(o[u].w);
+                        const bool pass = (d2 < P.smax2) && (fabs(dt) < P.tmax) && (o[u].z <= t) &&   // data.py:206-211
+                                          ((long long)oi != leave);
+                        const unsigned bal = __ballot_sync(FULL, pass);
+                        if (pass) {
+                            const int e = pend_n + __popc(bal & lt_mask);
+                            B.pend_d2[e] = d2;
+                            B.pend_lt[e] = fabs(dt);
+                            B.pend_idx[e] = oi;
                         }
+                        pend_n += __popc(bal);
+                    }
+                    if (pend_n >= 32) {
+                        in_window += pend_n;
+                        flush_pending<GV>(B, P, pend_n, m, truncated, lane);
                     }
                 }
             }
         }
     }
     in_window += pend_n;
-    flush_pending(B, P, pend_n, m, truncated, x, y, t, lane);
+    flush_pending<GV>(B, P, pend_n, m, truncated, lane);
     if (m > P.k) {
         select_k(B, m, P.k, lane);
         truncated = true;
@@ -503,9 +637,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams 
     sort_buf(B, m, truncated, lane);
     for (int e = lane; e < m; e += 32) {
         P.sel_idx[(size_t)tl * P.k + e] = B.idx[e];
-        unsigned long long kb = B.key[e];
-        kb = (kb & 0x8000000000000000ull) ? (kb & 0x7fffffffffffffffull) : ~kb;
-        P.sel_gamma[(size_t)tl * P.k + e] = __longlong_as_double((long long)kb);
+        P.sel_gamma[(size_t)tl * P.k + e] = key_gamma(B.key[e]);
     }
     if (lane == 0) P.sel_n[tl] = m;
 }
@@ -1324,7 +1456,13 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         SP.sel_gamma = c->k_scratch[S_SEL_GAMMA].as<double>();
         SP.cand_n = cand_n;
         SP.exam_n = exam_n;
-        search_kernel<<<(nc + SEARCH_WARPS - 1) / SEARCH_WARPS, SEARCH_WARPS * 32, 0, st>>>(SP);
+        {
+            const bool sph3 = M.ks == STIF_M_SPHERICAL && M.kt == STIF_M_SPHERICAL && M.km == STIF_M_SPHERICAL;
+            const unsigned sgrid = (nc + SEARCH_WARPS - 1) / SEARCH_WARPS;
+            if (sph3 && M.st == STIF_ST_SUM_METRIC) search_kernel<1><<<sgrid, SEARCH_WARPS * 32, 0, st>>>(SP);
+            else if (sph3 && M.st == STIF_ST_PRODUCT_SUM) search_kernel<2><<<sgrid, SEARCH_WARPS * 32, 0, st>>>(SP);
+            else search_kernel<0><<<sgrid, SEARCH_WARPS * 32, 0, st>>>(SP);
+        }
         STIF_CUDA(cudaGetLastError());
         if (c0 + chunk >= n_targets) STIF_CUDA(cudaEventRecord(c->ev[2], st));
 

@@ -372,7 +372,7 @@ def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, m
         "e2e": {"value": n_t * world / e2e_s, "unit": "predictions/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t},
         "gpu_launches": 4 * steps,
-        "roofline": {"bound": "fp64", "kernel": "stif::krig::solve_kernel", "achieved": achieved,
+        "roofline": {"bound": "fp64", "kernel": "stif::krig::solve_chol_kernel", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s per GPU", "frac": achieved / peak_tf,
                      "flops_per_prediction": flops, "kernel_ms": solve_ms_avg, "traffic": None,
                      "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)"},

@@ -32,6 +32,12 @@ namespace stif {
 namespace krig {
 
 constexpr int KMAX = 128;        // max_kriging_points limit
+#ifndef LU_WPT_MID
+#define LU_WPT_MID 2              // warps per target of the pivoted LU, 32 <= k <= 64
+#endif
+#ifndef LU_WPT_BIG
+#define LU_WPT_BIG 4              // ... k > 64
+#endif
 constexpr int SEARCH_WARPS = 4;  // warps per block in the search kernel
 constexpr int SCAN_U = 4;        // independent 32-candidate loads in flight per warp
 constexpr int PEND_CAP = 160;    // pending in-window candidates per warp; >= 31 + 32 * SCAN_U
@@ -903,11 +909,12 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 //      round-robin to the warps.  512 FMAs per tensor instruction instead of 32 per DFMA: the
 //      scalar shared-memory LU was issue-bound (ncu: 78 % issue-active at 27 % FP64 pipe).
 // The right-hand side is column n and is transformed with the matrix.
-template <int WPT>
+template <int WPT, int NS>
 __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int nr, int nc)
 {
     extern __shared__ __align__(16) double smem_d[];
     constexpr int NT = WPT * 32;
+    // NS = row slots of the panel step: 32 NS >= k + 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ld = P.ld;
     const SolveSmem S = carve(smem_d, P.k, ld, nr);
@@ -930,50 +937,84 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
         for (int jb = 0; jb < n; jb += 8) {
             if (warp == 0) {
                 // ---- 1. panel factorisation, columns jb .. jb+7 (pivot columns only while < n) ----
-                for (int jj = 0; jj < 8 && jb + jj < n; ++jj) {
+                // Lanes own rows lane + 32 s and keep their 8 panel entries in registers; rows are
+                // not moved: pos[s] is the row's position after the swaps so far, the pivot row is
+                // broadcast by shuffles, and every row is written back to its final position.
+                double a[NS][8];
+                int pos[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int r = lane + 32 * s;
+                    pos[s] = r;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a[s][c] = (r >= jb && r < n) ? A[r * ld + jb + c] : 0.0;
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
                     const int j = jb + jj;
-                    unsigned long long key = 0ull;
-                    for (int r = j + lane; r < n; r += 32) {
-                        const unsigned long long kb = pivot_key(A[r * ld + j], r);
-                        key = kb > key ? kb : key;
-                    }
-                    key = warp_max_u64(key);
-                    const int bi = 255 - (int)(key & 0xffull);
-                    const double bv = __longlong_as_double((long long)(key & ~0xffull));
-                    double pinv = 0.0;
-                    int prow = j;                     // row swapped with row j (j = no swap)
-                    if (bv > tol && bv < INFINITY) {
-                        if (bi != j) {
-                            // swap inside the panel now; the columns to its right are swapped by
-                            // their owner threads in step 2 (off warp 0's critical path)
-                            if (lane < 8) {
-                                const double tmp = A[j * ld + jb + lane];
-                                A[j * ld + jb + lane] = A[bi * ld + jb + lane];
-                                A[bi * ld + jb + lane] = tmp;
+                    if (j < n) {
+                        unsigned long long key = 0ull;
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            if (pos[s] >= j && pos[s] < n) {
+                                const unsigned long long kb = pivot_key(a[s][jj], pos[s]);
+                                key = kb > key ? kb : key;
                             }
-                            prow = bi;
-                            __syncwarp();
                         }
-                        pinv = 1.0 / A[j * ld + j];
-                    } else {
-                        singular = true;
-                    }
-                    if (lane == 0) S.piv[jj] = prow;
-                    // pivot row inside the panel, right of the diagonal
-                    double u[7];
+                        key = warp_max_u64(key);
+                        const int bi = 255 - (int)(key & 0xffull);
+                        const double bv = __longlong_as_double((long long)(key & ~0xffull));
+                        const bool ok = bv > tol && bv < INFINITY;
+                        if (!ok) singular = true;
+                        const int prow = ok ? bi : j;     // row swapped with row j (j = no swap)
+                        // pivot row -> all lanes (owner lane by ballot, owner slot is warp-uniform)
+                        double u[8];
 #pragma unroll
-                    for (int cc = 0; cc < 7; ++cc) u[cc] = (cc >= jj) ? A[j * ld + jb + cc + 1] : 0.0;
-                    for (int r = j + 1 + lane; r < n; r += 32) {
-                        double *row = A + r * ld + jb;
-                        const double mneg = -(row[jj] * pinv);   // negated multiplier
-                        row[jj] = mneg;
+                        for (int c = 0; c < 8; ++c) u[c] = 0.0;
 #pragma unroll
-                        for (int cc = 0; cc < 7; ++cc)
-                            if (cc >= jj) row[cc + 1] = __fma_rn(mneg, u[cc], row[cc + 1]);
+                        for (int s = 0; s < NS; ++s) {
+                            const unsigned own = __ballot_sync(FULL, pos[s] == prow);
+                            if (own) {
+                                const int owner = __ffs(own) - 1;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    if (c >= jj) u[c] = __shfl_sync(FULL, a[s][c], owner);
+                            }
+                        }
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            if (pos[s] == prow) pos[s] = j;
+                            else if (pos[s] == j) pos[s] = prow;
+                        }
+                        double pinv = 0.0;
+                        if (ok) {      // 1 / pivot: MUFU.RCP64H + two Newton steps
+                            double y;
+                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u[jj]));
+                            y = __fma_rn(y, __fma_rn(-u[jj], y, 1.0), y);
+                            pinv = __fma_rn(y, __fma_rn(-u[jj], y, 1.0), y);
+                        }
+                        if (lane == 0) S.piv[jj] = prow;
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            if (pos[s] > j && pos[s] < n) {
+                                const double mneg = -(a[s][jj] * pinv);   // negated multiplier
+                                a[s][jj] = mneg;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    if (c > jj) a[s][c] = __fma_rn(mneg, u[c], a[s][c]);
+                            } else if (pos[s] == j) {
+                                a[s][jj] = pinv;
+                            }
+                        }
                     }
-                    __syncwarp();
-                    if (lane == 0) A[j * ld + j] = pinv;
-                    __syncwarp();
+                }
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int r = lane + 32 * s;
+                    if (r >= jb && r < n) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) A[pos[s] * ld + jb + c] = a[s][c];
+                    }
                 }
             }
             __syncthreads();
@@ -1532,9 +1573,9 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             QP.count = fail_count;
         }
         {
-#define STIF_SOLVE(WPT_)                                                                           \
+#define STIF_SOLVE(WPT_, NS_)                                                                      \
     do {                                                                                           \
-        auto kern = solve_blk_kernel<WPT_>;                                                        \
+        auto kern = solve_blk_kernel<WPT_, NS_>;                                                   \
         STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        (int)solve_smem));                                          \
         int occ = 0;                                                                               \
@@ -1544,10 +1585,13 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         if (gsz > nc) gsz = nc;                                                                    \
         kern<<<(unsigned)gsz, WPT_ * 32, solve_smem, st>>>(QP, nr_pad, nc_pad);                    \
     } while (0)
-            if (k <= 16) STIF_SOLVE(1);
-            else if (k <= 32) STIF_SOLVE(2);
-            else if (k <= 64) STIF_SOLVE(4);
-            else STIF_SOLVE(8);
+            if (k <= 16) STIF_SOLVE(1, 1);
+            else if (k <= 31) STIF_SOLVE(2, 1);
+            else if (k <= 63) STIF_SOLVE(LU_WPT_MID, 2);
+            else if (k <= 64) STIF_SOLVE(LU_WPT_MID, 3);
+            else if (k <= 95) STIF_SOLVE(LU_WPT_BIG, 3);
+            else if (k <= 127) STIF_SOLVE(LU_WPT_BIG, 4);
+            else STIF_SOLVE(LU_WPT_BIG, 5);
 #undef STIF_SOLVE
         }
         STIF_CUDA(cudaGetLastError());

@@ -175,7 +175,10 @@ __device__ __forceinline__ double dec_key(unsigned long long k)
 struct GridDims {
     double x0, y0, t0, inv_cx, inv_cy, inv_ct;
     int nx, ny, nt;
+    int hx, hy, ht;   // stencil half-widths in cells: ceil(radius / cell)
 };
+
+constexpr double GRID_SUB = 2.0;   // cells per search radius (finer cells: fewer candidates examined)
 
 // Decide grid geometry on the device (no host round trip): cells are >= radius*(1+1e-9)
 // wide and the total number of cells is capped at max_cells by widening them.
@@ -192,10 +195,12 @@ __global__ void grid_dims_kernel(const double *bbox_enc, double smax, double tma
             hi[d] = 0.0;
         }
     }
-    double cell[3] = {smax, smax, tmax};
-    double n[3];
+    const double radius[3] = {smax, smax, tmax};
+    double cell[3], n[3];
+    bool valid[3];
     for (int d = 0; d < 3; ++d) {
-        if (!(cell[d] > 0.0) || isinf(cell[d])) cell[d] = (hi[d] - lo[d]) + 1.0;
+        valid[d] = radius[d] > 0.0 && !isinf(radius[d]);
+        cell[d] = valid[d] ? radius[d] / GRID_SUB : (hi[d] - lo[d]) + 1.0;
         cell[d] *= (1.0 + 1e-9);
         n[d] = floor((hi[d] - lo[d]) / cell[d]) + 2.0;  // one spare cell at the upper edge
         if (!(n[d] >= 2.0)) n[d] = 2.0;
@@ -218,13 +223,26 @@ __global__ void grid_dims_kernel(const double *bbox_enc, double smax, double tma
     out->nx = (int)n[0];
     out->ny = (int)n[1];
     out->nt = (int)n[2];
+    int h[3];
+    for (int d = 0; d < 3; ++d) {
+        double hd = valid[d] ? ceil(radius[d] / cell[d]) : n[d];
+        if (!(hd >= 1.0)) hd = 1.0;
+        if (hd > n[d]) hd = n[d];
+        h[d] = (int)hd;
+    }
+    out->hx = h[0];
+    out->hy = h[1];
+    out->ht = h[2];
 }
 
-__device__ __forceinline__ int raw_cell(double v, double v0, double inv, int n)
+// cell index, clamped to [-h-1, n+h] so that a stencil of half-width h around a point far
+// outside the grid is empty
+__device__ __forceinline__ int raw_cell(double v, double v0, double inv, int n, int h = 1)
 {
     double c = floor((v - v0) * inv);
-    if (!(c >= -2.0)) c = -2.0;  // also catches NaN
-    if (c > (double)n + 1.0) c = (double)n + 1.0;
+    const double lo = -(double)h - 1.0, hi = (double)(n + h);
+    if (!(c >= lo)) c = lo;  // also catches NaN
+    if (c > hi) c = hi;
     return (int)c;
 }
 
@@ -436,14 +454,13 @@ __device__ void sort_buf(const WarpBuf &B, int m, bool use_key, int lane)
                 if (stride == 1) {            // partner is the lane's other entry
                     const bool up = (((2 * lane) & size) == 0);
                     const bool gt = (K[0] > K[1]) || (K[0] == K[1] && I[0] > I[1]);
-                    if (gt == up) {
-                        const unsigned long long tk = K[0];
-                        const unsigned ti = I[0];
-                        K[0] = K[1];
-                        I[0] = I[1];
-                        K[1] = tk;
-                        I[1] = ti;
-                    }
+                    const bool sw = (gt == up);
+                    const unsigned long long k0 = sw ? K[1] : K[0], k1 = sw ? K[0] : K[1];
+                    const unsigned i0 = sw ? I[1] : I[0], i1 = sw ? I[0] : I[1];
+                    K[0] = k0;
+                    K[1] = k1;
+                    I[0] = i0;
+                    I[1] = i1;
                 } else {
                     const int d = stride >> 1;             // partner lane distance
                     const bool lower = (lane & d) == 0;
@@ -454,10 +471,9 @@ __device__ void sort_buf(const WarpBuf &B, int m, bool use_key, int lane)
                         const unsigned long long ok = __shfl_xor_sync(FULL, K[r], d);
                         const unsigned oi = __shfl_xor_sync(FULL, I[r], d);
                         const bool other_less = (ok < K[r]) || (ok == K[r] && oi < I[r]);
-                        if (other_less == keep_min) {
-                            K[r] = ok;
-                            I[r] = oi;
-                        }
+                        const bool take = (other_less == keep_min);
+                        K[r] = take ? ok : K[r];
+                        I[r] = take ? oi : I[r];
                     }
                 }
             }
@@ -535,23 +551,41 @@ struct SearchParams {
     unsigned *exam_n;      // [n] candidates examined
 };
 
-// gamma of the pending candidates -> (key, idx) buffer; all lanes busy
+// gamma of the pending candidates -> (key, idx) buffer.  Unless `all`, only full groups of 32
+// are evaluated (every lane busy) and the < 32 leftovers move to the front of the list.
 template <int GV>
 __device__ __forceinline__ void flush_pending(const WarpBuf &B, const SearchParams &P, int &pend_n,
-                                              int &m, bool &truncated, int lane)
+                                              int &m, bool &truncated, bool all, int lane)
 {
     __syncwarp();
-    if (m + pend_n > BUF_CAP) {
+    const int nproc = all ? pend_n : (pend_n & ~31);
+    if (m + nproc > BUF_CAP) {
         select_k(B, m, P.k, lane);
         truncated = true;
     }
-    for (int e = lane; e < pend_n; e += 32) {
+    for (int e = lane; e < nproc; e += 32) {
         const double h = sqrt(B.pend_d2[e]);              // predictor.py:627-634
         B.key[m + e] = gamma_key(gamma_search<GV>(P.M, h, B.pend_lt[e]));   // lag_t: predictor.py:635
         B.idx[m + e] = B.pend_idx[e];
     }
-    m += pend_n;
-    pend_n = 0;
+    m += nproc;
+    const int rem = pend_n - nproc;
+    if (rem > 0) {
+        double d2 = 0.0, lt = 0.0;
+        unsigned oi = 0u;
+        if (lane < rem) {
+            d2 = B.pend_d2[nproc + lane];
+            lt = B.pend_lt[nproc + lane];
+            oi = B.pend_idx[nproc + lane];
+        }
+        __syncwarp();
+        if (lane < rem) {
+            B.pend_d2[lane] = d2;
+            B.pend_lt[lane] = lt;
+            B.pend_idx[lane] = oi;
+        }
+    }
+    pend_n = rem;
     __syncwarp();
 }
 
@@ -563,6 +597,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams 
     __shared__ double s_plt[SEARCH_WARPS][PEND_CAP];
     __shared__ unsigned s_idx[SEARCH_WARPS][BUF_CAP];
     __shared__ unsigned s_pidx[SEARCH_WARPS][PEND_CAP];
+    __shared__ int s_rt[SEARCH_WARPS][32];          // run table: 16 virtual ends + 16 offsets
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SEARCH_WARPS + warp;
     if (slot >= P.n) return;
@@ -573,59 +608,88 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_kernel(SearchParams 
     const long long leave = P.leave_out ? P.leave_out[tg] : -1;
     const GridDims g = *P.gd;
 
-    const int cxr = raw_cell(x, g.x0, g.inv_cx, g.nx);
-    const int cyr = raw_cell(y, g.y0, g.inv_cy, g.ny);
-    const int ctr = raw_cell(t, g.t0, g.inv_ct, g.nt);
-    const int cx_lo = max(cxr - 1, 0), cx_hi = min(cxr + 1, g.nx - 1);
-    const int cy_lo = max(cyr - 1, 0), cy_hi = min(cyr + 1, g.ny - 1);
-    const int ct_lo = max(ctr - 1, 0), ct_hi = min(ctr, g.nt - 1);  // causal: t_obs <= t_tgt
+    const int cxr = raw_cell(x, g.x0, g.inv_cx, g.nx, g.hx);
+    const int cyr = raw_cell(y, g.y0, g.inv_cy, g.ny, g.hy);
+    const int ctr = raw_cell(t, g.t0, g.inv_ct, g.nt, g.ht);
+    const int cx_lo = max(cxr - g.hx, 0), cx_hi = min(cxr + g.hx, g.nx - 1);
+    const int cy_lo = max(cyr - g.hy, 0), cy_hi = min(cyr + g.hy, g.ny - 1);
+    const int ct_lo = max(ctr - g.ht, 0), ct_hi = min(ctr, g.nt - 1);  // causal: t_obs <= t_tgt
 
     int pend_n = 0, m = 0;
     bool truncated = false;
     unsigned examined = 0, in_window = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
-    if (cx_lo <= cx_hi) {
-        for (int ct = ct_lo; ct <= ct_hi; ++ct) {
-            for (int cy = cy_lo; cy <= cy_hi; ++cy) {
-                const int row = (ct * g.ny + cy) * g.nx;
-                const unsigned beg = P.cell_start[row + cx_lo];
-                const unsigned end = P.cell_start[row + cx_hi + 1];
-                examined += end - beg;
-                for (unsigned p0 = beg; p0 < end; p0 += 32 * SCAN_U) {
-                    double4 o[SCAN_U];
+    // The stencil is (cy, ct) rows of x-contiguous cells = contiguous runs of the cell-sorted
+    // observations.  The runs are concatenated into one virtual sequence (run table in shared
+    // memory, 16 runs at a time) so that every 32-candidate load is full.
+    const int ncy = cy_hi - cy_lo + 1, nct = ct_hi - ct_lo + 1;
+    const int nruns = (cx_lo <= cx_hi && ncy > 0 && nct > 0) ? ncy * nct : 0;
+    int *rt_vend = s_rt[warp], *rt_off = s_rt[warp] + 16;
+    for (int rbase = 0; rbase < nruns; rbase += 16) {
+        unsigned beg = 0, len = 0;
+        const int r = rbase + lane;
+        if (lane < 16 && r < nruns) {
+            const int ct = ct_lo + r / ncy, cy = cy_lo + r % ncy;
+            const int row = (ct * g.ny + cy) * g.nx;
+            beg = P.cell_start[row + cx_lo];
+            len = P.cell_start[row + cx_hi + 1] - beg;
+        }
+        unsigned vend = len;                  // inclusive prefix sum of the run lengths
 #pragma unroll
-                    for (int u = 0; u < SCAN_U; ++u) {     // loads first: SCAN_U requests in flight
-                        const unsigned p = p0 + 32 * u + lane;
-                        o[u] = make_double4(0.0, 0.0, INFINITY, 0.0);     // t_obs = inf fails the filter
-                        if (p < end) o[u] = P.obs[p];
-                    }
+        for (int off = 1; off < 16; off <<= 1) {
+            const unsigned o = __shfl_up_sync(FULL, vend, off);
+            if (lane >= off) vend += o;
+        }
+        const unsigned total = __shfl_sync(FULL, vend, 15);
+        __syncwarp();
+        if (lane < 16) {
+            rt_vend[lane] = (int)vend;
+            rt_off[lane] = (int)beg - (int)(vend - len);     // position = virtual index + off
+        }
+        __syncwarp();
+        examined += total;
+        for (unsigned v0 = 0; v0 < total; v0 += 32 * SCAN_U) {
+            double4 o[SCAN_U];
 #pragma unroll
-                    for (int u = 0; u < SCAN_U; ++u) {
-                        const double dx = o[u].x - x, dy = o[u].y - y;
-                        const double d2 = dx * dx + dy * dy;      // cdist sqeuclidean, data.py:195-199
-                        const double dt = o[u].z - t;
-                        const unsigned oi = (unsigned)__double_as_longlong(o[u].w);
-                        const bool pass = (d2 < P.smax2) && (fabs(dt) < P.tmax) && (o[u].z <= t) &&   // data.py:206-211
-                                          ((long long)oi != leave);
-                        const unsigned bal = __ballot_sync(FULL, pass);
-                        if (pass) {
-                            const int e = pend_n + __popc(bal & lt_mask);
-                            B.pend_d2[e] = d2;
-                            B.pend_lt[e] = fabs(dt);
-                            B.pend_idx[e] = oi;
-                        }
-                        pend_n += __popc(bal);
-                    }
-                    if (pend_n >= 32) {
-                        in_window += pend_n;
-                        flush_pending<GV>(B, P, pend_n, m, truncated, lane);
-                    }
+            for (int u = 0; u < SCAN_U; ++u) {     // loads first: SCAN_U requests in flight
+                const unsigned v = v0 + 32 * u + lane;
+                o[u] = make_double4(0.0, 0.0, INFINITY, 0.0);     // t_obs = inf fails the filter
+                if (v < total) {
+                    int rr = 0;                    // first run with vend > v
+                    if (rt_vend[rr + 7] <= (int)v) rr += 8;
+                    if (rt_vend[rr + 3] <= (int)v) rr += 4;
+                    if (rt_vend[rr + 1] <= (int)v) rr += 2;
+                    if (rt_vend[rr] <= (int)v) rr += 1;
+                    o[u] = P.obs[(int)v + rt_off[rr]];
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_U; ++u) {
+                if (v0 + 32 * u < total) {         // warp-uniform
+                    const double dx = o[u].x - x, dy = o[u].y - y;
+                    const double d2 = dx * dx + dy * dy;      // cdist sqeuclidean, data.py:195-199
+                    const double dt = o[u].z - t;
+                    const unsigned oi = (unsigned)__double_as_longlong(o[u].w);
+                    const bool pass = (d2 < P.smax2) && (fabs(dt) < P.tmax) && (o[u].z <= t) &&   // data.py:206-211
+                                      ((long long)oi != leave);
+                    const unsigned bal = __ballot_sync(FULL, pass);
+                    if (pass) {
+                        const int e = pend_n + __popc(bal & lt_mask);
+                        B.pend_d2[e] = d2;
+                        B.pend_lt[e] = fabs(dt);
+                        B.pend_idx[e] = oi;
+                    }
+                    pend_n += __popc(bal);
+                }
+            }
+            if (pend_n >= 32) {
+                in_window += pend_n & ~31;
+                flush_pending<GV>(B, P, pend_n, m, truncated, false, lane);
             }
         }
     }
     in_window += pend_n;
-    flush_pending<GV>(B, P, pend_n, m, truncated, lane);
+    flush_pending<GV>(B, P, pend_n, m, truncated, true, lane);
     if (m > P.k) {
         select_k(B, m, P.k, lane);
         truncated = true;

@@ -1,0 +1,239 @@
+"""GPU tests at BASELINE.json's full sizes (C2, C3, C4, C5), through the C ABI.
+
+The oracle cannot run 5e9 .. 5e11 pairs or millions of kriging systems in seconds, so these
+tests use size-independent properties of the domain
+
+  * variogram: culled vs un-culled tile work lists (two independent paths through the pair
+    kernel), invariance under a permutation of the observations, exact scaling of the sums
+    when the values are multiplied by a power of two, partitions (GPUs) summing to the whole,
+    and a closed-form total of the pair counts;
+  * kriging: the weights sum to one, the two independent solvers (covariance-form Cholesky
+    and pivoted LU of the bordered system) agree, targets are independent of how the call is
+    batched, translation of all coordinates changes nothing,
+
+plus a direct comparison with the CPU oracle on a bounded sample of the same workload (a row
+block of the variogram triangle; a few hundred kriging targets against ALL observations).
+Tolerances are the north star's: counts bit-exact, sums 1e-12, kriging 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from oracle import kriging as ok
+from oracle import variogram as ov
+from stif_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+VARIO = dict(smax=30.0, tmax=30.0, ns=30, nt=30)
+C4_MODEL = ("sum_metric", "spherical", "spherical", "spherical")
+C4_PARAMS = [400, 60, 500, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0]
+C5_MODEL = ("product_sum", "spherical", "spherical", "spherical")
+C5_PARAMS = [300, 60, 0.8, 0.7, 0.15, 0.10, 0.4]
+
+
+def synth_variogram(n):
+    rng = np.random.default_rng(20261019)          # SURVEY 8(d) C2 / C3 generator
+    x = rng.uniform(0, 100, n)
+    y = rng.uniform(0, 100, n)
+    t = rng.integers(0, 365, n).astype(np.float64)
+    v = rng.normal(size=n)
+    return x, y, t, v
+
+
+def vario(ctx, x, y, t, v, flags=_native.VARIO_PEEL, **kw):
+    return ctx.variogram_host(x, y, t, v, VARIO["smax"], VARIO["tmax"], VARIO["ns"], VARIO["nt"],
+                              flags=flags, **kw)
+
+
+def assert_sums_close(a, b, rtol=1e-12):
+    assert np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def c2(ctx):
+    x, y, t, v = synth_variogram(100_000)
+    counts, sums = vario(ctx, x, y, t, v)
+    return (x, y, t, v), counts, sums
+
+
+def test_c2_culled_equals_unculled(ctx, c2):
+    (x, y, t, v), counts, sums = c2
+    st = ctx.variogram_stats()
+    counts2, sums2 = vario(ctx, x, y, t, v, flags=_native.VARIO_PEEL | _native.VARIO_NO_CULL)
+    st2 = ctx.variogram_stats()
+    assert st2["pairs_evaluated"] > 3 * st["pairs_evaluated"]      # really a different work list
+    assert np.array_equal(counts, counts2)
+    assert_sums_close(sums, sums2)
+    assert 0.030 < counts.sum() / (100_000 * 99_999 // 2) < 0.036  # 3.34 % binned
+
+
+def test_c2_permutation_and_power_of_two_scaling(ctx, c2):
+    (x, y, t, v), counts, sums = c2
+    p = np.random.default_rng(1).permutation(len(x))
+    # the peeled first pair (rows 0, 1 of the caller's arrays) is a property of the ORDER;
+    # compare without it
+    c_a, s_a = vario(ctx, x, y, t, v, flags=0)
+    c_b, s_b = vario(ctx, x[p], y[p], t[p], v[p], flags=0)
+    assert np.array_equal(c_a, c_b)
+    assert_sums_close(s_a, s_b)
+    c_c, s_c = vario(ctx, x, y, t, 4.0 * v, flags=0)
+    assert np.array_equal(c_a, c_c)
+    # every term scales exactly; only the (atomic) summation order may differ
+    assert_sums_close(s_c, 16.0 * s_a)
+
+
+def test_c2_row_block_against_oracle(ctx):
+    """Rows 0..9999 of the C2 observations: 5e7 pairs the oracle does in a fraction of a second."""
+    x, y, t, v = synth_variogram(100_000)
+    n = 10_000
+    counts, sums = vario(ctx, x[:n], y[:n], t[:n], v[:n])
+    h, c = ov.raw(np.column_stack([x[:n], y[:n]]), t[:n], v[:n], VARIO["smax"], VARIO["tmax"], VARIO["ns"],
+                  VARIO["nt"])
+    assert np.array_equal(counts.astype(np.float64), c)
+    assert_sums_close(sums, h)
+
+
+def test_c2_space_cut_only_total_count(ctx):
+    """With the time window wide open and one bin, the count is the number of pairs closer than
+    smax (lag == smax lands in bin 1 of 1 and is dropped, utils.py:171-172) -- checked against
+    an independent k-d tree count."""
+    x, y, t, v = synth_variogram(100_000)
+    smax = 2.0
+    counts, _ = ctx.variogram_host(x, y, t, v, smax, 1e9, 1, 1, flags=0)
+    # independent count: k-d tree (pairs counted in both orders, plus the n self pairs)
+    from scipy.spatial import cKDTree
+    tree = cKDTree(np.column_stack([x, y]))
+    both = int(tree.count_neighbors(tree, smax * (1.0 - 1e-15)))
+    assert int(counts.sum()) == (both - len(x)) // 2
+
+
+def test_c3_partitions_and_permutation(ctx):
+    """1M observations (5e11 pairs): 8 partitions (what 8 GPUs would each do) sum to the whole;
+    a permuted input gives the same counts."""
+    x, y, t, v = synth_variogram(1_000_000)
+    counts, sums = vario(ctx, x, y, t, v, flags=0)
+    pairs = 1_000_000 * 999_999 // 2
+    assert 0.030 < counts.sum() / pairs < 0.036
+    acc_c = np.zeros_like(counts)
+    acc_s = np.zeros_like(sums)
+    for part in range(8):
+        c, s = vario(ctx, x, y, t, v, flags=0, part=part, nparts=8)
+        acc_c += c
+        acc_s += s
+    assert np.array_equal(acc_c, counts)
+    assert_sums_close(acc_s, sums)
+    p = np.random.default_rng(2).permutation(len(x))
+    c_p, s_p = vario(ctx, x[p], y[p], t[p], v[p], flags=0)
+    assert np.array_equal(c_p, counts)
+    assert_sums_close(s_p, sums)
+
+
+# ---------------------------------------------------------------------------------------------
+def synth_kriging(n_obs, n_t, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1000, n_obs)
+    y = rng.uniform(0, 1000, n_obs)
+    t = rng.uniform(0, 365, n_obs)
+    z = np.sin(x / 150) + np.cos(y / 200) + 0.5 * np.sin(t / 30) + 0.3 * rng.normal(size=n_obs)
+    tx = rng.uniform(0, 1000, n_t)
+    ty = rng.uniform(0, 1000, n_t)
+    tt = rng.uniform(30, 365, n_t)
+    return (x, y, t, z), (tx, ty, tt)
+
+
+def close_rel(a, b, scale, rtol=1e-9):
+    return np.all(np.abs(a - b) <= rtol * scale)
+
+
+def test_c4_solvers_agree_weights_sum_to_one_batching(ctx):
+    (x, y, t, z), (tx, ty, tt) = synth_kriging(1_000_000, 200_000, 20261020)
+    ctx.kriging_set_obs(x, y, t, z)
+    ctx.kriging_set_model(*C4_MODEL, C4_PARAMS)
+    m1, s1, w1, g1, i1, n1 = ctx.kriging_predict_host(tx, ty, tt, 1, 50, 30.0, 30.0, flags=0, want_weights=True)
+    ss = ctx.kriging_solver_stats()
+    st = ctx.kriging_stats()
+    assert ss["cholesky_enabled"] and ss["cholesky_to_lu"] == 0 and st["targets_singular"] == 0
+    assert 200 < st["candidates_in_window"] / len(tx) < 260          # C-bar ~ 226
+    assert np.all(n1 == 50)
+    assert np.all(np.abs(w1.astype(np.float64).sum(axis=1) - 1.0) < 1e-5)   # float32 outputs
+    # the pivoted LU of the bordered system on the same targets
+    m2, s2, w2, g2, i2, n2 = ctx.kriging_predict_host(tx, ty, tt, 1, 50, 30.0, 30.0,
+                                                      flags=_native.KRIG_FORCE_LU, want_weights=True)
+    assert np.array_equal(i1, i2) and np.array_equal(g1, g2)
+    mscale = np.sum(np.abs(w1.astype(np.float64)) * np.abs(z[i1.astype(np.int64)]), axis=1)
+    vscale = np.sum(np.abs(w1.astype(np.float64) * g1), axis=1)
+    assert close_rel(m1, m2, mscale)
+    assert close_rel(s1 ** 2, s2 ** 2, vscale)
+    # a target's result does not depend on what else is in the call
+    sel = slice(70_000, 70_512)
+    m3, s3 = ctx.kriging_predict_host(tx[sel], ty[sel], tt[sel], 1, 50, 30.0, 30.0, flags=0)
+    assert np.array_equal(m3, m1[sel]) and np.array_equal(s3, s1[sel])
+
+
+def test_c4_sample_against_oracle(ctx):
+    (x, y, t, z), (tx, ty, tt) = synth_kriging(1_000_000, 300, 20261020)
+    ctx.kriging_set_obs(x, y, t, z)
+    ctx.kriging_set_model(*C4_MODEL, C4_PARAMS)
+    space, tsp = np.column_stack([x, y]), np.column_stack([tx, ty])
+    for f32 in (False, True):
+        flags = _native.KRIG_F32_STORAGE if f32 else 0
+        m, s, w, g, idx, nu = ctx.kriging_predict_host(tx, ty, tt, 1, 50, 30.0, 30.0, flags=flags,
+                                                       want_weights=True)
+        o = ok.predict(space, t, z, tsp, tt, C4_MODEL, C4_PARAMS, 1, 50, 30.0, 30.0, f32_storage=f32)
+        rows = o["tie"] == 0
+        assert rows.mean() > 0.99
+        assert np.array_equal(idx[rows], o["idx"][rows])           # neighbour sets identical
+        assert np.array_equal(nu[rows], o["n_used"][rows])
+        mscale = np.sum(np.abs(o["w"].astype(np.float64)) * np.abs(z[o["idx"].astype(np.int64)]), axis=1)
+        vscale = np.sum(np.abs(o["w"].astype(np.float64) * o["gamma"]), axis=1)
+        tol = 2.0 ** -22 if f32 else 1e-9
+        assert np.all(np.abs(m - o["mean"])[rows] <= tol * mscale[rows])
+        assert np.all(np.abs(s ** 2 - o["std"] ** 2)[rows] <= 4 * tol * vscale[rows])
+
+
+def test_c4_translation_invariance(ctx):
+    (x, y, t, z), (tx, ty, tt) = synth_kriging(1_000_000, 20_000, 20261020)
+    ctx.kriging_set_obs(x, y, t, z)
+    ctx.kriging_set_model(*C4_MODEL, C4_PARAMS)
+    m1, s1, w1, g1, i1, n1 = ctx.kriging_predict_host(tx, ty, tt, 1, 50, 30.0, 30.0, flags=0, want_weights=True)
+    # power-of-two shifts keep every coordinate difference exact
+    ctx.kriging_set_obs(x + 4096.0, y - 2048.0, t + 512.0, z)
+    m2, s2, w2, g2, i2, n2 = ctx.kriging_predict_host(tx + 4096.0, ty - 2048.0, tt + 512.0, 1, 50, 30.0, 30.0,
+                                                      flags=0, want_weights=True)
+    same = np.all(i1 == i2, axis=1)
+    assert same.mean() > 0.999          # differences are rounded at a different magnitude
+    mscale = np.sum(np.abs(w1.astype(np.float64)) * np.abs(z[i1.astype(np.int64)]), axis=1)
+    assert np.all(np.abs(m1 - m2)[same] <= 1e-7 * mscale[same])
+
+
+def test_c5_indicator_kriging_k100(ctx):
+    """2M observations, presence/absence residuals, product_sum, k = 100: the model is not a
+    valid variogram, every system goes through the pivoted LU; sample vs the oracle."""
+    rng = np.random.default_rng(20261021)
+    n_obs = 2_000_000
+    x = rng.uniform(0, 1000, n_obs)
+    y = rng.uniform(0, 1000, n_obs)
+    t = rng.uniform(0, 365, n_obs)
+    field = np.sin(x / 150) + np.cos(y / 200) + 0.5 * np.sin(t / 30)
+    presence = rng.uniform(size=n_obs) < 1.0 / (1.0 + np.exp(-2.0 * field))
+    z = presence.astype(np.float64) - presence.mean()
+    n_t = 20_000
+    tx, ty, tt = rng.uniform(0, 1000, n_t), rng.uniform(0, 1000, n_t), rng.uniform(30, 365, n_t)
+    ctx.kriging_set_obs(x, y, t, z)
+    ctx.kriging_set_model(*C5_MODEL, C5_PARAMS)
+    m, s, w, g, idx, nu = ctx.kriging_predict_host(tx, ty, tt, 1, 100, 30.0, 30.0, flags=0, want_weights=True)
+    ss, st = ctx.kriging_solver_stats(), ctx.kriging_stats()
+    assert not ss["cholesky_enabled"]
+    assert 420 < st["candidates_in_window"] / n_t < 510               # C-bar ~ 465
+    assert np.all(nu == 100)
+    w64 = w.astype(np.float64)      # float32 outputs; product_sum weights are large and of both signs
+    assert np.all(np.abs(w64.sum(axis=1) - 1.0) <= 1e-6 * np.abs(w64).sum(axis=1))
+    assert np.isfinite(m).all()
+    ns = 60
+    o = ok.predict(np.column_stack([x, y]), t, z, np.column_stack([tx[:ns], ty[:ns]]), tt[:ns], C5_MODEL,
+                   C5_PARAMS, 1, 100, 30.0, 30.0, f32_storage=False)
+    rows = o["tie"] == 0
+    assert rows.mean() > 0.9
+    assert np.array_equal(idx[:ns][rows], o["idx"][rows])
+    mscale = np.sum(np.abs(o["w"].astype(np.float64)) * np.abs(z[o["idx"].astype(np.int64)]), axis=1)
+    assert np.all(np.abs(m[:ns] - o["mean"])[rows] <= 1e-9 * mscale[rows])

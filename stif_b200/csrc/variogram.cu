@@ -384,13 +384,34 @@ __global__ void reduce_kernel(Params P, int nblocks, const double *x, const doub
                               double ws, double wt, int peel, unsigned long long *counts,
                               double *sums)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.n_bins) return;
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // 256 threads = 32 bins x 8 slices of the block list: slice s adds the partials of blocks
+    // k = s, s+8, ... in increasing k (coalesced over the bins), then the 8 slices are combined
+    // in a fixed tree -- the same order for any launch, so the result is deterministic.
+    __shared__ double s_acc[8][32];
+    __shared__ unsigned long long s_cnt8[8][32];
+    const int bl = threadIdx.x & 31, ks = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + bl;
+    {
+        double a = 0.0;
+        unsigned long long cc = 0;
+        if (b < P.n_bins) {
+#pragma unroll 4
+            for (int k = ks; k < nblocks; k += 8) {
+                a += P.partial_sum[(size_t)k * P.n_bins + b];
+                cc += P.partial_cnt[(size_t)k * P.n_bins + b];
+            }
+        }
+        s_acc[ks][bl] = a;
+        s_cnt8[ks][bl] = cc;
+    }
+    __syncthreads();
+    if (ks != 0 || b >= P.n_bins) return;
+    double acc[8];
     unsigned long long c = 0;
-    for (int k = 0; k < nblocks; ++k) {
-        acc[k & 7] += P.partial_sum[(size_t)k * P.n_bins + b];
-        c += P.partial_cnt[(size_t)k * P.n_bins + b];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        acc[q] = s_acc[q][bl];
+        c += s_cnt8[q][bl];
     }
     double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     if (peel && n >= 2) {
@@ -732,7 +753,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
 
     // 5. reduce (+ peel fix-up on partition 0)
     const int peel = ((flags & STIF_VARIO_PEEL) && part == 0) ? 1 : 0;
-    reduce_kernel<<<(n_bins + 127) / 128, 128, 0, st>>>(
+    reduce_kernel<<<(n_bins + 31) / 32, 256, 0, st>>>(
         P, grid, x, y, t, v, n, smax, ws, wt, peel,
         reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
     STIF_CUDA(cudaGetLastError());
@@ -863,7 +884,7 @@ extern "C" int stif_variogram_sampled_dev(stif_ctx *c, const double *x, const do
     sampled_kernel<<<grid, VT, smem, st>>>(P, Q);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[2], st));
-    reduce_kernel<<<(n_bins + 127) / 128, 128, 0, st>>>(
+    reduce_kernel<<<(n_bins + 31) / 32, 256, 0, st>>>(
         P, grid, x, y, t, v, n, smax, ws, wt, 0, reinterpret_cast<unsigned long long *>(counts_dev),
         sums_dev);
     STIF_CUDA(cudaGetLastError());

@@ -247,7 +247,10 @@ def run_b200(args):
         "algorithmic_lane_instr_per_pair": lane_instr_per_pair,
         "kernel_ms": pair_ms_avg,
         "pairs_evaluated_frac": stats["pairs_evaluated"] * world / pairs,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full on this
+        # workload (profiles/r01_ncu_bench_v4_pair_summary.txt); = the 32 B/observation
+        "traffic": (3255552 if (workload == "c2" and world == 1) else None),
+        "traffic_unit": "bytes per launch (ncu capture, C2)",
         "note": "tile pairs outside the time window are culled (SURVEY 8d allows it); rate is "
                 "per algorithmic pair, so frac may exceed the un-culled FP64 bound",
     }
@@ -351,11 +354,13 @@ def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, m
     peak_tf = 2 * dfma_rate / 1e12
 
     (hx, _a), (hy, _b), (ht, _c) = pinned(tx), pinned(ty), pinned(tt)
-    ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1])
+    (hm, _d), (hs, _e) = pinned(np.zeros(n_t)), pinned(np.zeros(n_t))      # pinned result buffers
+    ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1], out_mean=hm, out_std=hs)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        m_host, s_host = ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1])
+        m_host, s_host = ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1],
+                                                  out_mean=hm, out_std=hs)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / steps
     return {
@@ -371,10 +376,14 @@ def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, m
         "phases_ms": {"search": max_over_ranks(search_ms) / steps, "solve": solve_ms_avg},
         "e2e": {"value": n_t * world / e2e_s, "unit": "predictions/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t},
-        "gpu_launches": 4 * steps,
+        "gpu_launches": 5 * steps,
         "roofline": {"bound": "fp64", "kernel": "stif::krig::solve_chol_kernel", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s per GPU", "frac": achieved / peak_tf,
-                     "flops_per_prediction": flops, "kernel_ms": solve_ms_avg, "traffic": None,
+                     "flops_per_prediction": flops, "kernel_ms": solve_ms_avg,
+                     # dram read + write of one launch over 1.25M targets, ncu --set full
+                     # (profiles/r01_ncu_bench_v4_chol_summary.txt): selection scratch + gathers
+                     "traffic": (1261838848 if n_t == C4_TARGETS_PER_GPU else None),
+                     "traffic_unit": "bytes per launch (ncu capture, 1.25M targets)",
                      "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)"},
         "clocks": clocks,
         "checksum": {"mean_sum": float(np.nansum(m_host)), "nan": int(np.isnan(m_host).sum())},

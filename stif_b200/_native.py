@@ -242,7 +242,10 @@ class Context:
         return out.reshape(shape)
 
     def kriging_predict_host(self, tx, ty, tt, min_pts, max_pts, space_dist_max, time_dist_max,
-                             leave_out=None, flags=KRIG_F32_STORAGE, want_weights=False):
+                             leave_out=None, flags=KRIG_F32_STORAGE, want_weights=False,
+                             out_mean=None, out_std=None):
+        """out_mean / out_std: optional preallocated float64 arrays of n targets (e.g. pinned
+        host memory, which makes the device-to-host copy of the result a plain DMA)."""
         tx, ty, tt = _f64(tx), _f64(ty), _f64(tt)
         n = len(tx)
         if not (len(ty) == n and len(tt) == n):
@@ -252,8 +255,13 @@ class Context:
             lo = np.ascontiguousarray(leave_out, dtype=np.int64)
             if len(lo) != n:
                 raise ValueError("leave_out_idxs must have one entry per target")
-        mean = np.zeros(n, dtype=np.float64)
-        std = np.zeros(n, dtype=np.float64)
+        def _out(a):
+            if a is None:
+                return np.empty(n, dtype=np.float64)
+            if a.dtype != np.float64 or a.shape != (n,) or not a.flags.c_contiguous:
+                raise ValueError("out_mean / out_std must be contiguous float64 arrays of n targets")
+            return a
+        mean, std = _out(out_mean), _out(out_std)
         w = g = idx = nused = None
         if want_weights:
             w = np.zeros((n, int(max_pts)), dtype=np.float32)

@@ -767,13 +767,17 @@ struct SolveSmem {
     unsigned *ids;                   // [k+1]
     int *piv;                        // [8] pivot rows of the current panel
     unsigned long long *scale;       // bits of max |entry| of the assembled system
+    double *pvals;                   // [8] pivot row of the current column (panel entries), 16-B aligned
+    unsigned long long *pkey;        // [8] per-warp pivot keys of the current column
 };
 
 __device__ __forceinline__ SolveSmem carve(double *base, int k, int ld, int nr)
 {
     SolveSmem S;
     S.A = base;
-    S.xs = base + (size_t)nr * ld;
+    S.pvals = base + (size_t)nr * ld;            // nr is a multiple of 8: 16-byte aligned
+    S.pkey = reinterpret_cast<unsigned long long *>(S.pvals + 8);
+    S.xs = S.pvals + 16;
     S.ys = S.xs + (k + 1);
     S.ts = S.ys + (k + 1);
     S.sol = S.ts + (k + 1);
@@ -973,12 +977,11 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 //      round-robin to the warps.  512 FMAs per tensor instruction instead of 32 per DFMA: the
 //      scalar shared-memory LU was issue-bound (ncu: 78 % issue-active at 27 % FP64 pipe).
 // The right-hand side is column n and is transformed with the matrix.
-template <int WPT, int NS>
+template <int WPT>
 __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int nr, int nc)
 {
     extern __shared__ __align__(16) double smem_d[];
     constexpr int NT = WPT * 32;
-    // NS = row slots of the panel step: 32 NS >= k + 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ld = P.ld;
     const SolveSmem S = carve(smem_d, P.k, ld, nr);
@@ -999,57 +1002,47 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
         const double tol = __longlong_as_double((long long)*S.scale) * (1.8e-15 * (double)n);
 
         for (int jb = 0; jb < n; jb += 8) {
-            if (warp == 0) {
+            {
                 // ---- 1. panel factorisation, columns jb .. jb+7 (pivot columns only while < n) ----
-                // Lanes own rows lane + 32 s and keep their 8 panel entries in registers; rows are
-                // not moved: pos[s] is the row's position after the swaps so far, the pivot row is
-                // broadcast by shuffles, and every row is written back to its final position.
-                double a[NS][8];
-                int pos[NS];
+                // The whole CTA: thread r owns row r and keeps its 8 panel entries in registers.
+                // Rows are not moved: `pos` is the row's position after the swaps so far.  Per
+                // column: warp-level REDUX on a packed magnitude/row key, the per-warp keys meet
+                // in shared memory (barrier), the owner of the pivot row publishes its entries
+                // (barrier), every thread eliminates its own row.  Rows are written back to their
+                // final positions at the end.
+                double a[8];
+                int pos = tid;
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const int r = lane + 32 * s;
-                    pos[s] = r;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) a[s][c] = (r >= jb && r < n) ? A[r * ld + jb + c] : 0.0;
-                }
+                for (int c = 0; c < 8; ++c) a[c] = (tid >= jb && tid < n) ? A[tid * ld + jb + c] : 0.0;
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                     const int j = jb + jj;
-                    if (j < n) {
+                    if (j < n) {          // CTA-uniform
                         unsigned long long key = 0ull;
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) {
-                            if (pos[s] >= j && pos[s] < n) {
-                                const unsigned long long kb = pivot_key(a[s][jj], pos[s]);
-                                key = kb > key ? kb : key;
-                            }
-                        }
+                        if (pos >= j && pos < n) key = pivot_key(a[jj], pos);
                         key = warp_max_u64(key);
+                        if (lane == 0) S.pkey[warp] = key;
+                        __syncthreads();
+#pragma unroll
+                        for (int w = 0; w < WPT; ++w) {
+                            const unsigned long long kw = S.pkey[w];
+                            key = kw > key ? kw : key;
+                        }
                         const int bi = 255 - (int)(key & 0xffull);
                         const double bv = __longlong_as_double((long long)(key & ~0xffull));
                         const bool ok = bv > tol && bv < INFINITY;
                         if (!ok) singular = true;
                         const int prow = ok ? bi : j;     // row swapped with row j (j = no swap)
-                        // pivot row -> all lanes (owner lane by ballot, owner slot is warp-uniform)
+                        if (pos == prow) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) S.pvals[c] = a[c];
+                        }
+                        __syncthreads();
                         double u[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) u[c] = 0.0;
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) {
-                            const unsigned own = __ballot_sync(FULL, pos[s] == prow);
-                            if (own) {
-                                const int owner = __ffs(own) - 1;
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    if (c >= jj) u[c] = __shfl_sync(FULL, a[s][c], owner);
-                            }
-                        }
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) {
-                            if (pos[s] == prow) pos[s] = j;
-                            else if (pos[s] == j) pos[s] = prow;
-                        }
+                        for (int c = 0; c < 8; ++c) u[c] = (c >= jj) ? S.pvals[c] : 0.0;
+                        if (pos == prow) pos = j;
+                        else if (pos == j) pos = prow;
                         double pinv = 0.0;
                         if (ok) {      // 1 / pivot: MUFU.RCP64H + two Newton steps
                             double y;
@@ -1057,28 +1050,21 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
                             y = __fma_rn(y, __fma_rn(-u[jj], y, 1.0), y);
                             pinv = __fma_rn(y, __fma_rn(-u[jj], y, 1.0), y);
                         }
-                        if (lane == 0) S.piv[jj] = prow;
+                        if (tid == 0) S.piv[jj] = prow;
+                        if (pos > j && pos < n) {
+                            const double mneg = -(a[jj] * pinv);   // negated multiplier
+                            a[jj] = mneg;
 #pragma unroll
-                        for (int s = 0; s < NS; ++s) {
-                            if (pos[s] > j && pos[s] < n) {
-                                const double mneg = -(a[s][jj] * pinv);   // negated multiplier
-                                a[s][jj] = mneg;
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    if (c > jj) a[s][c] = __fma_rn(mneg, u[c], a[s][c]);
-                            } else if (pos[s] == j) {
-                                a[s][jj] = pinv;
-                            }
+                            for (int c = 0; c < 8; ++c)
+                                if (c > jj) a[c] = __fma_rn(mneg, u[c], a[c]);
+                        } else if (pos == j) {
+                            a[jj] = pinv;
                         }
                     }
                 }
+                if (tid >= jb && tid < n) {
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const int r = lane + 32 * s;
-                    if (r >= jb && r < n) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) A[pos[s] * ld + jb + c] = a[s][c];
-                    }
+                    for (int c = 0; c < 8; ++c) A[pos * ld + jb + c] = a[c];
                 }
             }
             __syncthreads();
@@ -1491,7 +1477,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     const int nr_pad = (k + 1 + 7) / 8 * 8;      // rows of the padded system
     const int nc_pad = (k + 2 + 7) / 8 * 8;      // columns incl. the right-hand side
     const int ld = nc_pad + 1;                   // odd leading dimension
-    const int cta_doubles = nr_pad * ld + 5 * (k + 1) + 1 + 4 + (k + 2) / 2 + 1;
+    const int cta_doubles = nr_pad * ld + 16 + 5 * (k + 1) + 1 + 4 + (k + 2) / 2 + 1;
     const size_t solve_smem = sizeof(double) * (size_t)cta_doubles;
 
     CholParams CX;
@@ -1637,9 +1623,9 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             QP.count = fail_count;
         }
         {
-#define STIF_SOLVE(WPT_, NS_)                                                                      \
+#define STIF_SOLVE(WPT_)                                                                           \
     do {                                                                                           \
-        auto kern = solve_blk_kernel<WPT_, NS_>;                                                   \
+        auto kern = solve_blk_kernel<WPT_>;                                                        \
         STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        (int)solve_smem));                                          \
         int occ = 0;                                                                               \
@@ -1649,13 +1635,11 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         if (gsz > nc) gsz = nc;                                                                    \
         kern<<<(unsigned)gsz, WPT_ * 32, solve_smem, st>>>(QP, nr_pad, nc_pad);                    \
     } while (0)
-            if (k <= 16) STIF_SOLVE(1, 1);
-            else if (k <= 31) STIF_SOLVE(2, 1);
-            else if (k <= 63) STIF_SOLVE(LU_WPT_MID, 2);
-            else if (k <= 64) STIF_SOLVE(LU_WPT_MID, 3);
-            else if (k <= 95) STIF_SOLVE(LU_WPT_BIG, 3);
-            else if (k <= 127) STIF_SOLVE(LU_WPT_BIG, 4);
-            else STIF_SOLVE(LU_WPT_BIG, 5);
+            // one thread per row of the bordered system: 32 WPT >= k + 1
+            if (k <= 31) STIF_SOLVE(1);
+            else if (k <= 63) STIF_SOLVE(2);
+            else if (k <= 127) STIF_SOLVE(4);
+            else STIF_SOLVE(8);
 #undef STIF_SOLVE
         }
         STIF_CUDA(cudaGetLastError());

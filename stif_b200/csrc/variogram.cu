@@ -190,31 +190,31 @@ __device__ __forceinline__ void bin_entry(const Smem &S, const Params &P, int wa
         const double dy = __dsub_rn(pi.y, pj.y);
         const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
         const double lag_t = fabs(__dsub_rn(pi.z, pj.z));
-        long long bs;
+        // both bin indices are bounded by the cut-offs that let the pair in (lag <= max =
+        // n_bins * width), so 32-bit conversions are exact
+        int bs;
         if (P.use_thr) {
             // trunc(sqrt_rn(d2)*inv_ws) is monotone in d2: look the bin up in the exact d2
             // thresholds (host-bisected with the reference's formula) from a float guess
-            int b = __float2int_rz(fminf(__fsqrt_rn(__double2float_rn(d2)) * P.inv_ws_f,
-                                         (float)P.n_space_bins));
+            float f = __double2float_rn(d2), sq;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
+            int b = __float2int_rz(fminf(sq * P.inv_ws_f, (float)P.n_space_bins));
             b = b < 0 ? 0 : b;
             while (d2 < S.s_thr[b]) --b;
             while (d2 >= S.s_thr[b + 1]) ++b;
             bs = b;
         } else {
-            bs = __double2ll_rz(__dmul_rn(__dsqrt_rn(d2), P.inv_ws));
+            bs = __double2int_rz(__dmul_rn(__dsqrt_rn(d2), P.inv_ws));
         }
-        const long long bt = __double2ll_rz(__dmul_rn(lag_t, P.inv_wt));
-        if (bs >= 0 && bs < P.n_space_bins && bt >= 0 && bt < P.n_time_bins) {
-            double a, b;
+        const int bt = __double2int_rz(__dmul_rn(lag_t, P.inv_wt));
+        if ((unsigned)bs < (unsigned)P.n_space_bins && (unsigned)bt < (unsigned)P.n_time_bins) {
             if (P.mode == 0) {
-                a = __dsub_rn(pi.w, pj.w);
-                b = a;
+                const double a = __dsub_rn(pi.w, pj.w);
+                val = __dmul_rn(a, a);
             } else {
-                a = __dsub_rn(pi.w, P.mean);
-                b = __dsub_rn(pj.w, P.mean);
+                val = __dmul_rn(__dsub_rn(pi.w, P.mean), __dsub_rn(pj.w, P.mean));
             }
-            bin = (int)bs * P.n_time_bins + (int)bt;
-            val = __dmul_rn(a, b);
+            bin = bs * P.n_time_bins + bt;
         }
     }
     accumulate(S, bin, val);

@@ -66,6 +66,16 @@ def synth_kriging(n_obs, n_targets, rank=0):
     return (x, y, t, z), (tx, ty, tt)
 
 
+def measured_hbm_gbs():
+    """HBM copy bandwidth from MEASURED_PEAKS.json (driver-written), else the profiling guide's
+    fallback for B200."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6551.4
+
+
 def kriging_flops(k, cbar, f_gamma=42.0):
     """algorithmic FP64 flops per prediction (FMA = 2)."""
     return cbar * f_gamma + k * (k - 1) / 2 * f_gamma + (k + 1) ** 3 / 3 + 2 * (k + 1) ** 2 + 4 * k
@@ -384,7 +394,14 @@ def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, m
                      # (profiles/r01_ncu_bench_v4_chol_summary.txt): selection scratch + gathers
                      "traffic": (1261838848 if n_t == C4_TARGETS_PER_GPU else None),
                      "traffic_unit": "bytes per launch (ncu capture, 1.25M targets)",
-                     "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)"},
+                     "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)",
+                     "frac_incl_search": (n_t * flops / (ms_per_step * 1e-3) / 1e12) / peak_tf},
+        # neighbour search: candidates examined per second and the L2/HBM read rate
+        # that implies (32 B per candidate; the 32 MB observation set is L2-resident)
+        "search": {"kernel": "stif::krig::search_kernel",
+                   "candidates_examined_per_s": st["candidates_examined"] / (max_over_ranks(search_ms) / steps * 1e-3),
+                   "read_GBps": 32.0 * st["candidates_examined"] / (max_over_ranks(search_ms) / steps * 1e-3) / 1e9,
+                   "hbm_peak_GBps": measured_hbm_gbs()},
         "clocks": clocks,
         "checksum": {"mean_sum": float(np.nansum(m_host)), "nan": int(np.isnan(m_host).sum())},
     }

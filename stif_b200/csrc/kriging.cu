@@ -730,7 +730,25 @@ struct SolveParams {
     int *nused_out;              // nullable
     unsigned *singular;          // [n] chunk-local flag
     const unsigned *count;       // nullable: number of entries of `order` to process (device)
+    const double4 *obs4;         // observations {x, y, t, resid}, original order
+    const unsigned *pairtab;     // pair e -> a | b << 8 | ... (b < a), see CholParams::pairtab
+    // product / product_sum with spherical marginals and every neighbour pair inside both
+    // ranges: gamma_s = pbs + h (pas - pcs h^2), gamma_t = pbt + t (pat - pct t^2)
+    double pbs, pas, pcs, pbt, pat, pct;
 };
+
+enum { LU_GENERIC = 0, LU_PRODUCT_SPH = 1, LU_PRODUCT_SUM_SPH = 2 };
+
+// sqrt for the assembly fast paths: MUFU.RSQ64H + one cubic correction (<= ~1 ulp), x > 0
+__device__ __forceinline__ double sqrt_cubic_lu(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = __fma_rn(-t, y, 1.0);
+    const double p = __fma_rn(0.375, e, 0.5);
+    return __fma_rn(t * e, p, t);
+}
 
 // numpy's pairwise sum of a row of length n <= 128 (numpy/_core/src/umath/loops_utils.h.src),
 // preceded by the reduction's initial 0: bit-compatible with np.sum(row) -- checked against
@@ -807,13 +825,24 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long ke
 
 // Loads the selection, assembles [A | b] (predictor.py:573-585) and zero-fills the padding.
 // Returns m (neighbours used); m <= 0 means the outputs were written (zeros) and the CTA is done.
-template <int NT>
-__device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl, int64_t tg, int tid,
-                           int nr, int nc)
+// One neighbour per thread, fetched ahead of time into registers by the persistent loop.
+struct LuPrefetch {
+    unsigned tl;      // chunk-local target id
+    int m;            // neighbours (<= 0: nothing to solve)
+    unsigned id;      // this thread's neighbour (e = tid)
+    double4 o;        // its {x, y, t, resid}
+    double g;         // its gamma-vector entry
+};
+
+// Loads the selection, assembles [A | b] (predictor.py:573-585) and zero-fills the padding.
+// Returns m (neighbours used); m <= 0 means the outputs were written (zeros) and the CTA is done.
+template <int NT, int LUV>
+__device__ int solve_setup(const SolveParams &P, const SolveSmem &S, const LuPrefetch &F, int64_t tg,
+                           int tid, int nr, int nc)
 {
     const int k = P.k, ld = P.ld;
     double *A = S.A;
-    const int m = P.sel_n[tl];
+    const int m = F.m;
     if (m <= 0) {
         if (tid == 0) {
             P.mean[tg] = 0.0;
@@ -832,15 +861,14 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl
     for (int e = n * ld + tid; e < nr * ld; e += NT) A[e] = 0.0;
     for (int r = tid; r < n; r += NT)
         for (int c = n + 1; c < nc; ++c) A[r * ld + c] = 0.0;
-    for (int e = tid; e < m; e += NT) {
-        const unsigned id = P.sel_idx[(size_t)tl * k + e];
-        S.ids[e] = id;
-        S.xs[e] = P.ox[id];
-        S.ys[e] = P.oy[id];
-        S.ts[e] = P.ot[id];
-        const double g = P.sel_gamma[(size_t)tl * k + e];
-        S.g0[e] = g;
-        A[e * ld + n] = g;        // rhs = [gamma_vector; 1]   predictor.py:582-585
+    if (tid < m) {                // NT >= k + 1: one neighbour per thread
+        const int e = tid;
+        S.ids[e] = F.id;
+        S.xs[e] = F.o.x;
+        S.ys[e] = F.o.y;
+        S.ts[e] = F.o.z;
+        S.g0[e] = F.g;
+        A[e * ld + n] = F.g;      // rhs = [gamma_vector; 1]   predictor.py:582-585
         A[e * ld + m] = 1.0;      // Lagrange column            predictor.py:578
         A[m * ld + e] = 1.0;      // Lagrange row
     }
@@ -855,21 +883,26 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, unsigned tl
     double amax = fmax(fabs(gdiag), 1.0);   // largest |entry| (the border holds ones)
     for (int e = tid; e < m; e += NT) A[e * ld + e] = gdiag;
     const int npairs = m * (m - 1) / 2;
-    int a = 0, off = tid;  // pair (a, a+1+off)
     for (int e = tid; e < npairs; e += NT) {
-        while (off >= m - 1 - a) {
-            off -= (m - 1 - a);
-            ++a;
-        }
-        const int b = a + 1 + off;
+        const unsigned w = __ldg(P.pairtab + e);
+        const int a = w & 0xff, b = (w >> 8) & 0xff;       // b < a
         const double dx = S.xs[a] - S.xs[b], dy = S.ys[a] - S.ys[b];
-        const double h = sqrt(dx * dx + dy * dy);          // utils.py:40-44
         const double lt = fabs(S.ts[a] - S.ts[b]);         // utils.py:19-22
-        const double g = gamma_st(P.M, h, lt);
+        double g;
+        if (LUV == LU_GENERIC) {
+            const double h = sqrt(dx * dx + dy * dy);      // utils.py:40-44
+            g = gamma_st(P.M, h, lt);
+        } else {
+            const double d2 = __fma_rn(dy, dy, dx * dx) + 1e-290;    // sqrt(0) -> 1e-145, no 0 * inf
+            const double h = sqrt_cubic_lu(d2);
+            const double gs = __fma_rn(h, __fma_rn(-P.pcs, d2, P.pas), P.pbs);
+            const double gt = __fma_rn(lt, __fma_rn(-P.pct, lt * lt, P.pat), P.pbt);
+            const double pr = gs * gt;
+            g = (LUV == LU_PRODUCT_SUM_SPH) ? __fma_rn(P.M.k, pr, pr) : pr;
+        }
         A[a * ld + b] = g;
         A[b * ld + a] = g;
         amax = fmax(amax, fabs(g));         // fmax ignores NaN
-        off += NT;
     }
     {
         const unsigned long long wm = warp_max_u64((unsigned long long)__double_as_longlong(amax));
@@ -977,7 +1010,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 //      round-robin to the warps.  512 FMAs per tensor instruction instead of 32 per DFMA: the
 //      scalar shared-memory LU was issue-bound (ncu: 78 % issue-active at 27 % FP64 pipe).
 // The right-hand side is column n and is transformed with the matrix.
-template <int WPT>
+template <int WPT, int LUV>
 __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int nr, int nc)
 {
     extern __shared__ __align__(16) double smem_d[];
@@ -987,13 +1020,42 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
     const SolveSmem S = carve(smem_d, P.k, ld, nr);
     double *A = S.A;
     const int n_work = P.count ? (int)*P.count : P.n;
-    // persistent CTAs: targets in visit order, strided over the grid
+    // persistent CTAs: targets in visit order, strided over the grid.  The next target's
+    // selection is fetched into registers (one neighbour per thread) in three stages spread
+    // over the current target's phases, so no dependent global-load chain sits at the loop top.
+    LuPrefetch F, N;
+    F.tl = 0u; F.m = 0; F.id = 0u; F.o = make_double4(0.0, 0.0, 0.0, 0.0); F.g = 0.0;
+    N = F;
+    bool has_next = false;
+    auto fetch_ids = [&]() {
+        N.m = has_next ? P.sel_n[N.tl] : 0;
+        if (has_next && tid < P.k) N.id = P.sel_idx[(size_t)N.tl * P.k + tid];
+    };
+    auto fetch_obs = [&]() {
+        if (tid < N.m) {
+            N.o = P.obs4[N.id];
+            N.g = P.sel_gamma[(size_t)N.tl * P.k + tid];
+        }
+    };
+    if ((int)blockIdx.x < n_work) {
+        has_next = true;
+        N.tl = P.order[blockIdx.x];
+        fetch_ids();
+        fetch_obs();
+    }
     for (int slot = blockIdx.x; slot < n_work; slot += gridDim.x) {
         __syncthreads();   // the previous target's epilogue is done with the shared arrays
-        const unsigned tl = P.order[slot];
+        F = N;
+        const unsigned tl = F.tl;
         const int64_t tg = P.c0 + tl;
-        const int m = solve_setup<NT>(P, S, tl, tg, tid, nr, nc);
-        if (m <= 0) continue;
+        has_next = slot + (int)gridDim.x < n_work;
+        if (has_next) N.tl = P.order[slot + gridDim.x];
+        const int m = solve_setup<NT, LUV>(P, S, F, tg, tid, nr, nc);
+        fetch_ids();
+        if (m <= 0) {
+            fetch_obs();
+            continue;
+        }
         const int n = m + 1;
         bool singular = false;
         // rank tolerance: a pivot below n * 8 eps * max|entry| is rounding noise of an exactly
@@ -1112,6 +1174,7 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
             }
             __syncthreads();
         }
+        fetch_obs();
         if (warp == 0) solve_finish(P, S, m, tl, tg, lane, singular);
     }
 }
@@ -1483,6 +1546,13 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     CholParams CX;
     const int chol_var = chol_plan(c->model, M, flags, smax, tmax, CX);
     CX.obs4 = c->k_obs4.as<double4>();
+    // pivoted-LU assembly fast path: product / product_sum, spherical marginals, every neighbour
+    // pair inside both ranges (same bound as chol_plan)
+    int lu_var = LU_GENERIC;
+    if ((M.st == STIF_ST_PRODUCT || M.st == STIF_ST_PRODUCT_SUM) && M.ks == STIF_M_SPHERICAL &&
+        M.kt == STIF_M_SPHERICAL && M.rs > 0.0 && M.rt > 0.0 && 2.0 * smax * (1.0 + 1e-9) <= M.rs &&
+        tmax * (1.0 + 1e-9) <= M.rt && isfinite(M.is) && isfinite(M.it))
+        lu_var = (M.st == STIF_ST_PRODUCT_SUM) ? LU_PRODUCT_SUM_SPH : LU_PRODUCT_SPH;
     if (!c->k_pairtab.p) {
         std::vector<unsigned> tab;
         build_pair_table(tab);
@@ -1580,6 +1650,10 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         QP.nused_out = n_used_out;
         QP.singular = singular;
         QP.count = nullptr;
+        QP.obs4 = c->k_obs4.as<double4>();
+        QP.pairtab = c->k_pairtab.as<unsigned>();
+        QP.pbs = M.bs; QP.pas = 1.5 * M.c0s * M.is; QP.pcs = 0.5 * M.c0s * M.is * M.is * M.is;
+        QP.pbt = M.bt; QP.pat = 1.5 * M.c0t * M.it; QP.pct = 0.5 * M.c0t * M.it * M.it * M.it;
         // ---- covariance-form Cholesky (valid models), then the pivoted LU for the rest ----
         unsigned *fail_list = c->k_scratch[S_FAIL].as<unsigned>();
         unsigned *fail_count = fail_list + chunk;
@@ -1623,9 +1697,9 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             QP.count = fail_count;
         }
         {
-#define STIF_SOLVE(WPT_)                                                                           \
+#define STIF_SOLVE_V(WPT_, LUV_)                                                                   \
     do {                                                                                           \
-        auto kern = solve_blk_kernel<WPT_>;                                                        \
+        auto kern = solve_blk_kernel<WPT_, LUV_>;                                                  \
         STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        (int)solve_smem));                                          \
         int occ = 0;                                                                               \
@@ -1635,12 +1709,19 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         if (gsz > nc) gsz = nc;                                                                    \
         kern<<<(unsigned)gsz, WPT_ * 32, solve_smem, st>>>(QP, nr_pad, nc_pad);                    \
     } while (0)
+#define STIF_SOLVE(WPT_)                                                                           \
+    do {                                                                                           \
+        if (lu_var == LU_PRODUCT_SUM_SPH) STIF_SOLVE_V(WPT_, LU_PRODUCT_SUM_SPH);                  \
+        else if (lu_var == LU_PRODUCT_SPH) STIF_SOLVE_V(WPT_, LU_PRODUCT_SPH);                     \
+        else STIF_SOLVE_V(WPT_, LU_GENERIC);                                                       \
+    } while (0)
             // one thread per row of the bordered system: 32 WPT >= k + 1
             if (k <= 31) STIF_SOLVE(1);
             else if (k <= 63) STIF_SOLVE(2);
             else if (k <= 127) STIF_SOLVE(4);
             else STIF_SOLVE(8);
 #undef STIF_SOLVE
+#undef STIF_SOLVE_V
         }
         STIF_CUDA(cudaGetLastError());
         stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,

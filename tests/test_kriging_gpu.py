@@ -122,6 +122,45 @@ def test_cholesky_hands_indefinite_systems_to_lu(ctx):
     compare(g2, o, z, False)
 
 
+@pytest.mark.parametrize("models,params,k,radii", [
+    # every Cholesky kernel variant: {sum, metric, sum_metric} x spherical, with and without the
+    # range clamp (radii beyond the ranges), two- and four-column-slot kernels (k <= 64 / > 64)
+    (("sum", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 40, (30.0, 30.0)),
+    (("sum", "spherical", "spherical", "spherical"), [20, 10, 0.8, 0.7, 0.15, 0.10], 40, (30.0, 30.0)),
+    (("metric", "spherical", "spherical", "spherical"), [100, 1.0, 0.05, 5.0], 24, (30.0, 30.0)),
+    (SUM_METRIC, [40, 20, 50, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0], 50, (30.0, 30.0)),
+    (SUM_METRIC, [40, 20, 50, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0], 70, (40.0, 40.0)),
+    (("sum", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 90, (40.0, 40.0)),
+    (("sum_metric", "gaussian", "gaussian", "spherical"), P_SUM_METRIC, 80, (40.0, 40.0)),
+])
+def test_cholesky_variants(ctx, models, params, k, radii):
+    space, t, z, tsp, tt = synth(30000, 200, seed=31, extent=200.0)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32=False)
+    ss = ctx.kriging_solver_stats()
+    assert ss["cholesky_enabled"]
+    o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32_storage=False)
+    compare(g, o, z, False)
+    # and the same through the pivoted LU
+    g2 = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32=False, solver="lu")
+    compare(g2, o, z, False)
+
+
+@pytest.mark.parametrize("models,params,k,radii", [
+    # pivoted-LU assembly variants: polynomial product / product_sum (inside the ranges) and the
+    # verbatim formula (beyond them, or other marginals)
+    (PRODUCT_SUM, P_PRODUCT_SUM, 50, (30.0, 30.0)),
+    (PRODUCT_SUM, [40, 20, 0.8, 0.7, 0.15, 0.10, 0.4], 50, (30.0, 30.0)),
+    (("product", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 70, (40.0, 40.0)),
+    (("product_sum", "gaussian", "spherical", "spherical"), P_PRODUCT_SUM, 33, (30.0, 30.0)),
+])
+def test_lu_variants(ctx, models, params, k, radii):
+    space, t, z, tsp, tt = synth(30000, 200, seed=33, extent=200.0)
+    g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32=False)
+    assert not ctx.kriging_solver_stats()["cholesky_enabled"]
+    o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32_storage=False)
+    compare(g, o, z, False)
+
+
 def test_k100_many_candidates(ctx):
     # > 512 candidates per target exercises the streaming select
     space, t, z, tsp, tt = synth(60000, 120, seed=7)

@@ -66,6 +66,15 @@ def synth_kriging(n_obs, n_targets, rank=0):
     return (x, y, t, z), (tx, ty, tt)
 
 
+def workload_name(workload):
+    """The same string in both arms (the driver matches them)."""
+    if workload == "c2":
+        return ("C2: synthetic 100k observations x 365 days, all-pairs space-time variogram, "
+                "30x30 lag bins, smax=30 tmax=30")
+    return ("C3: synthetic 1M observations, all-pairs variogram, 30x30 lag bins, tile pairs "
+            "sharded over ranks + NCCL all-reduce of the histograms")
+
+
 def measured_hbm_gbs():
     """HBM copy bandwidth from MEASURED_PEAKS.json (driver-written), else the profiling guide's
     fallback for B200."""
@@ -291,10 +300,7 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "strong" if workload == "c3" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": ("C2: synthetic 100k observations x 365 days, all-pairs space-time variogram, "
-                         "30x30 lag bins, smax=30 tmax=30" if workload == "c2" else
-                         "C3: synthetic 1M observations, all-pairs variogram, 30x30 lag bins, tile pairs "
-                         "sharded over ranks + NCCL all-reduce of the histograms"),
+            "workload": workload_name(workload),
             "n_obs": n, "pairs": pairs, "binned_pairs": binned_total,
             "l2": "256 MB device write between steps (outside the per-step CUDA-event pairs); "
                   "inputs (32 B/obs) are L2-resident by design",
@@ -474,8 +480,7 @@ def run_reference(args):
         "ms_per_step": pairs / rate * 1e3, "higher_is_better": True,
         "scaling": "strong" if workload == "c3" else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C2: synthetic 100k observations, 30x30 bins" if workload == "c2" else
-                               "C3: synthetic 1M observations, 30x30 bins",
+        "config": {"workload": workload_name(workload),
                    "n_obs": n, "pairs": pairs,
                    "note": "ms_per_step is the full workload extrapolated from the measured per-pair "
                            "rate (rate is N-independent); each timed step is a bounded sample"},

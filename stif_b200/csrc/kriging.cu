@@ -1279,14 +1279,25 @@ static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax
     const bool use_s = km.st_model != STIF_ST_METRIC;
     const bool use_t = use_s;
     const bool use_m = km.st_model == STIF_ST_METRIC || km.st_model == STIF_ST_SUM_METRIC;
+    // A sum of marginals is a valid variogram iff every partial sill c0 is >= 0, every range is
+    // positive and the TOTAL nugget is >= 0: the marginal nuggets only enter through their sum
+    // (unconstrained Nelder-Mead fits often return large nuggets of opposite sign).
     auto ok = [](double r, double c0, double b) {
-        return r > 0.0 && isfinite(r) && c0 >= 0.0 && isfinite(c0) && b >= 0.0 && isfinite(b);
+        return r > 0.0 && isfinite(r) && c0 >= 0.0 && isfinite(c0) && isfinite(b);
     };
     bool valid = (km.st_model == STIF_ST_SUM || km.st_model == STIF_ST_METRIC ||
                   km.st_model == STIF_ST_SUM_METRIC);
-    if (use_s) valid = valid && ok(M.rs, M.c0s, M.bs);
-    if (use_t) valid = valid && ok(M.rt, M.c0t, M.bt);
-    if (use_m) valid = valid && ok(M.rm, M.c0m, M.bm) && M.ani2 >= 0.0 && isfinite(M.ani2);
+    bool plain = true;      // no marginal nugget is negative: nothing cancels in the sill
+    if (use_s) { valid = valid && ok(M.rs, M.c0s, M.bs); plain = plain && M.bs >= 0.0; }
+    if (use_t) { valid = valid && ok(M.rt, M.c0t, M.bt); plain = plain && M.bt >= 0.0; }
+    if (use_m) {
+        valid = valid && ok(M.rm, M.c0m, M.bm) && M.ani2 >= 0.0 && isfinite(M.ani2);
+        plain = plain && M.bm >= 0.0;
+    }
+    {
+        const double nug_total = (use_s ? M.bs : 0.0) + (use_t ? M.bt : 0.0) + (use_m ? M.bm : 0.0);
+        valid = valid && nug_total >= 0.0;
+    }
     if (!valid && !(flags & STIF_KRIG_TRY_CHOL)) return -1;
     const double ss = M.bs + M.c0s, stt = M.bt + M.c0t, sm = M.bm + M.c0m;   // marginal sills
     double sill, nug;
@@ -1301,8 +1312,10 @@ static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax
     X.csill = sill;
     X.cdiag = sill - nug;
     X.tol = 1e-10 * X.cdiag;
-    const bool sph = valid && (!use_s || M.ks == STIF_M_SPHERICAL) && (!use_t || M.kt == STIF_M_SPHERICAL) &&
-                     (!use_m || M.km == STIF_M_SPHERICAL);
+    // polynomial fast path: all-spherical and no cancelling nuggets (with cancellation the
+    // verbatim formula reproduces the reference's rounding, the regrouped one would not)
+    const bool sph = valid && plain && (!use_s || M.ks == STIF_M_SPHERICAL) &&
+                     (!use_t || M.kt == STIF_M_SPHERICAL) && (!use_m || M.km == STIF_M_SPHERICAL);
     if (!sph) return CHOL_GENERIC;
     X.is = M.is; X.it = M.it; X.im = M.im;
     X.ncs = -M.c0s; X.nct = -M.c0t; X.ncm = -M.c0m;

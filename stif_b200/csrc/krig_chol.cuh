@@ -38,6 +38,7 @@ struct CholParams {
     //   C = cb + h (as - bs h^2) + t (at - bt t^2) + d (am - bm d^2),  a = -c0 1.5 / r,  b = -c0 0.5 / r^3
     double pas, pbs, pat, pbt, pam, pbm;
     int clamp;               // 1: a neighbour pair can lie beyond a marginal's range
+    int mode;                // assembly: 0 polynomial, 1 regrouped + clamps (or generic), 2 reference expression + fast sqrt
     const unsigned *pairtab; // pair e = a(a-1)/2 + b (b < a)  ->  a | b << 8 | chol_off(a, b) << 16
     unsigned *fail_list;     // targets (chunk-local ids) that need the pivoted LU
     unsigned *fail_count;
@@ -161,18 +162,27 @@ struct CholLane {
 // Four pairs per lane and iteration (independent dependency chains); (a, b) and the tile offset
 // come from a precomputed table (coalesced, prefetched one iteration ahead) instead of a
 // divergent decode loop.
-template <int VAR, bool CLAMP>
+template <int VAR, int MODE>
 __device__ __forceinline__ double chol_cov(const Model &M, const CholParams &X, double2 pa, double ta,
                                            double2 pb, double tb)
 {
     const double dx = pa.x - pb.x, dy = pa.y - pb.y;
-    const double d2 = __fma_rn(dy, dy, dx * dx);
     const double lt = fabs(ta - tb);
-    if (VAR != CHOL_GENERIC && !CLAMP) return cov_entry_poly<VAR>(X, d2, lt);
-    return cov_entry<VAR, CLAMP>(M, X, d2, lt);
+    if (VAR != CHOL_GENERIC && MODE == 2) {
+        // the reference's expression marginal by marginal (b + c0 (...), summed in its order):
+        // with large cancelling nuggets every rounding of the reference is reproduced; only the
+        // square roots are the fast ones (<= 1 ulp, far below the ulp of the nuggets)
+        const double h = sqrt_cubic_lu((dx * dx + dy * dy) + 1e-290);
+        constexpr int ST = VAR == CHOL_SUM_SPH ? STIF_ST_SUM
+                         : VAR == CHOL_METRIC_SPH ? STIF_ST_METRIC : STIF_ST_SUM_METRIC;
+        return X.csill - gamma_tpl<ST, STIF_M_SPHERICAL, STIF_M_SPHERICAL, STIF_M_SPHERICAL, true>(M, h, lt);
+    }
+    const double d2 = __fma_rn(dy, dy, dx * dx);
+    if (VAR != CHOL_GENERIC && MODE == 0) return cov_entry_poly<VAR>(X, d2, lt);
+    return cov_entry<VAR, true>(M, X, d2, lt);
 }
 
-template <int VAR, bool CLAMP>
+template <int VAR, int MODE>
 __device__ __forceinline__ void chol_assemble(double *T, const double2 *pxy, const double *pt, int m,
                                               const Model &M, const CholParams &X, int lane)
 {
@@ -200,7 +210,7 @@ __device__ __forceinline__ void chol_assemble(double *T, const double2 *pxy, con
         }
         double c[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) c[u] = chol_cov<VAR, CLAMP>(M, X, pa[u], ta[u], pb[u], tb[u]);
+        for (int u = 0; u < U; ++u) c[u] = chol_cov<VAR, MODE>(M, X, pa[u], ta[u], pb[u], tb[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (e + 32 * u < npairs) T[w[u] >> 16] = c[u];
@@ -418,7 +428,7 @@ __device__ __forceinline__ void chol_backsub_row(const double *T, double *sol, d
     if (L.lane < 8 && 8 * J + L.lane < m) sol[8 * J + L.lane] = wkeep;
 }
 
-template <int VAR, int ZR, bool CLAMP>
+template <int VAR, int ZR, int MODE>
 __global__ void __maxnreg__(ZR == 2 ? 152 : 240) solve_chol_kernel(SolveParams P, CholParams X)
 {
     extern __shared__ __align__(16) double smem_d[];
@@ -523,7 +533,7 @@ __global__ void __maxnreg__(ZR == 2 ? 152 : 240) solve_chol_kernel(SolveParams P
         }
         const int nrow = m + 2, nt = (nrow + 7) >> 3;
         __syncwarp();
-        if (m > 1) chol_assemble<VAR, CLAMP>(T, pxy, pt, m, P.M, X, lane);
+        if (m > 1) chol_assemble<VAR, MODE>(T, pxy, pt, m, P.M, X, lane);
         __syncwarp();
         fetch_ids();
         // ---- left-looking tiled Cholesky ----

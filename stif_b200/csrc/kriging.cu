@@ -79,9 +79,22 @@ __device__ __forceinline__ double marginal(int kind, double h, double r, double 
     return b + c0 * (1.0 - exp(-((h * h) * inv)));
 }
 
+// sqrt for the assembly fast paths: MUFU.RSQ64H + one cubic correction (<= ~1 ulp), x > 0
+__device__ __forceinline__ double sqrt_cubic_lu(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = __fma_rn(-t, y, 1.0);
+    const double p = __fma_rn(0.375, e, 0.5);
+    return __fma_rn(t * e, p, t);
+}
+
 // ST / KS / KT / KM < 0: read the id from the model at run time; >= 0: compile-time constant
-// (same arithmetic, the warp-uniform branches disappear).
-template <int ST, int KS, int KT, int KM>
+// (same arithmetic, the warp-uniform branches disappear).  FSQ: the metric distance uses the
+// fast square root (<= 1 ulp) instead of the IEEE one -- for the kriging MATRIX only, never
+// for the gamma-vector that decides the neighbour set.
+template <int ST, int KS, int KT, int KM, bool FSQ = false>
 __device__ __forceinline__ double gamma_tpl(const Model &M, double h, double t)
 {
     const int st = ST < 0 ? M.st : ST;
@@ -97,11 +110,13 @@ __device__ __forceinline__ double gamma_tpl(const Model &M, double h, double t)
         return M.k * p + p;
     }
     case STIF_ST_METRIC: {  // :184-186
-        const double d = sqrt(h * h + (M.ani2 * t) * t);
+        const double d2m = h * h + (M.ani2 * t) * t;
+        const double d = FSQ ? sqrt_cubic_lu(d2m + 1e-290) : sqrt(d2m);
         return marginal(km, d, M.rm, M.c0m, M.bm, M.im);
     }
     default: {  // sum_metric :213-218
-        const double d = sqrt(h * h + (M.ani2 * t) * t);
+        const double d2m = h * h + (M.ani2 * t) * t;
+        const double d = FSQ ? sqrt_cubic_lu(d2m + 1e-290) : sqrt(d2m);
         return (marginal(ks, h, M.rs, M.c0s, M.bs, M.is) +
                 marginal(kt, t, M.rt, M.c0t, M.bt, M.it)) +
                marginal(km, d, M.rm, M.c0m, M.bm, M.im);
@@ -739,16 +754,7 @@ struct SolveParams {
 
 enum { LU_GENERIC = 0, LU_PRODUCT_SPH = 1, LU_PRODUCT_SUM_SPH = 2 };
 
-// sqrt for the assembly fast paths: MUFU.RSQ64H + one cubic correction (<= ~1 ulp), x > 0
-__device__ __forceinline__ double sqrt_cubic_lu(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = __fma_rn(-t, y, 1.0);
-    const double p = __fma_rn(0.375, e, 0.5);
-    return __fma_rn(t * e, p, t);
-}
+
 
 // numpy's pairwise sum of a row of length n <= 128 (numpy/_core/src/umath/loops_utils.h.src),
 // preceded by the reduction's initial 0: bit-compatible with np.sum(row) -- checked against
@@ -1314,9 +1320,12 @@ static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax
     X.tol = 1e-10 * X.cdiag;
     // polynomial fast path: all-spherical and no cancelling nuggets (with cancellation the
     // verbatim formula reproduces the reference's rounding, the regrouped one would not)
-    const bool sph = valid && plain && (!use_s || M.ks == STIF_M_SPHERICAL) &&
+    const bool sph = valid && (!use_s || M.ks == STIF_M_SPHERICAL) &&
                      (!use_t || M.kt == STIF_M_SPHERICAL) && (!use_m || M.km == STIF_M_SPHERICAL);
-    if (!sph) return CHOL_GENERIC;
+    if (!sph) {
+        X.mode = 1;
+        return CHOL_GENERIC;
+    }
     X.is = M.is; X.it = M.it; X.im = M.im;
     X.ncs = -M.c0s; X.nct = -M.c0t; X.ncm = -M.c0m;
     X.ani2 = M.ani2;
@@ -1330,6 +1339,9 @@ static int chol_plan(const KrigModel &km, const Model &M, int flags, double smax
         if (use_t) noclamp = noclamp && tmax * (1.0 + 1e-9) <= M.rt;
         if (use_m) noclamp = noclamp && dmax * (1.0 + 1e-9) <= M.rm;
         X.clamp = noclamp ? 0 : 1;     // NaN / inf radii compare false -> clamp
+        // 0: polynomial, every pair inside every range; 1: regrouped with range clamps;
+        // 2: the reference's expression per marginal (cancelling nuggets) with the fast sqrt
+        X.mode = plain ? X.clamp : 2;
     }
     {
         auto pa = [](double c0, double inv_r) { return -c0 * 1.5 * inv_r; };
@@ -1675,9 +1687,9 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             CX.fail_list = fail_list;
             CX.fail_count = fail_count;
             QP.count = nullptr;
-#define STIF_CHOL(VAR_, ZR_, CL_)                                                                  \
+#define STIF_CHOL(VAR_, ZR_, MODE_)                                                                \
     do {                                                                                           \
-        auto kern = solve_chol_kernel<VAR_, ZR_, CL_>;                                                \
+        auto kern = solve_chol_kernel<VAR_, ZR_, MODE_>;                                           \
         STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        (int)chol_smem));                                           \
         int occ = 0;                                                                               \
@@ -1687,23 +1699,28 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         if (gsz > nc) gsz = nc;                                                                    \
         kern<<<(unsigned)gsz, 32, chol_smem, st>>>(QP, CX);                                        \
     } while (0)
+#define STIF_CHOL_M(VAR_, ZR_)                                                                     \
+    do {                                                                                           \
+        if (CX.mode == 0) STIF_CHOL(VAR_, ZR_, 0);                                                 \
+        else if (CX.mode == 1) STIF_CHOL(VAR_, ZR_, 1);                                            \
+        else STIF_CHOL(VAR_, ZR_, 2);                                                              \
+    } while (0)
 #define STIF_CHOL_Z(VAR_)                                                                          \
     do {                                                                                           \
-        if (k <= 64) {                                                                             \
-            if (CX.clamp) STIF_CHOL(VAR_, 2, true);                                                \
-            else STIF_CHOL(VAR_, 2, false);                                                        \
-        } else {                                                                                   \
-            if (CX.clamp) STIF_CHOL(VAR_, 4, true);                                                \
-            else STIF_CHOL(VAR_, 4, false);                                                        \
-        }                                                                                          \
+        if (k <= 64) STIF_CHOL_M(VAR_, 2);                                                         \
+        else STIF_CHOL_M(VAR_, 4);                                                                 \
     } while (0)
             switch (chol_var) {
             case CHOL_SUM_SPH: STIF_CHOL_Z(CHOL_SUM_SPH); break;
             case CHOL_METRIC_SPH: STIF_CHOL_Z(CHOL_METRIC_SPH); break;
             case CHOL_SUM_METRIC_SPH: STIF_CHOL_Z(CHOL_SUM_METRIC_SPH); break;
-            default: CX.clamp = 1; STIF_CHOL_Z(CHOL_GENERIC); break;
+            default:
+                if (k <= 64) STIF_CHOL(CHOL_GENERIC, 2, 1);
+                else STIF_CHOL(CHOL_GENERIC, 4, 1);
+                break;
             }
 #undef STIF_CHOL_Z
+#undef STIF_CHOL_M
 #undef STIF_CHOL
             STIF_CUDA(cudaGetLastError());
             QP.order = fail_list;

@@ -132,6 +132,11 @@ def test_cholesky_hands_indefinite_systems_to_lu(ctx):
     (SUM_METRIC, [40, 20, 50, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0], 70, (40.0, 40.0)),
     (("sum", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, 0.15, 0.10], 90, (40.0, 40.0)),
     (("sum_metric", "gaussian", "gaussian", "spherical"), P_SUM_METRIC, 80, (40.0, 40.0)),
+    # marginal nuggets that cancel (what unconstrained Nelder-Mead fits return): a valid model
+    (SUM_METRIC, [400, 60, 500, 0.4, 0.2, 0.3, -1000.0, -500.0, 1500.09, 5.0], 50, (30.0, 30.0)),
+    (("sum", "spherical", "spherical", "spherical"), [300, 60, 0.8, 0.7, -70.0, 70.25], 70, (40.0, 40.0)),
+    (("sum_metric", "spherical", "gaussian", "spherical"), [400, 60, 500, 0.4, 0.2, 0.3, -10.0, -5.0, 15.09, 5.0], 30,
+     (30.0, 30.0)),
 ])
 def test_cholesky_variants(ctx, models, params, k, radii):
     space, t, z, tsp, tt = synth(30000, 200, seed=31, extent=200.0)

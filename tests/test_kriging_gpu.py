@@ -313,3 +313,15 @@ def test_saturated_model_ties_broken_by_index(ctx):
     assert o["tie"].mean() > 0.5
     # oracle applies the same (gamma, index) rule: the sets must agree even on tied rows
     assert np.array_equal(g["idx"], o["idx"])
+
+
+@pytest.mark.parametrize("models,params,k", [(SUM_METRIC, P_SUM_METRIC, 50), (PRODUCT_SUM, P_PRODUCT_SUM, 50),
+                                             (PRODUCT_SUM, P_PRODUCT_SUM, 100)])
+def test_bitwise_reproducible(ctx, models, params, k):
+    """Every output of the kriging path is a deterministic function of the inputs (no atomics on
+    the data path; the fall-back list order does not matter): two calls agree bit for bit."""
+    space, t, z, tsp, tt = synth(40000, 3000, seed=41)
+    a = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=False)
+    b = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=False)
+    for key in ("mean", "std", "w", "gamma", "idx", "n_used"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key

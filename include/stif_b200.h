@@ -147,6 +147,19 @@ int stif_kriging_set_model(stif_ctx *ctx, int st_model, int space_model, int tim
 int stif_variogram_model_eval(stif_ctx *ctx, const double *h, const double *t, int64_t n,
                               double *gamma_out);
 
+/* Objective of the variogram-model fit (stif/variogram_models.py:221-308: prediction_grid +
+ * weighted_mean_square_error, called by scipy's Nelder-Mead from Predictor.fit_variogram_model,
+ * stif/predictor.py:738-753).  The optimiser stays on the host; only the objective moves.
+ * stif_fit_set_grid uploads the lag-bin centres, the empirical variogram (NaN allowed) and the
+ * weights (host pointers, row-major [n_space][n_time]) once per fit; stif_fit_wmse evaluates
+ *   sum(w * (empirical - gamma(h, t; params))^2) / sum(w)
+ * for one parameter vector (model ids as in stif_kriging_set_model) and returns it in *out
+ * (one small kernel + an 8-byte read-back; NaN propagates like np.average). */
+int stif_fit_set_grid(stif_ctx *ctx, const double *bins_space, int n_space, const double *bins_time,
+                      int n_time, const double *empirical, const double *weights);
+int stif_fit_wmse(stif_ctx *ctx, int st_model, int space_model, int time_model, int metric_model,
+                  const double *params, int nparams, double *out);
+
 /* flags for stif_kriging_predict_* */
 #define STIF_KRIG_F32_STORAGE 1 /* round weights and gamma-vector to float32 before the
                                    mean/std reductions and reproduce numpy's pairwise

@@ -60,6 +60,9 @@ SIGNATURES = {
     "stif_kriging_set_model": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, _vp, ctypes.c_int]),
     "stif_variogram_model_eval": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
+    "stif_fit_set_grid": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
+    "stif_fit_wmse": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                     ctypes.c_int, _c_double_p]),
     "stif_kriging_predict_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int,
                                                  ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                                  ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -240,6 +243,24 @@ class Context:
         _check(self._lib.stif_variogram_model_eval(self._h, _ptr(h_c), _ptr(t_c), h_c.size, _ptr(out)),
                "stif_variogram_model_eval")
         return out.reshape(shape)
+
+    # ---- variogram-model fit objective ---------------------------------------------
+    def fit_set_grid(self, bins_space, bins_time, empirical, weights):
+        bs, bt = _f64(bins_space).ravel(), _f64(bins_time).ravel()
+        emp, w = _f64(empirical), _f64(weights)
+        if emp.shape != (len(bs), len(bt)) or w.shape != emp.shape:
+            raise ValueError("empirical / weights must have shape (len(bins_space), len(bins_time))")
+        self._fit_keep = (bs, bt, emp, w)
+        _check(self._lib.stif_fit_set_grid(self._h, _ptr(bs), len(bs), _ptr(bt), len(bt), _ptr(emp), _ptr(w)),
+               "stif_fit_set_grid")
+
+    def fit_wmse(self, st_model, space_model, time_model, metric_model, params):
+        p = _f64(params).ravel()
+        out = ctypes.c_double()
+        _check(self._lib.stif_fit_wmse(self._h, ST_MODELS[st_model], MARGINAL_MODELS[space_model],
+                                       MARGINAL_MODELS[time_model], MARGINAL_MODELS[metric_model],
+                                       _ptr(p), len(p), ctypes.byref(out)), "stif_fit_wmse")
+        return out.value
 
     def kriging_predict_host(self, tx, ty, tt, min_pts, max_pts, space_dist_max, time_dist_max,
                              leave_out=None, flags=KRIG_F32_STORAGE, want_weights=False,

@@ -99,6 +99,8 @@ int stif_ctx_destroy(stif_ctx *c)
     c->k_obs.release();
     c->k_obs4.release();
     c->k_pairtab.release();
+    c->k_fit.release();
+    if (c->fit_out_host) cudaFreeHost(c->fit_out_host);
     c->k_stats.release();
     for (auto &b : c->k_scratch) b.release();
     for (int i = 0; i < 6; ++i)

@@ -1253,6 +1253,33 @@ static int build_model(const KrigModel &km, Model &M)
     return STIF_OK;
 }
 
+// Weighted mean square error of the model on the lag grid (variogram_models.py:264-308).
+// One block; per-thread partial sums in row-major order, fixed shared-memory tree.
+__global__ void __launch_bounds__(256) wmse_kernel(Model M, const double *bins_space, int ns,
+                                                   const double *bins_time, int nt, const double *emp,
+                                                   const double *w, double *out)
+{
+    __shared__ double s_num[256], s_den[256];
+    double num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < ns * nt; i += 256) {
+        const double g = gamma_st(M, bins_space[i / nt], bins_time[i % nt]);
+        const double e = emp[i] - g;
+        num += w[i] * (e * e);
+        den += w[i];
+    }
+    s_num[threadIdx.x] = num;
+    s_den[threadIdx.x] = den;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            s_num[threadIdx.x] += s_num[threadIdx.x + off];
+            s_den[threadIdx.x] += s_den[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s_num[0] / s_den[0];
+}
+
 __global__ void obs_interleave_kernel(const double *x, const double *y, const double *t,
                                       const double *r, int64_t n, double4 *out)
 {
@@ -1847,5 +1874,62 @@ extern "C" int stif_kriging_solver_stats(stif_ctx *c, uint64_t out[2])
     unsigned long long h = 0;
     STIF_CUDA(cudaMemcpy(&h, c->k_stats.as<unsigned long long>() + 4, sizeof(h), cudaMemcpyDeviceToHost));
     out[0] = h;
+    return STIF_OK;
+}
+
+extern "C" int stif_fit_set_grid(stif_ctx *c, const double *bins_space, int ns, const double *bins_time,
+                                 int nt, const double *empirical, const double *weights)
+{
+    STIF_TRY(check_ctx(c, "stif_fit_set_grid"));
+    if (ns < 1 || nt < 1 || (int64_t)ns * nt > (1 << 24) || !bins_space || !bins_time || !empirical || !weights) {
+        set_error("stif_fit_set_grid: bad arguments (n_space=%d n_time=%d)", ns, nt);
+        return STIF_EINVAL;
+    }
+    const size_t g = (size_t)ns * nt;
+    STIF_TRY(c->k_fit.reserve(sizeof(double) * (ns + nt + 2 * g + 1)));
+    double *d = c->k_fit.as<double>();
+    STIF_CUDA(cudaMemcpyAsync(d, bins_space, 8 * (size_t)ns, cudaMemcpyHostToDevice, c->stream));
+    STIF_CUDA(cudaMemcpyAsync(d + ns, bins_time, 8 * (size_t)nt, cudaMemcpyHostToDevice, c->stream));
+    STIF_CUDA(cudaMemcpyAsync(d + ns + nt, empirical, 8 * g, cudaMemcpyHostToDevice, c->stream));
+    STIF_CUDA(cudaMemcpyAsync(d + ns + nt + g, weights, 8 * g, cudaMemcpyHostToDevice, c->stream));
+    STIF_CUDA(cudaStreamSynchronize(c->stream));
+    // mapped pinned landing buffer: the kernel writes the result straight into host memory
+    if (!c->fit_out_host) STIF_CUDA(cudaHostAlloc(&c->fit_out_host, sizeof(double), cudaHostAllocMapped));
+    c->fit_ns = ns;
+    c->fit_nt = nt;
+    return STIF_OK;
+}
+
+extern "C" int stif_fit_wmse(stif_ctx *c, int st_model, int space_model, int time_model, int metric_model,
+                             const double *params, int nparams, double *out)
+{
+    STIF_TRY(check_ctx(c, "stif_fit_wmse"));
+    static const int need[5] = {6, 6, 7, 4, 10};
+    if (c->fit_ns < 1) {
+        set_error("stif_fit_wmse: no grid set (stif_fit_set_grid)");
+        return STIF_ESTATE;
+    }
+    if (st_model < 0 || st_model > 4 || !params || !out || nparams != need[st_model]) {
+        set_error("stif_fit_wmse: bad model id / parameter count");
+        return STIF_EINVAL;
+    }
+    KrigModel km;
+    km.st_model = st_model;
+    km.space_model = space_model;
+    km.time_model = time_model;
+    km.metric_model = metric_model;
+    km.nparams = nparams;
+    for (int i = 0; i < nparams; ++i) km.x[i] = params[i];
+    Model M;
+    STIF_TRY(build_model(km, M));
+    const int ns = c->fit_ns, nt = c->fit_nt;
+    const size_t g = (size_t)ns * nt;
+    double *d = c->k_fit.as<double>();
+    double *out_dev = nullptr;
+    STIF_CUDA(cudaHostGetDevicePointer(&out_dev, c->fit_out_host, 0));
+    wmse_kernel<<<1, 256, 0, c->stream>>>(M, d, ns, d + ns, nt, d + ns + nt, d + ns + nt + g, out_dev);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaStreamSynchronize(c->stream));
+    *out = *c->fit_out_host;
     return STIF_OK;
 }

@@ -41,7 +41,7 @@ class Predictor:
     """Predictor(data, covariate_model=None, cv_splits=5, resampling=None)."""
 
     def __init__(self, data: Data, covariate_model=None, cv_splits: int = 5, resampling=None,
-                 emulate_f32_storage: bool = True, context=None):
+                 emulate_f32_storage: bool = True, context=None, device_fit_objective: bool = True):
         self._data = data
         self._cv_splits = cv_splits
         self._resampling = resampling
@@ -69,6 +69,9 @@ class Predictor:
         # stock reference rounds weights / gamma-vector to float32 before the final sums
         # (stif/predictor.py:610-618); False keeps everything float64
         self._emulate_f32_storage = emulate_f32_storage
+        # objective of the Nelder-Mead fit (prediction grid + weighted MSE) on the device
+        # (stif/variogram_models.py:221-308); the optimiser itself stays scipy on the host
+        self._device_fit_objective = device_fit_objective
         self._ctx = context
         self._obs_token = None
 
@@ -279,12 +282,18 @@ class Predictor:
                                self._variogram_samples_per_bin)
         x0 = get_initial_parameters(st_model, self._variogram, self._variogram_bins_space[-1],
                                     self._variogram_bins_time[-1], ani)
-        fit = minimize(
-            weighted_mean_square_error, x0,
-            args=(variogram_model_dict[st_model], variogram_model_dict[space_model],
-                  variogram_model_dict[time_model], variogram_model_dict[metric_model],
-                  self._variogram_bins_space, self._variogram_bins_time, self._variogram, weights),
-            method="Nelder-Mead", options={"maxiter": 10000})
+        if self._device_fit_objective:
+            ctx = self.context
+            ctx.fit_set_grid(self._variogram_bins_space, self._variogram_bins_time, self._variogram, weights)
+            fit = minimize(lambda x: ctx.fit_wmse(st_model, space_model, time_model, metric_model, x), x0,
+                           method="Nelder-Mead", options={"maxiter": 10000})
+        else:
+            fit = minimize(
+                weighted_mean_square_error, x0,
+                args=(variogram_model_dict[st_model], variogram_model_dict[space_model],
+                      variogram_model_dict[time_model], variogram_model_dict[metric_model],
+                      self._variogram_bins_space, self._variogram_bins_time, self._variogram, weights),
+                method="Nelder-Mead", options={"maxiter": 10000})
         self._variogram_fit = fit
         self._variogram_models = [st_model, space_model, time_model, metric_model]
         self._variogram_model_function = self._create_variogram_model_function()

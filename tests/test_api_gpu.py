@@ -153,3 +153,49 @@ def test_cross_validation_with_leave_out(pm10, ctx):
     scores = p.get_cross_val_metric(explained_variance_score)
     assert len(scores) == 3 and all(np.isfinite(s) for s in scores)
     assert max(scores) > 0.2
+
+
+def test_fit_objective_on_device_matches_host(golden_dir, pm10, ctx):
+    """stif_fit_wmse (prediction grid + weighted MSE of stif/variogram_models.py:221-308 on the
+    device) against the host numpy objective, on the PM10 empirical variogram; then the two
+    Nelder-Mead fits end at the same objective value."""
+    import time
+    from stif_b200 import variogram_models as vm
+    g = np.load(os.path.join(golden_dir, "variogram_pm10.npz"))
+    variogram, counts = g["variogram"], g["norm"]
+    bins_space = (np.arange(10) + 0.5) * (6e5 / 10)
+    bins_time = (np.arange(7) + 0.5) * (7 / 7)
+    weights = vm.calc_weights(bins_space, bins_time, 1e5, counts)
+    ctx.fit_set_grid(bins_space, bins_time, variogram, weights)
+    rng = np.random.default_rng(0)
+    for st, n in [("sum", 6), ("product", 6), ("product_sum", 7), ("metric", 4), ("sum_metric", 10)]:
+        for marg in ("spherical", "gaussian"):
+            x0 = vm.get_initial_parameters(st, variogram, bins_space[-1], bins_time[-1], 1e5)
+            for rep in range(4):
+                x = x0 * rng.uniform(0.5, 1.5, len(x0))
+                host = vm.weighted_mean_square_error(x, vm.variogram_model_dict[st], vm.variogram_model_dict[marg],
+                                                     vm.variogram_model_dict[marg], vm.variogram_model_dict[marg],
+                                                     bins_space, bins_time, variogram, weights)
+                dev = ctx.fit_wmse(st, marg, marg, marg, x)
+                assert np.isclose(dev, host, rtol=1e-12, atol=0), (st, marg, dev, host)
+    # timing of one evaluation (reported, not asserted) and end-to-end fits
+    x = vm.get_initial_parameters("sum_metric", variogram, bins_space[-1], bins_time[-1], 1e5)
+    t0 = time.perf_counter()
+    for _ in range(500):
+        ctx.fit_wmse("sum_metric", "spherical", "spherical", "spherical", x)
+    t_dev = (time.perf_counter() - t0) / 500
+    t0 = time.perf_counter()
+    for _ in range(500):
+        vm.weighted_mean_square_error(x, vm.sum_metric_model, vm.spherical, vm.spherical, vm.spherical, bins_space,
+                                      bins_time, variogram, weights)
+    t_host = (time.perf_counter() - t0) / 500
+    print(f"objective evaluation: device {t_dev * 1e6:.1f} us, host numpy {t_host * 1e6:.1f} us")
+    df = pm10
+    fits = []
+    for dev_obj in (True, False):
+        p = Predictor(Data(df, space_cols=["x", "y"], time_col="time", predictand_col="PM10"), context=ctx,
+                      device_fit_objective=dev_obj)
+        p.calc_empirical_variogram(space_dist_max=6e5, time_dist_max=7, n_space_bins=10, n_time_bins=7)
+        p.fit_variogram_model(st_model="product_sum")
+        fits.append(p._variogram_fit.fun)
+    assert np.isclose(fits[0], fits[1], rtol=1e-3)

@@ -136,6 +136,11 @@ int stif_variogram_stats(stif_ctx *ctx, uint64_t out[4]);
 int stif_kriging_set_obs(stif_ctx *ctx, const double *x, const double *y, const double *t,
                          const double *resid, int64_t n_obs, int on_device);
 
+/* Replace only the residuals of the bound observation set (same n_obs); coordinates and the
+ * cached space-time grid stay.  Cross-validation refits the covariate model per fold
+ * (stif/predictor.py:275, :211-229), which changes the residuals but not the coordinates. */
+int stif_kriging_set_residuals(stif_ctx *ctx, const double *resid, int64_t n_obs, int on_device);
+
 /* Fitted variogram model: ids + parameter vector x of Predictor._variogram_fit.x
  * (stif/predictor.py:755-758).  nparams: sum/product 6, product_sum 7, metric 4,
  * sum_metric 10. */

@@ -57,6 +57,7 @@ SIGNATURES = {
                                                    ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "stif_variogram_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "stif_kriging_set_obs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int]),
+    "stif_kriging_set_residuals": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int]),
     "stif_kriging_set_model": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, _vp, ctypes.c_int]),
     "stif_variogram_model_eval": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
@@ -219,6 +220,10 @@ class Context:
             raise ValueError("x, y, t, resid must have the same length")
         _check(self._lib.stif_kriging_set_obs(self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(resid), n, 0),
                "stif_kriging_set_obs")
+
+    def kriging_set_residuals(self, resid):
+        r = _f64(resid)
+        _check(self._lib.stif_kriging_set_residuals(self._h, _ptr(r), len(r), 0), "stif_kriging_set_residuals")
 
     def kriging_set_obs_dev(self, x_ptr, y_ptr, t_ptr, r_ptr, n):
         _check(self._lib.stif_kriging_set_obs(self._h, x_ptr, y_ptr, t_ptr, r_ptr, int(n), 1),

@@ -1280,6 +1280,12 @@ __global__ void __launch_bounds__(256) wmse_kernel(Model M, const double *bins_s
     if (threadIdx.x == 0) out[0] = s_num[0] / s_den[0];
 }
 
+__global__ void obs_resid_kernel(const double *r, int64_t n, double4 *obs4)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) obs4[i].w = r[i];
+}
+
 __global__ void obs_interleave_kernel(const double *x, const double *y, const double *t,
                                       const double *r, int64_t n, double4 *out)
 {
@@ -1490,6 +1496,23 @@ extern "C" int stif_kriging_set_obs(stif_ctx *c, const double *x, const double *
     STIF_CUDA(cudaStreamSynchronize(c->stream));
     c->n_obs = n;
     c->grid_nobs = -1;  // invalidate the grid
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_set_residuals(stif_ctx *c, const double *resid, int64_t n, int on_device)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_set_residuals"));
+    if (c->n_obs <= 0 || n != c->n_obs || !resid) {
+        set_error("stif_kriging_set_residuals: %lld residuals for %lld bound observations",
+                  (long long)n, (long long)c->n_obs);
+        return n != c->n_obs ? STIF_ESTATE : STIF_EINVAL;
+    }
+    double *d = c->k_obs.as<double>() + 3 * n;
+    STIF_CUDA(cudaMemcpyAsync(d, resid, sizeof(double) * (size_t)n,
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    obs_resid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d, n, c->k_obs4.as<double4>());
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaStreamSynchronize(c->stream));
     return STIF_OK;
 }
 

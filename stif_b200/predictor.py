@@ -87,10 +87,17 @@ class Predictor:
         space = self._data.space_coords
         time = self._data.time_coords
         token = (id(self._residuals), len(time))
-        if self._obs_token == token and getattr(self.context, "_obs_owner", None) is self:
+        mine = getattr(self.context, "_obs_owner", None) is self
+        if self._obs_token == token and mine:
             return
-        x, y = _native.split_space(space)
-        self.context.kriging_set_obs(x, y, time, np.asarray(self._residuals, dtype=np.float64))
+        resid = np.asarray(self._residuals, dtype=np.float64)
+        if mine and self._obs_token is not None and self._obs_token[1] == len(time):
+            # same observation set, new residuals (cross-validation refits the covariate model
+            # per fold): keep the coordinates and the space-time grid on the device
+            self.context.kriging_set_residuals(resid)
+        else:
+            x, y = _native.split_space(space)
+            self.context.kriging_set_obs(x, y, time, resid)
         self.context._obs_owner = self
         self._obs_token = token
 

@@ -199,3 +199,24 @@ def test_fit_objective_on_device_matches_host(golden_dir, pm10, ctx):
         p.fit_variogram_model(st_model="product_sum")
         fits.append(p._variogram_fit.fun)
     assert np.isclose(fits[0], fits[1], rtol=1e-3)
+
+
+def test_set_residuals_keeps_grid_and_matches_full_upload(ctx):
+    """stif_kriging_set_residuals (what the cross-validation folds use) == a fresh set_obs."""
+    from stif_b200 import _native
+    rng = np.random.default_rng(5)
+    n = 20000
+    x, y, t = rng.uniform(0, 200, n), rng.uniform(0, 200, n), rng.uniform(0, 365, n)
+    z1, z2 = rng.normal(size=n), rng.normal(size=n)
+    tx, ty, tt = rng.uniform(0, 200, 500), rng.uniform(0, 200, 500), rng.uniform(30, 365, 500)
+    ctx.kriging_set_model("sum_metric", "spherical", "spherical", "spherical",
+                          [400, 60, 500, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0])
+    ctx.kriging_set_obs(x, y, t, z1)
+    ctx.kriging_predict_host(tx, ty, tt, 1, 30, 30.0, 30.0)
+    ctx.kriging_set_residuals(z2)
+    m_a, s_a = ctx.kriging_predict_host(tx, ty, tt, 1, 30, 30.0, 30.0)
+    ctx.kriging_set_obs(x, y, t, z2)
+    m_b, s_b = ctx.kriging_predict_host(tx, ty, tt, 1, 30, 30.0, 30.0)
+    assert np.array_equal(m_a, m_b) and np.array_equal(s_a, s_b)
+    with pytest.raises(ValueError):
+        ctx.kriging_set_residuals(z2[:10])

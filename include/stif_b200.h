@@ -136,6 +136,17 @@ int stif_variogram_stats(stif_ctx *ctx, uint64_t out[4]);
 int stif_kriging_set_obs(stif_ctx *ctx, const double *x, const double *y, const double *t,
                          const double *resid, int64_t n_obs, int on_device);
 
+/* Data.get_kriging_idxs (stif/data.py:170-212) as a stand-alone call: every (observation,
+ * target) pair with  ||s_o - s_t||^2 < space_dist_max^2,  |t_o - t_t| < time_dist_max,
+ * t_o <= t_t  and  o != leave_out[target], found through the space-time grid (never the dense
+ * n_obs x n_targets matrices), sorted by observation index then target index like
+ * np.nonzero.  Targets are host pointers.  _count runs the search and returns the number of
+ * pairs; _fetch copies them out as int64 [n_pairs][2] = {obs_idx, target_idx}. */
+int stif_kriging_pairs_count(stif_ctx *ctx, const double *tx, const double *ty, const double *tt,
+                             const int64_t *leave_out, int64_t n_targets, double space_dist_max,
+                             double time_dist_max, int64_t *n_pairs);
+int stif_kriging_pairs_fetch(stif_ctx *ctx, int64_t *pairs_out);
+
 /* Replace only the residuals of the bound observation set (same n_obs); coordinates and the
  * cached space-time grid stay.  Cross-validation refits the covariate model per fold
  * (stif/predictor.py:275, :211-229), which changes the residuals but not the coordinates. */

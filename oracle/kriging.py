@@ -143,3 +143,19 @@ def weights(xs, ys, ts, gvec, models, params):
     if rc != 0:
         raise RuntimeError(f"dgelsd failed (info {rc})")
     return w, rank.value
+
+
+def kriging_idxs(obs_space, obs_time, space, time, space_dist_max, time_dist_max, leave_out_idxs=None):
+    """Restatement of Data.get_kriging_idxs (stif/data.py:170-212) -- TEST INFRASTRUCTURE: the
+    dense n_obs x n_targets filter with scipy's cdist, exactly as the reference writes it."""
+    import scipy.spatial.distance
+    obs_time = np.asarray(obs_time)
+    time = np.asarray(time)
+    space_dist_sq = scipy.spatial.distance.cdist(obs_space, space, metric="sqeuclidean")
+    time_dist = scipy.spatial.distance.cdist(obs_time.reshape(-1, 1), time.reshape(-1, 1))
+    index_mask = np.ones([len(obs_time), len(time)], dtype=bool)
+    if leave_out_idxs is not None:
+        index_mask[leave_out_idxs, np.arange(len(time))] = False
+    is_close_enough = ((space_dist_sq < space_dist_max ** 2) & (time_dist < time_dist_max) &
+                       (obs_time.reshape(-1, 1) <= time.reshape(1, -1)) & index_mask)
+    return np.column_stack(np.nonzero(is_close_enough))

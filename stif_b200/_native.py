@@ -57,6 +57,9 @@ SIGNATURES = {
                                                    ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "stif_variogram_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "stif_kriging_set_obs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int]),
+    "stif_kriging_pairs_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_double,
+                                                ctypes.c_double, ctypes.POINTER(ctypes.c_int64)]),
+    "stif_kriging_pairs_fetch": (ctypes.c_int, [_vp, _vp]),
     "stif_kriging_set_residuals": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int]),
     "stif_kriging_set_model": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, _vp, ctypes.c_int]),
@@ -220,6 +223,22 @@ class Context:
             raise ValueError("x, y, t, resid must have the same length")
         _check(self._lib.stif_kriging_set_obs(self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(resid), n, 0),
                "stif_kriging_set_obs")
+
+    def kriging_neighbour_pairs(self, tx, ty, tt, space_dist_max, time_dist_max, leave_out=None):
+        """(P, 2) int64 [obs_idx, target_idx] of Data.get_kriging_idxs (stif/data.py:170-212)."""
+        tx, ty, tt = _f64(tx), _f64(ty), _f64(tt)
+        n = len(tx)
+        lo = None if leave_out is None else np.ascontiguousarray(leave_out, dtype=np.int64)
+        if lo is not None and len(lo) != n:
+            raise ValueError("leave_out_idxs must have one entry per target")
+        total = ctypes.c_int64()
+        _check(self._lib.stif_kriging_pairs_count(self._h, _ptr(tx), _ptr(ty), _ptr(tt), _ptr(lo), n,
+                                                  float(space_dist_max), float(time_dist_max),
+                                                  ctypes.byref(total)), "stif_kriging_pairs_count")
+        out = np.empty((total.value, 2), dtype=np.int64)
+        if total.value:
+            _check(self._lib.stif_kriging_pairs_fetch(self._h, _ptr(out)), "stif_kriging_pairs_fetch")
+        return out
 
     def kriging_set_residuals(self, resid):
         r = _f64(resid)

@@ -94,6 +94,8 @@ struct stif_ctx {
     stif::DevBuf k_fit;        // fit objective: bins_space | bins_time | empirical | weights | out
     int fit_ns = 0, fit_nt = 0;
     double *fit_out_host = nullptr;   // pinned 8-byte landing buffer
+    stif::DevBuf k_pairs_a, k_pairs_b, k_pairs_cnt;   // stand-alone neighbour pair list
+    int64_t n_pairs = -1;
     stif::DevBuf k_pairtab;    // assembly pair table of the Cholesky kernel
     stif::DevBuf k_obs4;       // obs AoS {x, y, t, resid}, original order (neighbour gathers)
     stif::KrigModel model;

@@ -99,6 +99,9 @@ int stif_ctx_destroy(stif_ctx *c)
     c->k_obs.release();
     c->k_obs4.release();
     c->k_pairtab.release();
+    c->k_pairs_a.release();
+    c->k_pairs_b.release();
+    c->k_pairs_cnt.release();
     c->k_fit.release();
     if (c->fit_out_host) cudaFreeHost(c->fit_out_host);
     c->k_stats.release();

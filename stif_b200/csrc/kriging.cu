@@ -26,6 +26,7 @@
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <math.h>
 
 namespace stif {
@@ -1253,6 +1254,75 @@ static int build_model(const KrigModel &km, Model &M)
     return STIF_OK;
 }
 
+// ---- stand-alone neighbour pair list (Data.get_kriging_idxs, stif/data.py:170-212) --------
+struct PairsParams {
+    const double4 *obs;
+    const unsigned *cell_start;
+    const GridDims *gd;
+    const double *tx, *ty, *tt;
+    const long long *leave_out;        // nullable
+    int n;
+    double smax2, tmax;
+    unsigned long long *counts;        // [n] pairs per target (count pass)
+    const unsigned long long *offsets; // [n] exclusive prefix (fill pass)
+    unsigned long long *keys;          // (obs_idx << 32) | target (fill pass)
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) pairs_kernel(PairsParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int tg = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tg >= P.n) return;
+    const double x = P.tx[tg], y = P.ty[tg], t = P.tt[tg];
+    const long long leave = P.leave_out ? P.leave_out[tg] : -1;
+    const GridDims g = *P.gd;
+    const int cxr = raw_cell(x, g.x0, g.inv_cx, g.nx, g.hx);
+    const int cyr = raw_cell(y, g.y0, g.inv_cy, g.ny, g.hy);
+    const int ctr = raw_cell(t, g.t0, g.inv_ct, g.nt, g.ht);
+    const int cx_lo = max(cxr - g.hx, 0), cx_hi = min(cxr + g.hx, g.nx - 1);
+    const int cy_lo = max(cyr - g.hy, 0), cy_hi = min(cyr + g.hy, g.ny - 1);
+    const int ct_lo = max(ctr - g.ht, 0), ct_hi = min(ctr, g.nt - 1);
+    unsigned long long cnt = 0;
+    const unsigned long long base = FILL ? P.offsets[tg] : 0ull;
+    if (cx_lo <= cx_hi) {
+        for (int ct = ct_lo; ct <= ct_hi; ++ct) {
+            for (int cy = cy_lo; cy <= cy_hi; ++cy) {
+                const int row = (ct * g.ny + cy) * g.nx;
+                const unsigned beg = P.cell_start[row + cx_lo], end = P.cell_start[row + cx_hi + 1];
+                for (unsigned p0 = beg; p0 < end; p0 += 32) {
+                    const unsigned p = p0 + lane;
+                    bool pass = false;
+                    unsigned oi = 0u;
+                    if (p < end) {
+                        const double4 o = P.obs[p];
+                        const double dx = o.x - x, dy = o.y - y;
+                        const double d2 = dx * dx + dy * dy;            // data.py:195-199
+                        oi = (unsigned)__double_as_longlong(o.w);
+                        pass = (d2 < P.smax2) && (fabs(o.z - t) < P.tmax) && (o.z <= t) &&   // data.py:206-211
+                               ((long long)oi != leave);
+                    }
+                    const unsigned bal = __ballot_sync(FULL, pass);
+                    if (FILL && pass)
+                        P.keys[base + cnt + __popc(bal & ((1u << lane) - 1u))] =
+                            ((unsigned long long)oi << 32) | (unsigned)tg;
+                    cnt += __popc(bal);
+                }
+            }
+        }
+    }
+    if (!FILL && lane == 0) P.counts[tg] = cnt;
+}
+
+__global__ void pairs_unpack_kernel(const unsigned long long *keys, int64_t n, long long *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[2 * i] = (long long)(keys[i] >> 32);
+        out[2 * i + 1] = (long long)(keys[i] & 0xffffffffull);
+    }
+}
+
 // Weighted mean square error of the model on the lag grid (variogram_models.py:264-308).
 // One block; per-thread partial sums in row-major order, fixed shared-memory tree.
 __global__ void __launch_bounds__(256) wmse_kernel(Model M, const double *bins_space, int ns,
@@ -1954,5 +2024,100 @@ extern "C" int stif_fit_wmse(stif_ctx *c, int st_model, int space_model, int tim
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaStreamSynchronize(c->stream));
     *out = *c->fit_out_host;
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_pairs_count(stif_ctx *c, const double *tx, const double *ty, const double *tt,
+                                        const int64_t *leave_out, int64_t n, double smax, double tmax,
+                                        int64_t *n_pairs)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_pairs_count"));
+    if (!n_pairs || n < 0 || n >= 0x7fffffff || (n > 0 && (!tx || !ty || !tt))) {
+        set_error("stif_kriging_pairs_count: bad arguments");
+        return STIF_EINVAL;
+    }
+    if (c->n_obs <= 0) {
+        set_error("stif_kriging_pairs_count: no observations set (stif_kriging_set_obs)");
+        return STIF_ESTATE;
+    }
+    *n_pairs = 0;
+    c->n_pairs = 0;
+    if (n == 0) return STIF_OK;
+    cudaStream_t st = c->stream;
+    const size_t N = (size_t)n;
+    STIF_TRY(c->k_scratch[S_STAGE].reserve(8 * N * 4 + 1024));
+    double *dtx = c->k_scratch[S_STAGE].as<double>(), *dty = dtx + N, *dtt = dty + N;
+    long long *dlo = reinterpret_cast<long long *>(dtt + N);
+    STIF_CUDA(cudaMemcpyAsync(dtx, tx, 8 * N, cudaMemcpyHostToDevice, st));
+    STIF_CUDA(cudaMemcpyAsync(dty, ty, 8 * N, cudaMemcpyHostToDevice, st));
+    STIF_CUDA(cudaMemcpyAsync(dtt, tt, 8 * N, cudaMemcpyHostToDevice, st));
+    if (leave_out) STIF_CUDA(cudaMemcpyAsync(dlo, leave_out, 8 * N, cudaMemcpyHostToDevice, st));
+    STIF_TRY(ensure_grid(c, smax, tmax, st));
+    STIF_TRY(c->k_pairs_cnt.reserve(16 * N + 16));
+    unsigned long long *counts = c->k_pairs_cnt.as<unsigned long long>(), *offsets = counts + N;
+    PairsParams P;
+    P.obs = c->k_scratch[S_OBS_SORTED].as<double4>();
+    P.cell_start = c->k_scratch[S_CELL_START].as<unsigned>();
+    P.gd = reinterpret_cast<GridDims *>(c->k_scratch[S_GRIDHDR].as<double>() + 6);
+    P.tx = dtx; P.ty = dty; P.tt = dtt;
+    P.leave_out = leave_out ? dlo : nullptr;
+    P.n = (int)n;
+    P.smax2 = smax * smax;
+    P.tmax = tmax;
+    P.counts = counts;
+    P.offsets = offsets;
+    P.keys = nullptr;
+    const unsigned grid = (unsigned)((n + 3) / 4);
+    pairs_kernel<false><<<grid, 128, 0, st>>>(P);
+    STIF_CUDA(cudaGetLastError());
+    size_t tmp = 0;
+    STIF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, counts, offsets, (int)n, st));
+    STIF_TRY(c->k_scratch[S_CUB].reserve(tmp));
+    STIF_CUDA(cub::DeviceScan::ExclusiveSum(c->k_scratch[S_CUB].p, tmp, counts, offsets, (int)n, st));
+    unsigned long long last[2];
+    STIF_CUDA(cudaMemcpyAsync(&last[0], counts + (N - 1), 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaMemcpyAsync(&last[1], offsets + (N - 1), 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long total = last[0] + last[1];
+    if (total > 0) {
+        STIF_TRY(c->k_pairs_a.reserve(8 * (size_t)total));
+        STIF_TRY(c->k_pairs_b.reserve(16 * (size_t)total));   // sorted keys, later the unpacked pairs
+        P.keys = c->k_pairs_a.as<unsigned long long>();
+        pairs_kernel<true><<<grid, 128, 0, st>>>(P);
+        STIF_CUDA(cudaGetLastError());
+        unsigned long long *sorted = c->k_pairs_b.as<unsigned long long>();
+        STIF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, P.keys, sorted, (int64_t)total, 0, 64, st));
+        STIF_TRY(c->k_scratch[S_CUB].reserve(tmp));
+        STIF_CUDA(cub::DeviceRadixSort::SortKeys(c->k_scratch[S_CUB].p, tmp, P.keys, sorted, (int64_t)total, 0, 64, st));
+        // unpack into k_pairs_a (reused: 8 B per key -> 16 B per pair needs its own space)
+        STIF_TRY(c->k_pairs_cnt.reserve(16 * N + 16));
+        STIF_CUDA(cudaStreamSynchronize(st));
+    }
+    c->n_pairs = (int64_t)total;
+    *n_pairs = (int64_t)total;
+    return STIF_OK;
+}
+
+extern "C" int stif_kriging_pairs_fetch(stif_ctx *c, int64_t *pairs_out)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_pairs_fetch"));
+    if (c->n_pairs < 0) {
+        set_error("stif_kriging_pairs_fetch: call stif_kriging_pairs_count first");
+        return STIF_ESTATE;
+    }
+    if (c->n_pairs == 0) return STIF_OK;
+    if (!pairs_out) {
+        set_error("stif_kriging_pairs_fetch: NULL output");
+        return STIF_EINVAL;
+    }
+    const int64_t total = c->n_pairs;
+    cudaStream_t st = c->stream;
+    // sorted keys sit in the first half of k_pairs_b; unpack into k_pairs_a (16 B per pair)
+    STIF_TRY(c->k_pairs_a.reserve(16 * (size_t)total));
+    pairs_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        c->k_pairs_b.as<unsigned long long>(), total, c->k_pairs_a.as<long long>());
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaMemcpyAsync(pairs_out, c->k_pairs_a.p, 16 * (size_t)total, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
     return STIF_OK;
 }

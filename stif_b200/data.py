@@ -83,3 +83,20 @@ class Data:
 
     def get_training_covariates(self):
         return self.prepare_covariates(self._training_df)
+
+    def get_kriging_idxs(self, space, time, space_dist_max, time_dist_max, leave_out_idxs, context=None):
+        """Indices of the training data within the spatial and temporal distance of each target
+        (stif/data.py:170-212): (P, 2) int64 [obs_idx, target_idx], ordered like np.nonzero.
+        Found on the GPU through the space-time grid instead of the dense n_obs x n_targets
+        distance matrices.  (The Predictor does not call this: its kriging path fuses the
+        search with the selection of the k lowest-gamma neighbours.)"""
+        from . import _native
+        ctx = context if context is not None else _native.default_context()
+        if getattr(ctx, "_obs_owner", None) is not self:
+            x, y = _native.split_space(self.space_coords)
+            t = self.time_coords
+            ctx.kriging_set_obs(x, y, t, np.zeros(len(t)))
+            ctx._obs_owner = self
+        tx, ty = _native.split_space(np.asarray(space).reshape(-1, 2))
+        return ctx.kriging_neighbour_pairs(tx, ty, np.asarray(time).reshape(-1), space_dist_max,
+                                           time_dist_max, leave_out_idxs)

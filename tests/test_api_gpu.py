@@ -220,3 +220,29 @@ def test_set_residuals_keeps_grid_and_matches_full_upload(ctx):
     assert np.array_equal(m_a, m_b) and np.array_equal(s_a, s_b)
     with pytest.raises(ValueError):
         ctx.kriging_set_residuals(z2[:10])
+
+
+def test_data_get_kriging_idxs_matches_reference_filter(pm10, ctx):
+    """Data.get_kriging_idxs on the GPU == the reference's dense cdist filter (stif/data.py:170-212):
+    same pairs, same order; strict radii, causal filter, leave-out, integer times."""
+    data = Data(pm10, space_cols=["x", "y"], time_col="time", predictand_col="PM10")
+    sp, tm = data.space_coords, data.time_coords
+    sel = np.arange(0, len(tm), 47)
+    for leave in (None, sel):
+        got = data.get_kriging_idxs(sp[sel], tm[sel], 2e5, 4, leave, context=ctx)
+        want = ok.kriging_idxs(sp, tm, sp[sel], tm[sel], 2e5, 4, leave)
+        assert got.dtype == np.int64 and got.shape == want.shape
+        assert np.array_equal(got, want)
+    # synthetic, float times, targets outside the data, empty result
+    rng = np.random.default_rng(9)
+    n = 30000
+    df = pd.DataFrame({"x": rng.uniform(0, 100, n), "y": rng.uniform(0, 100, n), "time": rng.uniform(0, 365, n),
+                       "v": rng.normal(size=n)})
+    d2 = Data(df, space_cols=["x", "y"], time_col="time", predictand_col="v")
+    tsp = rng.uniform(-20, 120, (700, 2))
+    tt = rng.uniform(-10, 400, 700)
+    got = d2.get_kriging_idxs(tsp, tt, 7.5, 11.0, None, context=ctx)
+    want = ok.kriging_idxs(d2.space_coords, d2.time_coords, tsp, tt, 7.5, 11.0, None)
+    assert np.array_equal(got, want) and len(want) > 1000
+    none = d2.get_kriging_idxs(tsp[:5] + 1e6, tt[:5], 7.5, 11.0, None, context=ctx)
+    assert none.shape == (0, 2)

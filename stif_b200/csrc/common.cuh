@@ -76,6 +76,10 @@ struct stif_ctx {
     cudaEvent_t ev[6] = {nullptr};      // phase timing events
     int n_phase = 0;                    // number of valid phases recorded in the last call
     cudaStream_t last_stream = nullptr; // stream the last call was enqueued on
+    cudaStream_t stream2 = nullptr;     // copy stream of the chunked host pipeline
+    cudaEvent_t *ev_override = nullptr; // phase events of the chunk being enqueued (pipeline)
+    bool keep_stats = false;            // pipeline: accumulate the statistics over the chunks
+    std::vector<cudaEvent_t> chunk_ev;  // 4 phase events per chunk of the last pipelined call
 
     // ---- variogram scratch ----
     stif::DevBuf v_keys, v_keys_out, v_idx, v_idx_out, v_cubtmp;  // time sort

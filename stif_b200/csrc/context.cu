@@ -108,6 +108,8 @@ int stif_ctx_destroy(stif_ctx *c)
     for (auto &b : c->k_scratch) b.release();
     for (int i = 0; i < 6; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (auto e : c->chunk_ev) cudaEventDestroy(e);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return STIF_OK;
@@ -123,6 +125,17 @@ int stif_last_phase_ms(stif_ctx *c, float out[4])
     }
     STIF_CUDA(cudaSetDevice(c->device));
     for (int i = 0; i < 4; ++i) out[i] = 0.f;
+    if (!c->chunk_ev.empty()) {     // pipelined host call: phases summed over the chunks
+        for (size_t k = 0; k + 3 < c->chunk_ev.size(); k += 4) {
+            STIF_CUDA(cudaEventSynchronize(c->chunk_ev[k + 3]));
+            for (int i = 0; i < 3; ++i) {
+                float ms = 0.f;
+                STIF_CUDA(cudaEventElapsedTime(&ms, c->chunk_ev[k + i], c->chunk_ev[k + i + 1]));
+                out[i] += ms;
+            }
+        }
+        return STIF_OK;
+    }
     if (c->n_phase == 0) return STIF_OK;
     STIF_CUDA(cudaEventSynchronize(c->ev[c->n_phase]));
     for (int i = 0; i < c->n_phase && i < 4; ++i)

@@ -1668,18 +1668,23 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     }
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
     c->last_stream = st;
+    cudaEvent_t *ev = c->ev_override ? c->ev_override : c->ev;
+    if (!c->ev_override && !c->chunk_ev.empty()) {     // phases of an earlier pipelined call
+        for (auto e : c->chunk_ev) cudaEventDestroy(e);
+        c->chunk_ev.clear();
+    }
     STIF_TRY(c->k_stats.reserve(8 * sizeof(unsigned long long)));
-    STIF_CUDA(cudaMemsetAsync(c->k_stats.p, 0, 8 * sizeof(unsigned long long), st));
-    STIF_CUDA(cudaEventRecord(c->ev[0], st));
+    if (!c->keep_stats) STIF_CUDA(cudaMemsetAsync(c->k_stats.p, 0, 8 * sizeof(unsigned long long), st));
+    STIF_CUDA(cudaEventRecord(ev[0], st));
     c->n_phase = 3;
     if (n_targets == 0) {
-        for (int i = 1; i <= 3; ++i) STIF_CUDA(cudaEventRecord(c->ev[i], st));
+        for (int i = 1; i <= 3; ++i) STIF_CUDA(cudaEventRecord(ev[i], st));
         return STIF_OK;
     }
     Model M;
     STIF_TRY(build_model(c->model, M));
     STIF_TRY(ensure_grid(c, smax, tmax, st));
-    STIF_CUDA(cudaEventRecord(c->ev[1], st));
+    STIF_CUDA(cudaEventRecord(ev[1], st));
 
     const int k = max_pts;
     const int nr_pad = (k + 1 + 7) / 8 * 8;      // rows of the padded system
@@ -1770,7 +1775,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             else search_kernel<0><<<sgrid, SEARCH_WARPS * 32, 0, st>>>(SP);
         }
         STIF_CUDA(cudaGetLastError());
-        if (c0 + chunk >= n_targets) STIF_CUDA(cudaEventRecord(c->ev[2], st));
+        if (c0 + chunk >= n_targets) STIF_CUDA(cudaEventRecord(ev[2], st));
 
         SolveParams QP;
         QP.ox = ox;
@@ -1879,7 +1884,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
                                                  c->k_stats.as<unsigned long long>());
         STIF_CUDA(cudaGetLastError());
     }
-    STIF_CUDA(cudaEventRecord(c->ev[3], st));
+    STIF_CUDA(cudaEventRecord(ev[3], st));
     return STIF_OK;
 }
 
@@ -1915,6 +1920,69 @@ extern "C" int stif_kriging_predict_host(stif_ctx *c, const double *tx, const do
     STIF_TRY(c->k_scratch[S_STAGE].reserve(off));
     char *b = c->k_scratch[S_STAGE].as<char>();
     cudaStream_t st = c->stream;
+    constexpr int64_t PIPE_MIN = 600000, PIPE_CHUNK = 1 << 18;
+    if (n > PIPE_MIN) {
+        // Chunked two-stream pipeline: the host-to-device copy of chunk i+1 and the
+        // device-to-host copy of chunk i-1 run under the kernels of chunk i.
+        if (!c->stream2) STIF_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        cudaStream_t cs = c->stream2;
+        const int nchunk = (int)((n + PIPE_CHUNK - 1) / PIPE_CHUNK);
+        for (auto e : c->chunk_ev) cudaEventDestroy(e);
+        c->chunk_ev.assign((size_t)4 * nchunk, nullptr);
+        for (auto &e : c->chunk_ev) STIF_CUDA(cudaEventCreate(&e));
+        std::vector<cudaEvent_t> ev_h(nchunk), ev_d(nchunk);
+        for (int i = 0; i < nchunk; ++i) {
+            STIF_CUDA(cudaEventCreateWithFlags(&ev_h[i], cudaEventDisableTiming));
+            STIF_CUDA(cudaEventCreateWithFlags(&ev_d[i], cudaEventDisableTiming));
+        }
+        STIF_TRY(c->k_stats.reserve(8 * sizeof(unsigned long long)));
+        STIF_CUDA(cudaMemsetAsync(c->k_stats.p, 0, 8 * sizeof(unsigned long long), st));
+        int rc = STIF_OK;
+        auto d2h = [&](int ci) -> int {
+            const size_t o = (size_t)ci * PIPE_CHUNK, len = (size_t)((n - (int64_t)o < PIPE_CHUNK) ? n - (int64_t)o : PIPE_CHUNK);
+            STIF_CUDA(cudaStreamWaitEvent(cs, ev_d[ci], 0));
+            STIF_CUDA(cudaMemcpyAsync(mean_out + o, b + o_mean + 8 * o, 8 * len, cudaMemcpyDeviceToHost, cs));
+            STIF_CUDA(cudaMemcpyAsync(std_out + o, b + o_std + 8 * o, 8 * len, cudaMemcpyDeviceToHost, cs));
+            if (w_out) STIF_CUDA(cudaMemcpyAsync(w_out + o * k, b + o_w + 4 * o * k, 4 * len * k, cudaMemcpyDeviceToHost, cs));
+            if (gamma_out) STIF_CUDA(cudaMemcpyAsync(gamma_out + o * k, b + o_g + 4 * o * k, 4 * len * k, cudaMemcpyDeviceToHost, cs));
+            if (idx_out) STIF_CUDA(cudaMemcpyAsync(idx_out + o * k, b + o_idx + 4 * o * k, 4 * len * k, cudaMemcpyDeviceToHost, cs));
+            if (n_used_out) STIF_CUDA(cudaMemcpyAsync(n_used_out + o, b + o_nu + 4 * o, 4 * len, cudaMemcpyDeviceToHost, cs));
+            return STIF_OK;
+        };
+        for (int ci = 0; ci < nchunk && rc == STIF_OK; ++ci) {
+            const size_t o = (size_t)ci * PIPE_CHUNK, len = (size_t)((n - (int64_t)o < PIPE_CHUNK) ? n - (int64_t)o : PIPE_CHUNK);
+            cudaMemcpyAsync(b + o_tx + 8 * o, tx + o, 8 * len, cudaMemcpyHostToDevice, cs);
+            cudaMemcpyAsync(b + o_ty + 8 * o, ty + o, 8 * len, cudaMemcpyHostToDevice, cs);
+            cudaMemcpyAsync(b + o_tt + 8 * o, tt + o, 8 * len, cudaMemcpyHostToDevice, cs);
+            if (leave_out) cudaMemcpyAsync(b + o_lo + 8 * o, leave_out + o, 8 * len, cudaMemcpyHostToDevice, cs);
+            cudaEventRecord(ev_h[ci], cs);
+            cudaStreamWaitEvent(st, ev_h[ci], 0);
+            c->ev_override = &c->chunk_ev[(size_t)4 * ci];
+            c->keep_stats = true;
+            rc = stif_kriging_predict_dev(
+                c, (double *)(b + o_tx) + o, (double *)(b + o_ty) + o, (double *)(b + o_tt) + o,
+                leave_out ? (int64_t *)(b + o_lo) + o : nullptr, (int64_t)len, min_pts, max_pts, smax, tmax, flags,
+                (double *)(b + o_mean) + o, (double *)(b + o_std) + o, w_out ? (float *)(b + o_w) + o * k : nullptr,
+                gamma_out ? (float *)(b + o_g) + o * k : nullptr, idx_out ? (uint32_t *)(b + o_idx) + o * k : nullptr,
+                n_used_out ? (int32_t *)(b + o_nu) + o : nullptr, st);
+            c->ev_override = nullptr;
+            c->keep_stats = false;
+            if (rc != STIF_OK) break;
+            cudaEventRecord(ev_d[ci], st);
+            if (ci > 0) rc = d2h(ci - 1);
+        }
+        if (rc == STIF_OK) rc = d2h(nchunk - 1);
+        cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
+        for (int i = 0; i < nchunk; ++i) {
+            cudaEventDestroy(ev_h[i]);
+            cudaEventDestroy(ev_d[i]);
+        }
+        if (rc != STIF_OK) return rc;
+        STIF_CUDA(e1);
+        STIF_CUDA(e2);
+        STIF_CUDA(cudaGetLastError());
+        return STIF_OK;
+    }
     STIF_CUDA(cudaMemcpyAsync(b + o_tx, tx, 8 * N, cudaMemcpyHostToDevice, st));
     STIF_CUDA(cudaMemcpyAsync(b + o_ty, ty, 8 * N, cudaMemcpyHostToDevice, st));
     STIF_CUDA(cudaMemcpyAsync(b + o_tt, tt, 8 * N, cudaMemcpyHostToDevice, st));

@@ -237,3 +237,35 @@ def test_c5_indicator_kriging_k100(ctx):
     assert np.array_equal(idx[:ns][rows], o["idx"][rows])
     mscale = np.sum(np.abs(o["w"].astype(np.float64)) * np.abs(z[o["idx"].astype(np.int64)]), axis=1)
     assert np.all(np.abs(m[:ns] - o["mean"])[rows] <= 1e-9 * mscale[rows])
+
+
+def test_pipelined_host_call_equals_plain_calls(ctx):
+    """Host calls with more than 600k targets take the chunked two-stream pipeline (copies of
+    the neighbouring chunks under the kernels): bit-identical to plain calls on pieces below the
+    threshold, statistics accumulated over the chunks, optional outputs and leave-out included."""
+    (x, y, t, z), (tx, ty, tt) = synth_kriging(1_000_000, 1_500_000, 77)
+    ctx.kriging_set_obs(x, y, t, z)
+    ctx.kriging_set_model(*C4_MODEL, C4_PARAMS)
+    m, s = ctx.kriging_predict_host(tx, ty, tt, 1, 50, 30.0, 30.0)
+    st = ctx.kriging_stats()
+    ph = ctx.last_phase_ms()
+    assert ph[1] > 0 and ph[2] > 0
+    pieces = [slice(0, 500_000), slice(500_000, 1_000_000), slice(1_000_000, 1_500_000)]
+    ms, ss, sts = [], [], []
+    for p in pieces:
+        a, b = ctx.kriging_predict_host(tx[p], ty[p], tt[p], 1, 50, 30.0, 30.0)
+        ms.append(a)
+        ss.append(b)
+        sts.append(ctx.kriging_stats())
+    assert np.array_equal(m, np.concatenate(ms)) and np.array_equal(s, np.concatenate(ss))
+    for key in st:
+        assert st[key] == sum(q[key] for q in sts), key
+    # optional outputs + leave-out
+    n = 900_000
+    lo = np.random.default_rng(3).integers(0, len(x), n)
+    a = ctx.kriging_predict_host(tx[:n], ty[:n], tt[:n], 1, 8, 30.0, 30.0, leave_out=lo, want_weights=True)
+    h = 450_000
+    b1 = ctx.kriging_predict_host(tx[:h], ty[:h], tt[:h], 1, 8, 30.0, 30.0, leave_out=lo[:h], want_weights=True)
+    b2 = ctx.kriging_predict_host(tx[h:n], ty[h:n], tt[h:n], 1, 8, 30.0, 30.0, leave_out=lo[h:], want_weights=True)
+    for q in range(6):
+        assert np.array_equal(a[q], np.concatenate([b1[q], b2[q]])), q

@@ -8,21 +8,24 @@
 //   stif/predictor.py:882-906   mean / std epilogue
 //
 // Pipeline per call (one stream, no host synchronisation inside):
-//   grid   : observations binned into a uniform space-time grid whose cells are at least
-//            one search radius wide; (cell, obs-index) radix-sorted (CUB, plumbing), so each
-//            cell is a contiguous run in ascending observation index.  Cached per
-//            (obs set, radii).
+//   grid   : observations binned into a uniform space-time grid with two cells per search
+//            radius; (cell, obs-index) radix-sorted (CUB, plumbing), so each cell is a contiguous
+//            run in ascending observation index.  Cached per (obs set, radii).
 //   search : one warp per target (targets visited in grid-cell order for L2 locality).  The
-//            3x3x2 (causal) cell stencil is 6 contiguous runs; lanes stream the runs
-//            coalesced, apply the reference's exact filter
+//            causal 5x5x3 cell stencil is 15 contiguous runs, concatenated into one virtual
+//            sequence; lanes stream it coalesced (four loads in flight), apply the reference's
+//            exact filter
 //              rn(dx*dx)+rn(dy*dy) < smax^2  &  |dt| < tmax  &  t_obs <= t_tgt  &  not left out
 //            (stif/data.py:195-211; unfused like scipy cdist), compact survivors with a
 //            ballot, evaluate gamma(h,t) densely, and keep the k lowest (gamma, index) with a
-//            warp-wide bisection select; bounded shared memory for any candidate count.
-//   solve  : one warp per target assembles the (k+1)x(k+2) augmented ordinary-kriging system
-//            in shared memory, factorises with partially pivoted LU, back-substitutes, and
-//            runs the fused epilogue (float32 storage emulation + numpy pairwise order, or
-//            all-float64).
+//            warp-wide select; bounded shared memory for any candidate count.
+//   solve  : valid variogram models: covariance-form Cholesky, one warp per target
+//            (krig_chol.cuh); every other model, and targets whose covariance matrix is not
+//            positive definite: pivoted LU of the reference's bordered system, one CTA per
+//            target (solve_blk_kernel).  Both end in the fused epilogue (float32 storage
+//            emulation + numpy pairwise order, or all-float64).
+// Also here: the stand-alone neighbour pair list (Data.get_kriging_idxs), the elementwise
+// model evaluation, and the objective of the variogram-model fit.
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>

@@ -149,10 +149,10 @@ __global__ void scan_kernel(const int *count, int nI, int *prefix)
 }
 
 struct Smem {
+    double *g_sum;         // [n_bins] this block's partial sums in GLOBAL memory (native L2 f64 atomics)
     double4 *s_i;          // [TI]
     double4 *s_j;          // [TJ]
     unsigned short *q;     // [QCAP][VT]
-    double *s_sum;         // [n_bins]
     unsigned *s_cnt;       // [n_bins]
     double *s_thr;         // [n_space_bins + 2]
     unsigned *stg;         // [VT/32][64] per-warp staging of compacted queue entries
@@ -163,15 +163,19 @@ __device__ __forceinline__ void st_shared_u16(unsigned addr, unsigned short v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
-// Histogram update of one binned pair: shared-memory atomics (the FP64 add is a CAS loop on
-// sm_100a -- ATOMS.CAST.SPIN.64 -- the count a native ATOMS.POPC.INC).  A warp-aggregated
+// Histogram update of one binned pair.  The count is a native shared-memory atomic
+// (ATOMS.POPC.INC).  The FP64 sum goes to the block's partial histogram in GLOBAL memory with a
+// native L2 atomic (REDG.E.ADD.F64, fire and forget): on sm_100a a shared-memory f64 add is a
+// compare-and-swap loop (ATOMS.CAST.SPIN.64, 2.95 tries per warp on C2 because a warp's pairs
+// share the time bin) and was 16 % of the kernel's stall samples; the block's 7.2 KB of
+// partial sums stay in L2.  A warp-aggregated
 // variant (match_any + shuffle reduction per distinct bin) was measured 2x SLOWER on C2
 // (profiles/r01_notes.md): a warp's 32 staged pairs spread over ~25 distinct bins, so there
 // is little to aggregate and the extra shuffles dominate.
 __device__ __forceinline__ void accumulate(const Smem &S, int bin /* < 0: nothing */, double val)
 {
     if (bin >= 0) {
-        atomicAdd(&S.s_sum[bin], val);
+        atomicAdd(&S.g_sum[bin], val);
         atomicAdd(&S.s_cnt[bin], 1u);
     }
 }
@@ -312,20 +316,22 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
     S.s_i = reinterpret_cast<double4 *>(smem_raw);
     S.s_j = S.s_i + TI;
     S.q = reinterpret_cast<unsigned short *>(S.s_j + TJ);
-    S.s_sum = reinterpret_cast<double *>(S.q + QCAP * VT);
-    S.s_thr = S.s_sum + P.n_bins;
+    S.s_thr = reinterpret_cast<double *>(S.q + QCAP * VT);
     S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
     S.stg = S.s_cnt + P.n_bins;
 
     const int tid = threadIdx.x;
     for (int b = tid; b < P.n_bins; b += VT) {
-        S.s_sum[b] = 0.0;
         S.s_cnt[b] = 0u;
     }
     for (int b = tid; b < P.n_space_bins + 2; b += VT) S.s_thr[b] = P.thr[b];
     unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
     double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
-    for (int b = tid; b < P.n_bins; b += VT) my_cnt[b] = 0ull;
+    for (int b = tid; b < P.n_bins; b += VT) {
+        my_cnt[b] = 0ull;
+        my_sum[b] = 0.0;
+    }
+    S.g_sum = my_sum;
 
     const long long M = P.item_prefix[P.nI];  // total items
     unsigned long long npass = 0;
@@ -370,7 +376,6 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
     __syncthreads();
     for (int b = tid; b < P.n_bins; b += VT) {
         my_cnt[b] += S.s_cnt[b];
-        my_sum[b] = S.s_sum[b];
     }
     // stats: passing pairs (warp reduce, one atomic per warp)
     for (int off = 16; off > 0; off >>= 1) npass += __shfl_xor_sync(0xffffffffu, npass, off);
@@ -732,7 +737,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     }
 
     const size_t smem = sizeof(double4) * (TI + TJ) + sizeof(unsigned short) * QCAP * VT +
-                        (sizeof(double) + sizeof(unsigned)) * (size_t)n_bins +
+                        sizeof(unsigned) * (size_t)n_bins +
                         sizeof(double) * ((size_t)ns + 2) + sizeof(unsigned) * 64 * (VT / 32);
     STIF_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));

@@ -25,6 +25,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace stif {
@@ -33,12 +34,19 @@ namespace vario {
 constexpr int VT = 256;        // threads per block
 constexpr int VR = 4;          // i-points per thread (registers)
 constexpr int TI = VT * VR;    // i-tile: 1024 observations
-constexpr int TJ = 256;        // j-sub-tile: 256 observations (8-bit index in the queue)
+constexpr int TJ = 256;        // j-sub-tile: 256 observations
 constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
-constexpr int QCAP = 32;       // queue slots per thread (uint16 each)
-constexpr int VG = 4;          // j-iterations between queue-overflow checks
+constexpr int QW = 512;       // entries (uint32) of a warp's circular queue
+constexpr int VG = 4;          // j-points between queue checks (each queues <= 32 entries)
 constexpr int MAX_BINS = 8192; // shared-memory histogram limit (12 B per bin)
 constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x 2^18 pairs < 2^32: u32 counts are safe
+
+// Constants of the float pre-filter, written by filter_setup_kernel.
+struct FilterConst {
+    double cx, cy, ct;  // centre of the bounding box (subtracted before the float conversion)
+    float thi;          // d2f > thi  => the pair is certainly outside the space cut-off
+    float tmaxf;        // |dtf| > tmaxf => certainly outside the time cut-off
+};
 
 struct Params {
     const double4 *pts;   // sorted, padded observations
@@ -58,6 +66,9 @@ struct Params {
     const double *thr;    // [n_space_bins + 2] d2 thresholds: bin b <=> thr[b] <= d2 < thr[b+1]
     int use_thr;          // 0: evaluate sqrt/mul/trunc per binned pair (degenerate widths)
     float inv_ws_f;       // float copy of inv_ws for the first guess
+    float guard;          // distance from an integer below which the float guess is re-checked
+    int sorted;           // observations are time-sorted (culling on)
+    const FilterConst *filter;
 };
 
 __global__ void pack_keys_kernel(const double *t, int64_t n, double *keys, unsigned *idx)
@@ -75,20 +86,83 @@ __global__ void iota_kernel(int64_t n, unsigned *idx)
     if (i < n) idx[i] = (unsigned)i;
 }
 
+// Order-preserving map double -> uint64 (every real maps above 0, so zero-initialised
+// atomicMax cells mean "no data yet").
+__device__ __forceinline__ unsigned long long ord_enc(double d)
+{
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_dec(unsigned long long e)
+{
+    const unsigned long long u = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)u);
+}
+
+// Gather into the sorted AoS array; also the bounding box of (x, y, t) for the float pre-filter:
+// ext[0..5] = max of enc(x), enc(-x), enc(y), enc(-y), enc(t), enc(-t) over the non-NaN values.
 __global__ void gather_kernel(const double *x, const double *y, const double *t, const double *v,
-                              const unsigned *idx, int64_t n, int64_t n_pad, double4 *pts)
+                              const unsigned *idx, int64_t n, int64_t n_pad, double4 *pts,
+                              unsigned long long *ext)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_pad) return;
-    double4 p;
-    if (k < n) {
-        unsigned i = idx[k];
-        p = make_double4(x[i], y[i], t[i], v[i]);
-    } else {
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-        p = make_double4(qnan, qnan, qnan, 0.0);  // NaN never passes d2 <= tcut
+    unsigned long long e[6] = {0, 0, 0, 0, 0, 0};
+    if (k < n_pad) {
+        double4 p;
+        if (k < n) {
+            unsigned i = idx[k];
+            p = make_double4(x[i], y[i], t[i], v[i]);
+            if (p.x == p.x) { e[0] = ord_enc(p.x); e[1] = ord_enc(-p.x); }
+            if (p.y == p.y) { e[2] = ord_enc(p.y); e[3] = ord_enc(-p.y); }
+            if (p.z == p.z) { e[4] = ord_enc(p.z); e[5] = ord_enc(-p.z); }
+        } else {
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            p = make_double4(qnan, qnan, qnan, 0.0);  // NaN never passes d2 <= tcut
+        }
+        pts[k] = p;
     }
-    pts[k] = p;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        unsigned long long m = e[c];
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
+            m = o > m ? o : m;
+        }
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(&ext[c], m);
+    }
+}
+
+// Constants of the float pre-filter (one thread).  Coordinates are centred on the bounding box
+// and converted to float; with X = the half extent, a float coordinate difference is within
+// Ex = X * 2^-22 of the exact one (two conversions at X * 2^-24 each, the float subtraction at
+// 2X * 2^-24), the float distance within E = Ex + Ey of the exact distance, and its square as
+// computed (FMUL + FFMA) within a relative 2^-22 of that.  Every pair the reference keeps
+// (sqrt_rn(d2) <= smax) therefore has d2f <= thi; pairs above thi are dropped in the sweep,
+// everything else is decided exactly, in FP64, by the drain.  Same for the time lag.
+// Non-finite extents or bounds make thi / tmaxf infinite: the filter passes everything.
+__global__ void filter_setup_kernel(const unsigned long long *ext, double smax, double tmax,
+                                    FilterConst *F)
+{
+    double lo[3], hi[3], c[3], h[3];
+    for (int a = 0; a < 3; ++a) {
+        const bool any = ext[2 * a] != 0ull;
+        hi[a] = any ? ord_dec(ext[2 * a]) : 0.0;
+        lo[a] = any ? -ord_dec(ext[2 * a + 1]) : 0.0;
+        c[a] = 0.5 * lo[a] + 0.5 * hi[a];
+        if (!isfinite(c[a])) c[a] = 0.0;
+        h[a] = fmax(fabs(hi[a] - c[a]), fabs(lo[a] - c[a])) * (1.0 + 1e-6);
+    }
+    const double k22 = 2.384185791015625e-07 * (1.0 + 1e-6);  // 2^-22
+    const double E = (h[0] + h[1]) * k22, Et = h[2] * k22;
+    const double s = fabs(smax) * (1.0 + 1e-9) + E;
+    double thi = s * s * (1.0 + 1e-6);
+    double tm = (fabs(tmax) + Et) * (1.0 + 1e-6);
+    const float inf = __int_as_float(0x7f800000);
+    F->cx = c[0];
+    F->cy = c[1];
+    F->ct = c[2];
+    F->thi = (isfinite(thi) && thi < 1e37) ? __double2float_ru(thi) : inf;
+    F->tmaxf = (isfinite(tm) && tm < 1e37) ? __double2float_ru(tm) : inf;
 }
 
 // One thread per i-tile: last j-sub-tile that may hold a pair with rn(tj - ti) <= tmax.
@@ -149,181 +223,192 @@ __global__ void scan_kernel(const int *count, int nI, int *prefix)
 }
 
 struct Smem {
-    double *g_sum;         // [n_bins] this block's partial sums in GLOBAL memory (native L2 f64 atomics)
-    double4 *s_i;          // [TI]
-    double4 *s_j;          // [TJ]
-    unsigned short *q;     // [QCAP][VT]
-    unsigned *s_cnt;       // [n_bins]
-    double *s_thr;         // [n_space_bins + 2]
-    unsigned *stg;         // [VT/32][64] per-warp staging of compacted queue entries
+    double *g_sum;           // [n_bins] this block's partial sums in GLOBAL memory (L2 f64 atomics)
+    // tiles split into 16-byte halves: a random-index LDS.128 then spreads over all eight
+    // 16-byte bank groups (a 32-byte AoS stride uses only four: 2-way conflicts at best)
+    double2 *s_ixy, *s_itv;  // [TI] {x,y}, {t,v}
+    double2 *s_jxy, *s_jtv;  // [TJ]
+    float4 *s_jf;            // [TJ] {x-cx, y-cy, t-ct, 0} in float: the sweep's copy
+    unsigned *q;             // [VT/32][QW] one circular queue per warp
+    unsigned *s_cnt;         // [n_bins]
+    double *s_thr;           // [n_space_bins + 2]
 };
 
-__device__ __forceinline__ void st_shared_u16(unsigned addr, unsigned short v)
+__device__ __forceinline__ void st_shared_u32(unsigned addr, unsigned v)
 {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// Histogram update of one binned pair.  The count is a native shared-memory atomic
-// (ATOMS.POPC.INC).  The FP64 sum goes to the block's partial histogram in GLOBAL memory with a
-// native L2 atomic (REDG.E.ADD.F64, fire and forget): on sm_100a a shared-memory f64 add is a
-// compare-and-swap loop (ATOMS.CAST.SPIN.64, 2.95 tries per warp on C2 because a warp's pairs
-// share the time bin) and was 16 % of the kernel's stall samples; the block's 7.2 KB of
-// partial sums stay in L2.  A warp-aggregated
-// variant (match_any + shuffle reduction per distinct bin) was measured 2x SLOWER on C2
-// (profiles/r01_notes.md): a warp's 32 staged pairs spread over ~25 distinct bins, so there
-// is little to aggregate and the extra shuffles dominate.
-__device__ __forceinline__ void accumulate(const Smem &S, int bin /* < 0: nothing */, double val)
+// Bin one queued pair per lane: j-point j and i-point ii of the staged tiles, everything in
+// FP64 exactly as the reference executes it.  The queue holds every pair the float pre-filter
+// could not rule out, so the reference's two cut-off tests are applied here.  Returns whether
+// the pair is inside the window (statistics).
+//
+// Histogram update: the count is a native shared-memory atomic (ATOMS.POPC.INC).  The FP64 sum
+// goes to the block's partial histogram in GLOBAL memory with a native L2 atomic
+// (REDG.E.ADD.F64, fire and forget): on sm_100a a shared-memory f64 add is a compare-and-swap
+// loop (ATOMS.CAST.SPIN.64, 2.95 tries per warp on C2) and was 16 % of the kernel's stall
+// samples; the block's 7.2 KB of partial sums stay in L2.  A warp-aggregated variant (match_any
+// + shuffle reduction per distinct bin) was measured 2x SLOWER on C2 (profiles/r01_notes.md): a
+// warp's 32 pairs spread over ~25 distinct bins, so there is little to aggregate.
+__device__ __forceinline__ double2 lds_d2(unsigned addr)
 {
-    if (bin >= 0) {
-        atomicAdd(&S.g_sum[bin], val);
-        atomicAdd(&S.s_cnt[bin], 1u);
-    }
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_d(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
 }
 
-// Bin one in-window pair per lane.  e = (owner lane << 16) | (r << 8) | j.
-__device__ __forceinline__ void bin_entry(const Smem &S, const Params &P, int warp_base, int lane,
-                                          unsigned e, bool have)
+template <int MODE>
+__device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigned sbase, int j,
+                                         int ii, bool have)
 {
-    int bin = -1;
-    double val = 0.0;
+    // byte offsets of the tile halves from the start of dynamic shared memory (= sbase)
+    constexpr unsigned O_IXY = 0, O_ITV = 16 * TI, O_JXY = 32 * TI, O_JTV = 32 * TI + 16 * TJ;
+    bool inside = false;
     if (have) {
-        const int j = e & 0xff, r = (e >> 8) & 0xff, owner = e >> 16;
-        const double4 pi = S.s_i[r * VT + warp_base + owner];
-        const double4 pj = S.s_j[j];
-        const double dx = __dsub_rn(pi.x, pj.x);
-        const double dy = __dsub_rn(pi.y, pj.y);
+        const double2 ixy = lds_d2(sbase + O_IXY + 16u * ii), itv = lds_d2(sbase + O_ITV + 16u * ii);
+        const double2 jxy = lds_d2(sbase + O_JXY + 16u * j), jtv = lds_d2(sbase + O_JTV + 16u * j);
+        const double dx = __dsub_rn(ixy.x, jxy.x);
+        const double dy = __dsub_rn(ixy.y, jxy.y);
         const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
-        const double lag_t = fabs(__dsub_rn(pi.z, pj.z));
-        // both bin indices are bounded by the cut-offs that let the pair in (lag <= max =
-        // n_bins * width), so 32-bit conversions are exact
-        int bs;
-        if (P.use_thr) {
-            // trunc(sqrt_rn(d2)*inv_ws) is monotone in d2: look the bin up in the exact d2
-            // thresholds (host-bisected with the reference's formula) from a float guess
+        const double lag_t = fabs(__dsub_rn(itv.x, jtv.x));
+        inside = (d2 <= P.tcut) && (lag_t <= P.tmax);  // utils.py:160-165
+        if (inside) {
+            // both bin indices are bounded by the cut-offs that let the pair in (lag <= max =
+            // n_bins * width), so 32-bit conversions are exact.
+            // trunc(sqrt_rn(d2)*inv_ws) is monotone in d2: the bin is looked up in the exact d2
+            // thresholds (host-bisected with the reference's formula) from a float guess.  The
+            // guess itself is already the answer unless it lies within the float error bound
+            // (relative 2^-21.4: rounding of d2, sqrt.approx, inv_ws_f, the product) of an
+            // integer; `guard` = 2^-19 * n_space_bins, so ~1e-4 of the pairs take the lookup
+            // (guard = 2 with degenerate bin widths: every pair takes the slow path, which then
+            // evaluates the reference's expression).
             float f = __double2float_rn(d2), sq;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
-            int b = __float2int_rz(fminf(sq * P.inv_ws_f, (float)P.n_space_bins));
-            b = b < 0 ? 0 : b;
-            while (d2 < S.s_thr[b]) --b;
-            while (d2 >= S.s_thr[b + 1]) ++b;
-            bs = b;
-        } else {
-            bs = __double2int_rz(__dmul_rn(__dsqrt_rn(d2), P.inv_ws));
-        }
-        const int bt = __double2int_rz(__dmul_rn(lag_t, P.inv_wt));
-        if ((unsigned)bs < (unsigned)P.n_space_bins && (unsigned)bt < (unsigned)P.n_time_bins) {
-            if (P.mode == 0) {
-                const double a = __dsub_rn(pi.w, pj.w);
-                val = __dmul_rn(a, a);
-            } else {
-                val = __dmul_rn(__dsub_rn(pi.w, P.mean), __dsub_rn(pj.w, P.mean));
-            }
-            bin = bs * P.n_time_bins + bt;
-        }
-    }
-    accumulate(S, bin, val);
-}
-
-// Drain the 32 per-thread queues of a warp.  Slot s of every lane that has one is compacted
-// (ballot) into the warp's staging buffer; whenever 32 entries are staged they are binned
-// with all lanes active.  `nst` (warp-uniform) carries the < 32 leftovers to the next call;
-// `flush` bins them too (end of an item, before the tiles are replaced).
-__device__ __forceinline__ void drain(const Smem &S, const Params &P, int tid, int cnt, int &nst,
-                                      bool flush)
-{
-    const int lane = tid & 31, warp_base = tid & ~31;
-    unsigned *stg = S.stg + (tid >> 5) * 64;
-    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-    for (int s = 0; s < maxcnt; ++s) {
-        const bool has = s < cnt;
-        const unsigned bal = __ballot_sync(0xffffffffu, has);
-        if (has) stg[nst + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)lane << 16) | S.q[s * VT + tid];
-        nst += __popc(bal);
-        __syncwarp();
-        if (nst >= 32) {
-            bin_entry(S, P, warp_base, lane, stg[lane], true);
-            const int rem = nst - 32;
-            const unsigned mv = (lane < rem) ? stg[32 + lane] : 0u;
-            __syncwarp();
-            if (lane < rem) stg[lane] = mv;
-            nst = rem;
-            __syncwarp();
-        }
-    }
-    if (flush && nst > 0) {
-        bin_entry(S, P, warp_base, lane, stg[lane], lane < nst);
-        nst = 0;
-        __syncwarp();
-    }
-}
-
-template <bool DIAG>
-__device__ __forceinline__ unsigned scan_item(const Smem &S, const Params &P, int tid, int ioff0)
-{
-    double xi[VR], yi[VR], ti[VR];
-    int ioff[VR];
-#pragma unroll
-    for (int r = 0; r < VR; ++r) {
-        const double4 p = S.s_i[r * VT + tid];
-        xi[r] = p.x;
-        yi[r] = p.y;
-        ti[r] = p.z;
-        ioff[r] = ioff0 + r * VT;  // (global i) - (global j of sub-tile start)
-    }
-    const double tcut = P.tcut, tmax = P.tmax;
-    unsigned npass = 0;
-    int nst = 0;
-    // 32-bit shared-window address of this thread's next free queue slot
-    const unsigned qbase = (unsigned)__cvta_generic_to_shared(S.q + tid);
-    unsigned qa = qbase;
-    const unsigned qhigh = qbase + (QCAP - VG * VR) * VT * 2;
-    for (int jb = 0; jb < TJ; jb += VG) {
-        if (__any_sync(0xffffffffu, qa > qhigh)) {
-            const int cnt = (int)((qa - qbase) / (2 * VT));
-            drain(S, P, tid, cnt, nst, false);
-            npass += cnt;
-            qa = qbase;
-        }
-#pragma unroll
-        for (int g = 0; g < VG; ++g) {
-            const int j = jb + g;
-            const double4 pj = S.s_j[j];
-#pragma unroll
-            for (int r = 0; r < VR; ++r) {
-                const double dx = __dsub_rn(xi[r], pj.x);
-                const double dy = __dsub_rn(yi[r], pj.y);
-                const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
-                const double dt = fabs(__dsub_rn(ti[r], pj.z));
-                bool pass = (d2 <= tcut) && (dt <= tmax);
-                if (DIAG) pass = pass && (j > ioff[r]);
-                if (pass) {
-                    st_shared_u16(qa, (unsigned short)(j | (r << 8)));
-                    qa += 2 * VT;
+            const float vf = __fmul_rn(sq, P.inv_ws_f), fl = floorf(vf), fr = __fsub_rn(vf, fl);
+            int bs = __float2int_rz(fminf(vf, (float)P.n_space_bins));
+            if (!(fr > P.guard && fr < 1.0f - P.guard && fl < (float)P.n_space_bins)) {
+                if (P.use_thr) {
+                    const unsigned thr = (unsigned)__cvta_generic_to_shared(S.s_thr);
+                    bs = bs < 0 ? 0 : bs;
+                    while (d2 < lds_d(thr + 8u * bs)) --bs;
+                    while (d2 >= lds_d(thr + 8u * bs + 8u)) ++bs;
+                } else {
+                    bs = __double2int_rz(__dmul_rn(__dsqrt_rn(d2), P.inv_ws));
                 }
             }
+            const int bt = __double2int_rz(__dmul_rn(lag_t, P.inv_wt));
+            if ((unsigned)bs < (unsigned)P.n_space_bins && (unsigned)bt < (unsigned)P.n_time_bins) {
+                double val;
+                if (MODE == 0) {
+                    const double a = __dsub_rn(itv.y, jtv.y);
+                    val = __dmul_rn(a, a);
+                } else {
+                    val = __dmul_rn(__dsub_rn(itv.y, P.mean), __dsub_rn(jtv.y, P.mean));
+                }
+                const int bin = bs * P.n_time_bins + bt;
+                atomicAdd(&S.g_sum[bin], val);
+                atomicAdd(&S.s_cnt[bin], 1u);
+            }
         }
     }
-    const int cnt = (int)((qa - qbase) / (2 * VT));
-    drain(S, P, tid, cnt, nst, true);
-    npass += cnt;
-    return npass;
+    return inside;
 }
 
+// Queue entry = (j >> 1) | owner lane << 7 | m << 12, m = the 8-bit set of pending pairs between
+// the owner's 4 i-points (rows r of the i-tile) and the j-points 2(j>>1), 2(j>>1)+1: bit 4h + r.
+// A batch of 32 entries bins the lowest pending pair of each entry with all lanes active;
+// entries with pairs left are re-queued at the tail (ballot compaction),
+// so every batch but an item's last is full whatever the hit density.  The queue is circular:
+// a batch frees 32 slots before it appends at most 32.
+template <int MODE>
+__device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned sbase, unsigned wq_addr, int warp_base,
+                                      int lane, unsigned lt, unsigned &head, unsigned &tail,
+                                      unsigned &npass, bool flush)
+{
+    while (tail - head >= 32u || (flush && tail != head)) {
+        __syncwarp();
+        const unsigned nv = min(tail - head, 32u);
+        const bool have = (unsigned)lane < nv;
+        unsigned e;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + (((head + lane) & (QW - 1)) << 2)) : "memory");
+        const unsigned m = e >> 12;
+        const unsigned b = (unsigned)__ffs((int)m) - 1u;  // lowest pending pair: row b & 3, j parity b >> 2
+        npass += bin_pair<MODE>(S, P, sbase, ((e & 0x7fu) << 1) | ((b >> 2) & 1u),
+                                (b & 3u) * VT + warp_base + ((e >> 7) & 31u), have) ? 1u : 0u;
+        const unsigned m2 = m & (m - 1u);
+        const bool left = have && m2 != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, left);
+        __syncwarp();
+        if (left)
+            st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2),
+                          (e & 0xfffu) | (m2 << 12));
+        head += nv;
+        tail += __popc(bal);
+    }
+    __syncwarp();
+}
+
+// Float pre-filter of 4 i-points x VG j-points per thread; pairs it cannot rule out are queued.
+//   DIAG: the sub-tile overlaps the i-tile, keep only j > i.   TCHK: the time test is needed
+//   (false when the whole item is provably inside the time window).
+template <bool DIAG, bool TCHK>
+__device__ __forceinline__ void sweep(const Smem &S, const float (&xf)[VR], const float (&yf)[VR],
+                                      const float (&tf)[VR], const int (&ioff)[VR], float thi,
+                                      float tmaxf, int jb, unsigned wq_addr, unsigned lt,
+                                      unsigned tag, unsigned &tail)
+{
+#pragma unroll
+    for (int g = 0; g < VG; g += 2) {
+        const int j = jb + g;  // even
+        unsigned m = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 pj = S.s_jf[j + h];
+#pragma unroll
+            for (int r = 0; r < VR; ++r) {
+                const float dx = __fsub_rn(xf[r], pj.x);
+                const float dy = __fsub_rn(yf[r], pj.y);
+                const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                // negated comparisons: a NaN (float overflow of absurd coordinates) is kept
+                // and decided exactly in the drain
+                bool p = !(d2 > thi);
+                if (TCHK) p = p && !(fabsf(__fsub_rn(tf[r], pj.z)) > tmaxf);
+                if (DIAG) p = p && (j + h > ioff[r]);
+                m |= p ? (1u << (4 * h + r)) : 0u;
+            }
+        }
+        const bool any = m != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, any);
+        if (any)
+            st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2),
+                          tag | (m << 12) | (unsigned)(j >> 1));
+        tail += __popc(bal);
+    }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem S;
-    S.s_i = reinterpret_cast<double4 *>(smem_raw);
-    S.s_j = S.s_i + TI;
-    S.q = reinterpret_cast<unsigned short *>(S.s_j + TJ);
-    S.s_thr = reinterpret_cast<double *>(S.q + QCAP * VT);
+    S.s_ixy = reinterpret_cast<double2 *>(smem_raw);
+    S.s_itv = S.s_ixy + TI;
+    S.s_jxy = S.s_itv + TI;
+    S.s_jtv = S.s_jxy + TJ;
+    S.s_jf = reinterpret_cast<float4 *>(S.s_jtv + TJ);
+    S.q = reinterpret_cast<unsigned *>(S.s_jf + TJ);
+    S.s_thr = reinterpret_cast<double *>(S.q + (VT / 32) * QW);
     S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
-    S.stg = S.s_cnt + P.n_bins;
 
-    const int tid = threadIdx.x;
-    for (int b = tid; b < P.n_bins; b += VT) {
-        S.s_cnt[b] = 0u;
-    }
+    const int tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
+    for (int b = tid; b < P.n_bins; b += VT) S.s_cnt[b] = 0u;
     for (int b = tid; b < P.n_space_bins + 2; b += VT) S.s_thr[b] = P.thr[b];
     unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
     double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
@@ -332,12 +417,22 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
         my_sum[b] = 0.0;
     }
     S.g_sum = my_sum;
+    const FilterConst F = *P.filter;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned wq_addr = (unsigned)__cvta_generic_to_shared(S.q + (tid >> 5) * QW);
+    const unsigned lt = (1u << lane) - 1u, tag = (unsigned)lane << 7;
 
     const long long M = P.item_prefix[P.nI];  // total items
-    unsigned long long npass = 0;
+    unsigned long long npass_total = 0;
     unsigned items_done = 0, items_total = 0;
-    // this partition owns items w with w % nparts == part; block b takes every grid-th
-    for (long long k = blockIdx.x;; k += gridDim.x) {
+    // This partition owns items w with w % nparts == part.  A block starts with item blockIdx.x
+    // and then takes the next unclaimed one (stats[0] counts the claims beyond the first round):
+    // items differ in cost (diagonal, edge of the time window) and a static round-robin leaves
+    // ceil(M/grid) - M/grid of an item's time idle (12 % at C2 with 8.02 items per block).
+    // Which block bins which item only changes the order of the FP64 sums, which the atomics
+    // leave open anyway; the counts are exact.
+    __shared__ long long s_next;
+    for (long long k = blockIdx.x;;) {
         const long long w = k * P.nparts + P.part;
         if (w >= M) break;
         // item -> (I, J): largest I with prefix[I] <= w
@@ -352,17 +447,53 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
         __syncthreads();  // previous item finished with the tiles
         const double4 *gi = P.pts + (size_t)I * TI;
         const double4 *gj = P.pts + (size_t)J * TJ;
+        float xf[VR], yf[VR], tf[VR];
+        int ioff[VR];
 #pragma unroll
-        for (int r = 0; r < VR; ++r) S.s_i[r * VT + tid] = gi[r * VT + tid];
-        S.s_j[tid] = gj[tid];
+        for (int r = 0; r < VR; ++r) {
+            const double4 p = gi[r * VT + tid];
+            S.s_ixy[r * VT + tid] = make_double2(p.x, p.y);
+            S.s_itv[r * VT + tid] = make_double2(p.z, p.w);
+            xf[r] = __double2float_rn(__dsub_rn(p.x, F.cx));
+            yf[r] = __double2float_rn(__dsub_rn(p.y, F.cy));
+            tf[r] = __double2float_rn(__dsub_rn(p.z, F.ct));
+            ioff[r] = (I * TI + tid) - J * TJ + r * VT;  // (global i) - (global j of sub-tile start)
+        }
+        {
+            const double4 p = gj[tid];
+            S.s_jxy[tid] = make_double2(p.x, p.y);
+            S.s_jtv[tid] = make_double2(p.z, p.w);
+            S.s_jf[tid] = make_float4(__double2float_rn(__dsub_rn(p.x, F.cx)),
+                                      __double2float_rn(__dsub_rn(p.y, F.cy)),
+                                      __double2float_rn(__dsub_rn(p.z, F.ct)), 0.0f);
+        }
+        if (tid == 0) s_next = (long long)gridDim.x + (long long)atomicAdd(&P.stats[0], 1ull);
         __syncthreads();
 
-        const int ioff0 = (I * TI + tid) - J * TJ;
+        // 0: diagonal item; 1: time test needed; 2: the whole item is inside the time window
+        // (observations are time-sorted and j > i: every lag is in [0, rn(t_lastJ - t_firstI)],
+        // rounding is monotone)
+        int variant = 1;
         if (J < I * JPI + JPI)
-            npass += scan_item<true>(S, P, tid, ioff0);
-        else
-            npass += scan_item<false>(S, P, tid, ioff0);
+            variant = 0;
+        else if (P.sorted && __dsub_rn(S.s_jtv[TJ - 1].x, S.s_itv[0].x) <= P.tmax)
+            variant = 2;
 
+        unsigned head = 0, tail = 0, npass = 0;
+        for (int jb = 0; jb < TJ; jb += VG) {
+            if (tail - head > (unsigned)(QW - VG * 32))
+                drain<MODE>(S, P, sbase, wq_addr, warp_base, lane, lt, head, tail, npass, false);
+            if (variant == 2)
+                sweep<false, false>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
+            else if (variant == 1)
+                sweep<false, true>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
+            else
+                sweep<true, true>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
+        }
+        drain<MODE>(S, P, sbase, wq_addr, warp_base, lane, lt, head, tail, npass, true);
+        npass_total += npass;
+
+        k = s_next;  // written before this item's second barrier
         ++items_total;
         if (++items_done == FLUSH_ITEMS) {
             __syncthreads();
@@ -377,11 +508,13 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
     for (int b = tid; b < P.n_bins; b += VT) {
         my_cnt[b] += S.s_cnt[b];
     }
-    // stats: passing pairs (warp reduce, one atomic per warp)
-    for (int off = 16; off > 0; off >>= 1) npass += __shfl_xor_sync(0xffffffffu, npass, off);
-    if ((tid & 31) == 0 && npass) atomicAdd(&P.stats[2], npass);
+    // stats: pairs inside the window (warp reduce, one atomic per warp)
+    for (int off = 16; off > 0; off >>= 1)
+        npass_total += __shfl_xor_sync(0xffffffffu, npass_total, off);
+    if (lane == 0 && npass_total) atomicAdd(&P.stats[2], npass_total);
     if (tid == 0 && items_total) atomicAdd(&P.stats[3], (unsigned long long)items_total);
 }
+
 
 // Fixed-order reduction over the per-block partials + the reference's peeled first pair.
 __global__ void reduce_kernel(Params P, int nblocks, const double *x, const double *y,
@@ -648,8 +781,9 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     const int n_bins = ns * nt;
     const bool cull = !(flags & STIF_VARIO_NO_CULL);
 
-    STIF_TRY(c->v_stats.reserve(4 * sizeof(unsigned long long)));
-    STIF_CUDA(cudaMemsetAsync(c->v_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    // [0..3] counters, [4..9] bounding box (gather_kernel), then the FilterConst
+    STIF_TRY(c->v_stats.reserve(10 * sizeof(unsigned long long) + sizeof(FilterConst)));
+    STIF_CUDA(cudaMemsetAsync(c->v_stats.p, 0, 10 * sizeof(unsigned long long), st));
     STIF_CUDA(cudaEventRecord(c->ev[0], st));
     c->n_phase = 3;
 
@@ -691,8 +825,11 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     }
     // 2. gather into sorted, padded AoS
     STIF_TRY(c->v_pts.reserve(sizeof(double4) * n_pad));
+    unsigned long long *ext = c->v_stats.as<unsigned long long>() + 4;
+    FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 6);
     gather_kernel<<<(unsigned)((n_pad + tb - 1) / tb), tb, 0, st>>>(x, y, t, v, order, n, n_pad,
-                                                                    c->v_pts.as<double4>());
+                                                                    c->v_pts.as<double4>(), ext);
+    filter_setup_kernel<<<1, 1, 0, st>>>(ext, smax, tmax, filter);
     // 3. work list
     STIF_TRY(c->v_tileinfo.reserve(sizeof(int) * (3 * (size_t)nI + 1)));
     int *count = c->v_tileinfo.as<int>();
@@ -724,7 +861,11 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     P.mean = mean;
     P.stats = c->v_stats.as<unsigned long long>();
     P.inv_ws_f = (float)P.inv_ws;
+    P.guard = (float)ns * 1.9073486328125e-06f;  // 2^-19 * ns (ns <= 8192: < 0.016)
+    P.sorted = cull ? 1 : 0;
+    P.filter = filter;
     P.use_thr = (P.inv_ws > 0.0 && isfinite(P.inv_ws) && isfinite((double)P.inv_ws_f)) ? 1 : 0;
+    if (!P.use_thr) P.guard = 2.0f;  // no pair trusts the float guess
     {
         // context-owned host copy: stays valid until the next call, so no synchronisation
         std::vector<double> &thr = c->v_thr_host;
@@ -736,13 +877,14 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         P.thr = c->v_thr.as<double>();
     }
 
-    const size_t smem = sizeof(double4) * (TI + TJ) + sizeof(unsigned short) * QCAP * VT +
-                        sizeof(unsigned) * (size_t)n_bins +
-                        sizeof(double) * ((size_t)ns + 2) + sizeof(unsigned) * 64 * (VT / 32);
-    STIF_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    void (*kern)(Params) = mode == 0 ? pair_kernel<0> : pair_kernel<1>;
+    const size_t smem = sizeof(double4) * (TI + TJ) + sizeof(float4) * TJ +
+                        sizeof(unsigned) * QW * (VT / 32) + sizeof(unsigned) * (size_t)n_bins +
+                        sizeof(double) * ((size_t)ns + 2);
+    STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     int occ = 0;
-    STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel, VT, smem));
+    STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, VT, smem));
     if (occ < 1) {
         set_error("stif_variogram: pair kernel does not fit (smem %zu B)", smem);
         return STIF_ECUDA;
@@ -752,7 +894,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
                                   n_bins));
     P.partial_sum = c->v_partial.as<double>();
     P.partial_cnt = reinterpret_cast<unsigned long long *>(P.partial_sum + (size_t)grid * n_bins);
-    pair_kernel<<<grid, VT, smem, st>>>(P);
+    kern<<<grid, VT, smem, st>>>(P);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[2], st));
 

@@ -10,16 +10,19 @@
 //
 // Pipeline (all on one stream, no host synchronisation):
 //   1. pack time keys, radix-sort observation indices by time (CUB; plumbing)
-//   2. gather into a time-sorted AoS double4 {x,y,t,v} array, NaN-padded to a tile multiple
+//   2. gather into a time-sorted AoS double4 {x,y,t,v} array, NaN-padded to a tile multiple;
+//      bounding box of (x,y,t) -> constants of the float pre-filter (filter_setup_kernel)
 //   3. per i-tile (1024 obs) find the last j-sub-tile (256 obs) that can still be inside
 //      the time window -> work list of (i-tile, j-sub-tile) items; every other tile pair
 //      is provably outside |dt| <= tmax and is never visited ("culling")
-//   4. persistent pair kernel: grid = SMs x resident CTAs; block b takes items
-//      b, b+grid, ... of its partition (static, deterministic).  Per item each thread
-//      keeps 4 i-points in registers and sweeps the 256 j-points broadcast from shared
-//      memory: 7 FP64-pipe instructions per pair.  Pairs inside the window are pushed to
-//      a per-thread shared-memory queue (2 predicated instructions, no branch) and binned
-//      later in a dense drain loop with shared-memory histogram atomics.
+//   4. persistent pair kernel: grid = SMs x resident CTAs; a block starts with item
+//      blockIdx.x of its partition and then claims the next unclaimed one.  Per item each
+//      thread keeps 4 i-points in registers AS CENTRED FLOATS and sweeps the 256 j-points
+//      broadcast from shared memory through a float pre-filter with a rigorous error band
+//      (no false negatives; 5-7 FP32 instructions per pair).  Pairs it cannot rule out are
+//      appended (ballot compaction, 8-pair mask entries) to the warp's circular queue and
+//      binned in dense batches of 32 with the reference's exact FP64 arithmetic: cut-off
+//      tests, bins, shared-memory count atomics, global (L2) f64 sum atomics.
 //   5. deterministic fixed-order reduction of the per-block partial histograms.
 #include "common.cuh"
 

@@ -77,6 +77,57 @@ def test_duplicates_and_edges(ctx):
     check(ctx, space, t, v, 10.0, 5, 7, 3)
 
 
+@pytest.mark.parametrize("offset", [0.0, 5.4e6, -3.3e9, 1e15])
+def test_float_prefilter_large_offsets(ctx, offset):
+    """The sweep's float pre-filter centres the coordinates and keeps every pair within its
+    error bound of the cut-offs; pairs are decided in FP64.  Large common offsets (UTM-like
+    metres, 1e15) leave few or no float bits for the differences: counts must stay bit-exact.
+    Lattice spacing 1 with cut-offs on lattice distances puts many pairs exactly ON them."""
+    g = np.arange(48, dtype=np.float64)
+    xx, yy = np.meshgrid(g, g)
+    space = np.column_stack([xx.ravel() + offset, yy.ravel() - 2 * offset])
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 20, len(space)).astype(np.float64) + offset
+    v = rng.normal(size=len(space))
+    check(ctx, space, t, v, 5.0, 5.0, 5, 5)      # 3-4-5 triangles: lag == max, dropped
+    check(ctx, space, t, v, 13.0, 3.0, 13, 3)    # 5-12-13
+
+
+def test_float_prefilter_overflow_and_nan(ctx):
+    """Coordinates beyond the float range (the filter passes everything, the drain decides)
+    and NaN coordinates / times (never bin, as in the oracle)."""
+    rng = np.random.default_rng(6)
+    n = 3000
+    space = rng.uniform(0, 50, (n, 2))
+    t = rng.uniform(0, 30, n)
+    v = rng.normal(size=n)
+    space[::7, 0] *= 1e40
+    space[5::11, 1] = -1e300
+    t[3::13] = 1e200
+    check(ctx, space, t, v, 10.0, 5.0, 10, 5)
+    space[1::17, 0] = np.nan
+    t[2::19] = np.nan
+    x, y = _native.split_space(space)
+    counts, sums = ctx.variogram_host(x, y, t, v, 10.0, 5.0, 10, 5)
+    ok = np.isfinite(space).all(axis=1) & np.isfinite(t)
+    x2, y2 = _native.split_space(space[ok])
+    c2, s2 = ctx.variogram_host(x2, y2, t[ok], v[ok], 10.0, 5.0, 10, 5, flags=0)
+    c1, _ = ctx.variogram_host(x, y, t, v, 10.0, 5.0, 10, 5, flags=0)
+    assert np.array_equal(c1, c2)
+
+
+def test_float_prefilter_tiny_radius(ctx):
+    """Cut-offs far below the float resolution of the centred coordinates: the error bound
+    dominates the radius, the filter keeps a wide band, the result is still exact."""
+    rng = np.random.default_rng(8)
+    n = 5000
+    base = rng.integers(0, 40, (n, 2)).astype(np.float64) * 1e6
+    space = base + rng.uniform(0, 1e-3, (n, 2))
+    t = rng.integers(0, 3, n)
+    v = rng.normal(size=n)
+    check(ctx, space, t, v, 1e-3, 2, 8, 2)
+
+
 def test_unsorted_negative_times(ctx):
     rng = np.random.default_rng(11)
     n = 6000

@@ -193,11 +193,13 @@ class Context:
     def variogram_sampled_host(self, x, y, t, v, space_dist_max, time_dist_max, n_space_bins,
                                n_time_bins, n_samples, mode=0, mean=0.0, seed=None, seed_offset=0):
         """Sampled-pair branch (el_max).  seed=None draws a fresh seed (like the reference's
-        OS-seeded RNG); pass an int for a reproducible call."""
+        OS-seeded RNG) unless STIF_B200_SEED is set in the environment; pass an int (or set the
+        variable) for a reproducible call."""
         x, y, t, v = _f64(x), _f64(y), _f64(t), _f64(v)
         n = len(x)
         if seed is None:
-            seed = int.from_bytes(os.urandom(8), "little")
+            env = os.environ.get("STIF_B200_SEED")
+            seed = int(env) if env else int.from_bytes(os.urandom(8), "little")
         seed = (int(seed) + 0x9E3779B97F4A7C15 * int(seed_offset)) & 0xFFFFFFFFFFFFFFFF
         nb = int(n_space_bins) * int(n_time_bins)
         counts = np.zeros(max(nb, 0), dtype=np.uint64)

@@ -12,12 +12,12 @@
 //   1. pack time keys, radix-sort observation indices by time (CUB; plumbing)
 //   2. gather into a time-sorted AoS double4 {x,y,t,v} array, NaN-padded to a tile multiple;
 //      bounding box of (x,y,t) -> constants of the float pre-filter (filter_setup_kernel)
-//   3. per i-tile (1024 obs) find the last j-sub-tile (256 obs) that can still be inside
+//   3. per i-tile (512 obs) find the last j-sub-tile (256 obs) that can still be inside
 //      the time window -> work list of (i-tile, j-sub-tile) items; every other tile pair
 //      is provably outside |dt| <= tmax and is never visited ("culling")
 //   4. persistent pair kernel: grid = SMs x resident CTAs; a block starts with item
 //      blockIdx.x of its partition and then claims the next unclaimed one.  Per item each
-//      thread keeps 4 i-points in registers AS CENTRED FLOATS and sweeps the 256 j-points
+//      thread keeps 2 i-points in registers AS CENTRED FLOATS and sweeps the 256 j-points
 //      broadcast from shared memory through a float pre-filter with a rigorous error band
 //      (no false negatives; 5-7 FP32 instructions per pair).  Pairs it cannot rule out are
 //      appended (ballot compaction, 8-pair mask entries) to the warp's circular queue and
@@ -35,11 +35,14 @@ namespace stif {
 namespace vario {
 
 constexpr int VT = 256;        // threads per block
-constexpr int VR = 4;          // i-points per thread (registers)
-constexpr int TI = VT * VR;    // i-tile: 1024 observations
+constexpr int VR = 2;          // i-points per thread (registers)
+constexpr int TI = VT * VR;    // i-tile: 512 observations
 constexpr int TJ = 256;        // j-sub-tile: 256 observations
 constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
 constexpr int QW = 512;       // entries (uint32) of a warp's circular queue
+constexpr int JV = 8 / VR;     // j-points per queue entry (8 pair tests per lane and vote)
+constexpr int LVR = VR == 4 ? 2 : 1, LJV = 3 - LVR;
+constexpr int MINB = VR == 4 ? 3 : 4;  // resident CTAs per SM the kernel is compiled for
 constexpr int VG = 4;          // j-points between queue checks (each queues <= 32 entries)
 constexpr int MAX_BINS = 8192; // shared-memory histogram limit (12 B per bin)
 constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x 2^18 pairs < 2^32: u32 counts are safe
@@ -324,8 +327,8 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
     return inside;
 }
 
-// Queue entry = (j >> 1) | owner lane << 7 | m << 12, m = the 8-bit set of pending pairs between
-// the owner's 4 i-points (rows r of the i-tile) and the j-points 2(j>>1), 2(j>>1)+1: bit 4h + r.
+// Queue entry = (j / JV) | owner lane << 7 | m << 12, m = the 8-bit set of pending pairs between
+// the owner's VR i-points (rows r of the i-tile) and JV consecutive j-points: bit VR h + r.
 // A batch of 32 entries bins the lowest pending pair of each entry with all lanes active;
 // entries with pairs left are re-queued at the tail (ballot compaction),
 // so every batch but an item's last is full whatever the hit density.  The queue is circular:
@@ -342,9 +345,9 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned s
         unsigned e;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + (((head + lane) & (QW - 1)) << 2)) : "memory");
         const unsigned m = e >> 12;
-        const unsigned b = (unsigned)__ffs((int)m) - 1u;  // lowest pending pair: row b & 3, j parity b >> 2
-        npass += bin_pair<MODE>(S, P, sbase, ((e & 0x7fu) << 1) | ((b >> 2) & 1u),
-                                (b & 3u) * VT + warp_base + ((e >> 7) & 31u), have) ? 1u : 0u;
+        const unsigned b = (unsigned)__ffs((int)m) - 1u;  // lowest pending pair: row b % VR, j offset b / VR
+        npass += bin_pair<MODE>(S, P, sbase, ((e & 0x7fu) << LJV) | (b >> LVR),
+                                (b & (VR - 1)) * VT + warp_base + ((e >> 7) & 31u), have) ? 1u : 0u;
         const unsigned m2 = m & (m - 1u);
         const bool left = have && m2 != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, left);
@@ -358,7 +361,7 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned s
     __syncwarp();
 }
 
-// Float pre-filter of 4 i-points x VG j-points per thread; pairs it cannot rule out are queued.
+// Float pre-filter of VR i-points x VG j-points per thread; pairs it cannot rule out are queued.
 //   DIAG: the sub-tile overlaps the i-tile, keep only j > i.   TCHK: the time test is needed
 //   (false when the whole item is provably inside the time window).
 template <bool DIAG, bool TCHK>
@@ -368,11 +371,11 @@ __device__ __forceinline__ void sweep(const Smem &S, const float (&xf)[VR], cons
                                       unsigned tag, unsigned &tail)
 {
 #pragma unroll
-    for (int g = 0; g < VG; g += 2) {
-        const int j = jb + g;  // even
+    for (int g = 0; g < VG; g += JV) {
+        const int j = jb + g;  // multiple of JV
         unsigned m = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < JV; ++h) {
             const float4 pj = S.s_jf[j + h];
 #pragma unroll
             for (int r = 0; r < VR; ++r) {
@@ -384,20 +387,20 @@ __device__ __forceinline__ void sweep(const Smem &S, const float (&xf)[VR], cons
                 bool p = !(d2 > thi);
                 if (TCHK) p = p && !(fabsf(__fsub_rn(tf[r], pj.z)) > tmaxf);
                 if (DIAG) p = p && (j + h > ioff[r]);
-                m |= p ? (1u << (4 * h + r)) : 0u;
+                m |= p ? (1u << (VR * h + r)) : 0u;
             }
         }
         const bool any = m != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, any);
         if (any)
             st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2),
-                          tag | (m << 12) | (unsigned)(j >> 1));
+                          tag | (m << 12) | (unsigned)(j >> LJV));
         tail += __popc(bal);
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
+__global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem S;
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
             tf[r] = __double2float_rn(__dsub_rn(p.z, F.ct));
             ioff[r] = (I * TI + tid) - J * TJ + r * VT;  // (global i) - (global j of sub-tile start)
         }
-        {
+        if (TJ == VT || tid < TJ) {
             const double4 p = gj[tid];
             S.s_jxy[tid] = make_double2(p.x, p.y);
             S.s_jtv[tid] = make_double2(p.z, p.w);
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(VT, 3) pair_kernel(Params P)
 
         unsigned head = 0, tail = 0, npass = 0;
         for (int jb = 0; jb < TJ; jb += VG) {
-            if (tail - head > (unsigned)(QW - VG * 32))
+            if (tail - head > (unsigned)(QW - (VG / JV) * 32))
                 drain<MODE>(S, P, sbase, wq_addr, warp_base, lane, lt, head, tail, npass, false);
             if (variant == 2)
                 sweep<false, false>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);

@@ -9,7 +9,8 @@
 // monotone; found on the host); bins are trunc(sqrt_rn(d2)*(1/ws)), trunc(|dt|*(1/wt)).
 //
 // Pipeline (all on one stream, no host synchronisation):
-//   1. pack time keys, radix-sort observation indices by time (CUB; plumbing)
+//   1. pack time keys, radix-sort observation indices by the top 32 bits of the time key
+//      (CUB; plumbing)
 //   2. gather into a time-sorted AoS double4 {x,y,t,v} array, NaN-padded to a tile multiple;
 //      bounding box of (x,y,t) -> constants of the float pre-filter (filter_setup_kernel)
 //   3. per i-tile (512 obs) find the last j-sub-tile (256 obs) that can still be inside
@@ -171,9 +172,26 @@ __global__ void filter_setup_kernel(const unsigned long long *ext, double smax, 
     F->tmaxf = (isfinite(tm) && tm < 1e37) ? __double2float_ru(tm) : inf;
 }
 
+// The observations are radix-sorted by the TOP 32 BITS of the order-preserving time key only
+// (4 CUB passes instead of 8; the sort is launch-latency bound at 1e5 keys): positions p < q
+// satisfy coarse(t_p) <= coarse(t_q), and keys that share a coarse key (relative spacing 2^-20)
+// stay in input order.  Everything that reasons about a tile's time range therefore uses the
+// edges of the first / last element's coarse bucket, which bound every element of the tile.
+// Zero is special-cased (CUB may or may not sort -0.0 with +0.0).
+__device__ __forceinline__ double coarse_lo(double t)
+{
+    if (t == 0.0) return -2.2250738585072014e-308;
+    return ord_dec(ord_enc(t) & 0xffffffff00000000ull);
+}
+__device__ __forceinline__ double coarse_hi(double t)
+{
+    if (t == 0.0) return 2.2250738585072014e-308;
+    return ord_dec(ord_enc(t) | 0x00000000ffffffffull);   // NaN for the +inf bucket: never culled
+}
+
 // One thread per i-tile: last j-sub-tile that may hold a pair with rn(tj - ti) <= tmax.
-// Sorted ascending by t, so the smallest lag between i-tile I and sub-tile J (beyond the
-// diagonal) is rn(t[J*TJ] - t_last(I)), and rounding is monotone.
+// The smallest lag between i-tile I and sub-tile J (beyond the diagonal) is at least
+// rn(coarse_lo(t[J*TJ]) - coarse_hi(t_last(I))), and rounding is monotone.
 __global__ void tile_range_kernel(const double4 *pts, int64_t n, int nI, int nJ, double tmax,
                                   int cull, int *count, int *jbeg)
 {
@@ -184,12 +202,12 @@ __global__ void tile_range_kernel(const double4 *pts, int64_t n, int nI, int nJ,
     if (cull) {
         int64_t last = (int64_t)I * TI + TI - 1;
         if (last > n - 1) last = n - 1;
-        const double ti_max = pts[last].z;
+        const double ti_max = coarse_hi(pts[last].z);
         // first J in (jb+JPI-1, nJ) with lag > tmax; all later ones are also outside
         int lo = jb + JPI, hi = nJ;  // search in [lo, hi)
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            double lag = __dsub_rn(pts[(int64_t)mid * TJ].z, ti_max);
+            double lag = __dsub_rn(coarse_lo(pts[(int64_t)mid * TJ].z), ti_max);
             if (lag > tmax) hi = mid; else lo = mid + 1;
         }
         jend = lo - 1;
@@ -477,12 +495,14 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
         __syncthreads();
 
         // 0: diagonal item; 1: time test needed; 2: the whole item is inside the time window
-        // (observations are time-sorted and j > i: every lag is in [0, rn(t_lastJ - t_firstI)],
+        // (every t of a tile lies between the coarse-bucket edges of its first and last element;
         // rounding is monotone)
         int variant = 1;
         if (J < I * JPI + JPI)
             variant = 0;
-        else if (P.sorted && __dsub_rn(S.s_jtv[TJ - 1].x, S.s_itv[0].x) <= P.tmax)
+        else if (P.sorted &&
+                 __dsub_rn(coarse_hi(S.s_jtv[TJ - 1].x), coarse_lo(S.s_itv[0].x)) <= P.tmax &&
+                 __dsub_rn(coarse_hi(S.s_itv[TI - 1].x), coarse_lo(S.s_jtv[0].x)) <= P.tmax)
             variant = 2;
 
         unsigned head = 0, tail = 0, npass = 0;
@@ -818,12 +838,12 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         STIF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->v_keys.as<double>(),
                                                   c->v_keys_out.as<double>(),
                                                   c->v_idx.as<unsigned>(),
-                                                  c->v_idx_out.as<unsigned>(), (int)n, 0, 64, st));
+                                                  c->v_idx_out.as<unsigned>(), (int)n, 32, 64, st));
         STIF_TRY(c->v_cubtmp.reserve(tmp_bytes));
         STIF_CUDA(cub::DeviceRadixSort::SortPairs(c->v_cubtmp.p, tmp_bytes, c->v_keys.as<double>(),
                                                   c->v_keys_out.as<double>(),
                                                   c->v_idx.as<unsigned>(),
-                                                  c->v_idx_out.as<unsigned>(), (int)n, 0, 64, st));
+                                                  c->v_idx_out.as<unsigned>(), (int)n, 32, 64, st));
         order = c->v_idx_out.as<unsigned>();
     } else {
         iota_kernel<<<nb_n, tb, 0, st>>>(n, c->v_idx.as<unsigned>());

@@ -128,6 +128,25 @@ def test_float_prefilter_tiny_radius(ctx):
     check(ctx, space, t, v, 1e-3, 2, 8, 2)
 
 
+@pytest.mark.parametrize("t0,span,tmax", [(1.7e9, 40000.0, 700.0), (-3.0e5, 900.0, 0.05), (0.0, 1e-300, 1e-301)])
+def test_coarse_time_sort(ctx, t0, span, tmax):
+    """The observations are sorted by the top 32 bits of the time key only; tiles are bounded
+    by coarse-bucket edges.  Times whose differences live far below that resolution (unix
+    seconds with a minutes window, a sub-resolution window, a window at 1e-301) and more than
+    one i-tile: culling and the skipped time test must not lose or add a pair."""
+    rng = np.random.default_rng(17)
+    n = 5000
+    space = rng.uniform(0, 20, (n, 2))
+    t = t0 + rng.uniform(0, span, n)
+    t[::97] = t0            # exact ties, and for t0 = 0 a mix of +0.0 and -0.0
+    t[5::193] = -t[5::193] if t0 == 0.0 else t[5::193]
+    if t0 == 0.0:
+        t[::194] = -0.0
+    v = rng.normal(size=n)
+    counts, _ = check(ctx, space, t, v, 8.0, tmax, 8, 6)
+    assert counts.sum() > 0
+
+
 def test_unsorted_negative_times(ctx):
     rng = np.random.default_rng(11)
     n = 6000

@@ -41,10 +41,14 @@ constexpr int TI = VT * VR;    // i-tile: 512 observations
 constexpr int TJ = 256;        // j-sub-tile: 256 observations
 constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
 constexpr int QW = 512;       // entries (uint32) of a warp's circular queue
-constexpr int JV = 8 / VR;     // j-points per queue entry (8 pair tests per lane and vote)
-constexpr int LVR = VR == 4 ? 2 : 1, LJV = 3 - LVR;
+#ifndef STIF_VARIO_NB
+#define STIF_VARIO_NB 8
+#endif
+constexpr int NB = STIF_VARIO_NB;  // pair tests per lane and vote = bits of a queue entry's mask
+constexpr int JV = NB / VR;    // j-points per queue entry
+constexpr int LVR = VR == 4 ? 2 : 1, LJV = (NB == 16 ? 4 : 3) - LVR;
 constexpr int MINB = VR == 4 ? 3 : 4;  // resident CTAs per SM the kernel is compiled for
-constexpr int VG = 4;          // j-points between queue checks (each queues <= 32 entries)
+constexpr int VG = JV > 4 ? JV : 4;  // j-points between queue checks
 constexpr int MAX_BINS = 8192; // shared-memory histogram limit (12 B per bin)
 constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x 2^18 pairs < 2^32: u32 counts are safe
 

@@ -330,7 +330,10 @@ def run_b200(args):
             "timing": "per-step CUDA events on torch's current stream, summed; max over ranks",
             "parallelism": f"tile-pair partition x{world}",
         },
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 6 * args.steps,
+        "clocks": clocks, "e2e": e2e,
+        # own kernels per step: pack_keys, gather, filter_setup, tile_range, scan, pair, reduce
+        # (the CUB radix-sort passes in between are library launches and not counted)
+        "gpu_launches": 7 * args.steps,
         "roofline": roofline, "wall_s_bracket": wall_bracket,
     }
 

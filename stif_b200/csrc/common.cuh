@@ -77,6 +77,8 @@ struct stif_ctx {
     int n_phase = 0;                    // number of valid phases recorded in the last call
     cudaStream_t last_stream = nullptr; // stream the last call was enqueued on
     cudaStream_t stream2 = nullptr;     // copy stream of the chunked host pipeline
+    cudaEvent_t v_upload_ev = nullptr;  // variogram host call: x, y, v uploaded (stream2)
+    bool v_wait_upload = false;         // stif_variogram_dev waits for it before the gather
     cudaEvent_t *ev_override = nullptr; // phase events of the chunk being enqueued (pipeline)
     bool keep_stats = false;            // pipeline: accumulate the statistics over the chunks
     std::vector<cudaEvent_t> chunk_ev;  // 4 phase events per chunk of the last pipelined call

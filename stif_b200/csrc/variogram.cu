@@ -857,6 +857,10 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     STIF_TRY(c->v_pts.reserve(sizeof(double4) * n_pad));
     unsigned long long *ext = c->v_stats.as<unsigned long long>() + 4;
     FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 6);
+    if (c->v_wait_upload) {   // host entry point: x, y, v arrive on the copy stream under the sort
+        STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_ev, 0));
+        c->v_wait_upload = false;
+    }
     gather_kernel<<<(unsigned)((n_pad + tb - 1) / tb), tb, 0, st>>>(x, y, t, v, order, n, n_pad,
                                                                     c->v_pts.as<double4>(), ext);
     filter_setup_kernel<<<1, 1, 0, st>>>(ext, smax, tmax, filter);
@@ -986,13 +990,28 @@ extern "C" int stif_variogram_host(stif_ctx *c, const double *x, const double *y
     double *ds = (double *)(base + out_off + nb * 8);
     cudaStream_t st = c->stream;
     if (n > 0) {
-        STIF_CUDA(cudaMemcpyAsync(dx, x, in_bytes, cudaMemcpyHostToDevice, st));
-        STIF_CUDA(cudaMemcpyAsync(dy, y, in_bytes, cudaMemcpyHostToDevice, st));
+        // the time sort needs t only: x, y, v travel on the copy stream underneath it and the
+        // gather waits for them (an event); the previous call's kernels are done with the
+        // staging buffers because every host call ends with a stream synchronisation
+        if (!c->stream2) STIF_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        if (!c->v_upload_ev) STIF_CUDA(cudaEventCreateWithFlags(&c->v_upload_ev, cudaEventDisableTiming));
         STIF_CUDA(cudaMemcpyAsync(dt, t, in_bytes, cudaMemcpyHostToDevice, st));
-        STIF_CUDA(cudaMemcpyAsync(dv, v, in_bytes, cudaMemcpyHostToDevice, st));
+        STIF_CUDA(cudaMemcpyAsync(dx, x, in_bytes, cudaMemcpyHostToDevice, c->stream2));
+        STIF_CUDA(cudaMemcpyAsync(dy, y, in_bytes, cudaMemcpyHostToDevice, c->stream2));
+        STIF_CUDA(cudaMemcpyAsync(dv, v, in_bytes, cudaMemcpyHostToDevice, c->stream2));
+        STIF_CUDA(cudaEventRecord(c->v_upload_ev, c->stream2));
+        c->v_wait_upload = true;
     }
-    STIF_TRY(stif_variogram_dev(c, dx, dy, dt, dv, n, smax, tmax, ns, nt, mode, mean, flags, part,
-                                nparts, dc, ds, st));
+    const int rc = stif_variogram_dev(c, dx, dy, dt, dv, n, smax, tmax, ns, nt, mode, mean, flags,
+                                      part, nparts, dc, ds, st);
+    if (c->v_wait_upload) {   // early return before the gather: still join the copy stream
+        c->v_wait_upload = false;
+        STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_ev, 0));
+    }
+    if (rc != STIF_OK) {
+        cudaStreamSynchronize(st);   // the caller may free its arrays
+        return rc;
+    }
     STIF_CUDA(cudaMemcpyAsync(counts_host, dc, nb * 8, cudaMemcpyDeviceToHost, st));
     STIF_CUDA(cudaMemcpyAsync(sums_host, ds, nb * 8, cudaMemcpyDeviceToHost, st));
     STIF_CUDA(cudaStreamSynchronize(st));

@@ -192,6 +192,27 @@ def test_stats_and_culling(ctx):
     assert st_cull["pairs_evaluated"] < st_all["pairs_evaluated"]
 
 
+@pytest.mark.parametrize("ns,nt", [(8192, 1), (1, 8192), (90, 91), (1000, 8)])
+def test_many_bins(ctx, ns, nt):
+    """Bin grids up to the 8192-bin limit: shared-memory sizing of the pair kernel, the float
+    guard of the space-bin lookup at its widest (2^-19 * 8192), thresholds for 8192 bins."""
+    space, t, v = synth(3000, seed=41, int_time=False)
+    counts, _ = check(ctx, space, t, v, 35.0, 40.0, ns, nt)
+    assert counts.sum() > 0
+
+
+@pytest.mark.parametrize("smax", [1e-310, 5e-324, 1e308])
+def test_degenerate_bin_widths(ctx, smax):
+    """Space cut-offs whose bin width or its reciprocal leaves the float / double range: the
+    kernel falls back to the reference's expression per binned pair (no threshold table)."""
+    rng = np.random.default_rng(43)
+    n = 1500
+    space = rng.integers(0, 3, (n, 2)).astype(np.float64) * (smax if smax < 1 else 1.0)
+    t = rng.integers(0, 5, n)
+    v = rng.normal(size=n)
+    check(ctx, space, t, v, smax, 3, 4, 3)
+
+
 def test_bad_arguments(ctx):
     z = np.zeros(4)
     with pytest.raises(ValueError):

@@ -40,7 +40,7 @@ constexpr int VR = 2;          // i-points per thread (registers)
 constexpr int TI = VT * VR;    // i-tile: 512 observations
 constexpr int TJ = 256;        // j-sub-tile: 256 observations
 constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
-constexpr int QW = 512;       // entries (uint32) of a warp's circular queue
+constexpr int QW = 512;        // entries (uint32) of a warp's circular queue
 #ifndef STIF_VARIO_NB
 #define STIF_VARIO_NB 8
 #endif
@@ -49,8 +49,8 @@ constexpr int JV = NB / VR;    // j-points per queue entry
 constexpr int LVR = VR == 4 ? 2 : 1, LJV = (NB == 16 ? 4 : 3) - LVR;
 constexpr int MINB = VR == 4 ? 3 : 4;  // resident CTAs per SM the kernel is compiled for
 constexpr int VG = JV > 4 ? JV : 4;  // j-points between queue checks
-constexpr int MAX_BINS = 8192; // shared-memory histogram limit (12 B per bin)
-constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x 2^18 pairs < 2^32: u32 counts are safe
+constexpr int MAX_BINS = 8192; // histogram limit (4 B of shared memory per bin)
+constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x TI*TJ (<= 2^18) pairs < 2^32: u32 counts are safe
 
 // Constants of the float pre-filter, written by filter_setup_kernel.
 struct FilterConst {
@@ -73,7 +73,8 @@ struct Params {
     double mean;
     double *partial_sum;           // [grid][n_bins]
     unsigned long long *partial_cnt;  // [grid][n_bins]
-    unsigned long long *stats;     // [4]
+    unsigned long long *stats;     // [0] items claimed beyond the first round, [2] pairs inside
+                                   // the window, [3] items visited
     const double *thr;    // [n_space_bins + 2] d2 thresholds: bin b <=> thr[b] <= d2 < thr[b+1]
     int use_thr;          // 0: evaluate sqrt/mul/trunc per binned pair (degenerate widths)
     float inv_ws_f;       // float copy of inv_ws for the first guess

@@ -135,11 +135,12 @@ __global__ void gather_kernel(const double *x, const double *y, const double *t,
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        unsigned long long m = e[c];
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
-            m = o > m ? o : m;
-        }
+        // warp maximum of a 64-bit key with two 32-bit REDUX: high words, then the low words
+        // of the lanes that hold the maximal high word
+        const unsigned hi = (unsigned)(e[c] >> 32), lo = (unsigned)e[c];
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const unsigned long long m = ((unsigned long long)mh << 32) | ml;
         if ((threadIdx.x & 31) == 0 && m) atomicMax(&ext[c], m);
     }
 }

@@ -258,7 +258,7 @@ struct Smem {
     // 16-byte bank groups (a 32-byte AoS stride uses only four: 2-way conflicts at best)
     double2 *s_ixy, *s_itv;  // [TI] {x,y}, {t,v}
     double2 *s_jxy, *s_jtv;  // [TJ]
-    float4 *s_jf;            // [TJ] {x-cx, y-cy, t-ct, 0} in float: the sweep's copy
+    float *s_jf;             // [3][TJ] x-cx, y-cy, t-ct in float (SoA): the sweep's copy
     unsigned *q;             // [VT/32][QW] one circular queue per warp
     unsigned *s_cnt;         // [n_bins]
     double *s_thr;           // [n_space_bins + 2]
@@ -385,12 +385,46 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned s
     __syncwarp();
 }
 
+// Blackwell's packed single-precision instructions (FADD2 / FMUL2 / FFMA2: two IEEE round-to-
+// nearest FP32 operations per lane and issue slot).  The sweep is issue-bound, so it tests two
+// j-points per instruction: the operands are {j, j+1} pairs straight out of the SoA j-tile and
+// the thread's i-point duplicated into both halves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // Float pre-filter of VR i-points x VG j-points per thread; pairs it cannot rule out are queued.
 //   DIAG: the sub-tile overlaps the i-tile, keep only j > i.   TCHK: the time test is needed
 //   (false when the whole item is provably inside the time window).
 template <bool DIAG, bool TCHK>
-__device__ __forceinline__ void sweep(const Smem &S, const float (&xf)[VR], const float (&yf)[VR],
-                                      const float (&tf)[VR], const int (&ioff)[VR], float thi,
+__device__ __forceinline__ void sweep(const Smem &S, const f32x2 (&xf)[VR], const f32x2 (&yf)[VR],
+                                      const f32x2 (&tf)[VR], const int (&ioff)[VR], float thi,
                                       float tmaxf, int jb, unsigned wq_addr, unsigned lt,
                                       unsigned tag, unsigned &tail)
 {
@@ -399,19 +433,36 @@ __device__ __forceinline__ void sweep(const Smem &S, const float (&xf)[VR], cons
         const int j = jb + g;  // multiple of JV
         unsigned m = 0;
 #pragma unroll
-        for (int h = 0; h < JV; ++h) {
-            const float4 pj = S.s_jf[j + h];
+        for (int h = 0; h < JV; h += 2) {
+            // {j+h, j+h+1}: 8-byte aligned pairs of the SoA rows, the same for every lane
+            const float2 jx = *reinterpret_cast<const float2 *>(S.s_jf + j + h);
+            const float2 jy = *reinterpret_cast<const float2 *>(S.s_jf + TJ + j + h);
+            const f32x2 jx2 = pack2(jx.x, jx.y), jy2 = pack2(jy.x, jy.y);
+            f32x2 jt2 = 0;
+            if (TCHK) {
+                const float2 jt = *reinterpret_cast<const float2 *>(S.s_jf + 2 * TJ + j + h);
+                jt2 = pack2(jt.x, jt.y);
+            }
 #pragma unroll
             for (int r = 0; r < VR; ++r) {
-                const float dx = __fsub_rn(xf[r], pj.x);
-                const float dy = __fsub_rn(yf[r], pj.y);
-                const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                const f32x2 dx = sub2(xf[r], jx2), dy = sub2(yf[r], jy2);
+                float d2a, d2b;
+                unpack2(fma2(dy, dy, mul2(dx, dx)), d2a, d2b);
                 // negated comparisons: a NaN (float overflow of absurd coordinates) is kept
                 // and decided exactly in the drain
-                bool p = !(d2 > thi);
-                if (TCHK) p = p && !(fabsf(__fsub_rn(tf[r], pj.z)) > tmaxf);
-                if (DIAG) p = p && (j + h > ioff[r]);
-                m |= p ? (1u << (VR * h + r)) : 0u;
+                bool pa = !(d2a > thi), pb = !(d2b > thi);
+                if (TCHK) {
+                    float dta, dtb;
+                    unpack2(sub2(tf[r], jt2), dta, dtb);
+                    pa = pa && !(fabsf(dta) > tmaxf);
+                    pb = pb && !(fabsf(dtb) > tmaxf);
+                }
+                if (DIAG) {
+                    pa = pa && (j + h > ioff[r]);
+                    pb = pb && (j + h + 1 > ioff[r]);
+                }
+                m |= pa ? (1u << (VR * h + r)) : 0u;
+                m |= pb ? (1u << (VR * (h + 1) + r)) : 0u;
             }
         }
         const bool any = m != 0u;
@@ -432,8 +483,8 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
     S.s_itv = S.s_ixy + TI;
     S.s_jxy = S.s_itv + TI;
     S.s_jtv = S.s_jxy + TJ;
-    S.s_jf = reinterpret_cast<float4 *>(S.s_jtv + TJ);
-    S.q = reinterpret_cast<unsigned *>(S.s_jf + TJ);
+    S.s_jf = reinterpret_cast<float *>(S.s_jtv + TJ);
+    S.q = reinterpret_cast<unsigned *>(S.s_jf + 4 * TJ);
     S.s_thr = reinterpret_cast<double *>(S.q + (VT / 32) * QW);
     S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
 
@@ -477,25 +528,28 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
         __syncthreads();  // previous item finished with the tiles
         const double4 *gi = P.pts + (size_t)I * TI;
         const double4 *gj = P.pts + (size_t)J * TJ;
-        float xf[VR], yf[VR], tf[VR];
+        f32x2 xf[VR], yf[VR], tf[VR];   // the i-points as centred floats, duplicated into both halves
         int ioff[VR];
 #pragma unroll
         for (int r = 0; r < VR; ++r) {
             const double4 p = gi[r * VT + tid];
             S.s_ixy[r * VT + tid] = make_double2(p.x, p.y);
             S.s_itv[r * VT + tid] = make_double2(p.z, p.w);
-            xf[r] = __double2float_rn(__dsub_rn(p.x, F.cx));
-            yf[r] = __double2float_rn(__dsub_rn(p.y, F.cy));
-            tf[r] = __double2float_rn(__dsub_rn(p.z, F.ct));
+            const float fx = __double2float_rn(__dsub_rn(p.x, F.cx));
+            const float fy = __double2float_rn(__dsub_rn(p.y, F.cy));
+            const float ft = __double2float_rn(__dsub_rn(p.z, F.ct));
+            xf[r] = pack2(fx, fx);
+            yf[r] = pack2(fy, fy);
+            tf[r] = pack2(ft, ft);
             ioff[r] = (I * TI + tid) - J * TJ + r * VT;  // (global i) - (global j of sub-tile start)
         }
         if (TJ == VT || tid < TJ) {
             const double4 p = gj[tid];
             S.s_jxy[tid] = make_double2(p.x, p.y);
             S.s_jtv[tid] = make_double2(p.z, p.w);
-            S.s_jf[tid] = make_float4(__double2float_rn(__dsub_rn(p.x, F.cx)),
-                                      __double2float_rn(__dsub_rn(p.y, F.cy)),
-                                      __double2float_rn(__dsub_rn(p.z, F.ct)), 0.0f);
+            S.s_jf[tid] = __double2float_rn(__dsub_rn(p.x, F.cx));
+            S.s_jf[TJ + tid] = __double2float_rn(__dsub_rn(p.y, F.cy));
+            S.s_jf[2 * TJ + tid] = __double2float_rn(__dsub_rn(p.z, F.ct));
         }
         if (tid == 0) s_next = (long long)gridDim.x + (long long)atomicAdd(&P.stats[0], 1ull);
         __syncthreads();

@@ -3,6 +3,8 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from stif_b200 import _native
+if os.environ.get("STIF_LIB"):            # A/B against another build of the library
+    _native.LIB_PATH = os.path.abspath(os.environ["STIF_LIB"])
 ctx = _native.Context(0)
 n_obs = int(os.environ.get("NOBS", 1_000_000)); n_t = int(os.environ.get("NT", 1_000_000))
 rng = np.random.default_rng(20261020)
@@ -14,7 +16,8 @@ for models, params, k in [(("sum_metric","spherical","spherical","spherical"), [
                           (("product_sum","spherical","spherical","spherical"), [300,60,0.8,0.7,0.15,0.10,0.4], 100)]:
     ctx.kriging_set_model(*models, params)
     nt = n_t if k == 50 else n_t // 4
-    for rep in range(2):
+    if k != 50 and os.environ.get("ONLY50"): continue
+    for rep in range(int(os.environ.get("REPS", 2))):
         t0 = time.time()
         mean, std = ctx.kriging_predict_host(tx[:nt], ty[:nt], tt[:nt], 1, k, 30.0, 30.0)
         wall = time.time() - t0

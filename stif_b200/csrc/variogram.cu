@@ -603,24 +603,26 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
 
 
 // Fixed-order reduction over the per-block partials + the reference's peeled first pair.
-__global__ void reduce_kernel(Params P, int nblocks, const double *x, const double *y,
+__global__ void __launch_bounds__(1024) reduce_kernel(Params P, int nblocks, const double *x, const double *y,
                               const double *t, const double *v, int64_t n, double smax,
                               double ws, double wt, int peel, unsigned long long *counts,
                               double *sums)
 {
-    // 256 threads = 32 bins x 8 slices of the block list: slice s adds the partials of blocks
-    // k = s, s+8, ... in increasing k (coalesced over the bins), then the 8 slices are combined
-    // in a fixed tree -- the same order for any launch, so the result is deterministic.
-    __shared__ double s_acc[8][32];
-    __shared__ unsigned long long s_cnt8[8][32];
+    // 1024 threads = 32 bins x 32 slices of the block list: slice s adds the partials of blocks
+    // k = s, s+32, ... in increasing k (coalesced over the bins, all loads of a thread in flight
+    // together), then the 32 slices are combined in a fixed binary tree -- the same order for any
+    // launch, so the result is deterministic.
+    constexpr int NSL = 32;
+    __shared__ double s_acc[NSL][32];
+    __shared__ unsigned long long s_cnt8[NSL][32];
     const int bl = threadIdx.x & 31, ks = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + bl;
     {
         double a = 0.0;
         unsigned long long cc = 0;
         if (b < P.n_bins) {
-#pragma unroll 4
-            for (int k = ks; k < nblocks; k += 8) {
+#pragma unroll 8
+            for (int k = ks; k < nblocks; k += NSL) {
                 a += P.partial_sum[(size_t)k * P.n_bins + b];
                 cc += P.partial_cnt[(size_t)k * P.n_bins + b];
             }
@@ -630,14 +632,18 @@ __global__ void reduce_kernel(Params P, int nblocks, const double *x, const doub
     }
     __syncthreads();
     if (ks != 0 || b >= P.n_bins) return;
-    double acc[8];
+    double acc[NSL];
     unsigned long long c = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NSL; ++q) {
         acc[q] = s_acc[q][bl];
         c += s_cnt8[q][bl];
     }
-    double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+#pragma unroll
+    for (int w = 1; w < NSL; w <<= 1)
+#pragma unroll
+        for (int q = 0; q < NSL; q += 2 * w) acc[q] = acc[q] + acc[q + w];
+    double s = acc[0];
     if (peel && n >= 2) {
         // rows 0 and 1 of the caller's arrays: the pair kernel binned them with the
         // reciprocal multiply; the reference bins this one pair with a true division.
@@ -990,7 +996,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
 
     // 5. reduce (+ peel fix-up on partition 0)
     const int peel = ((flags & STIF_VARIO_PEEL) && part == 0) ? 1 : 0;
-    reduce_kernel<<<(n_bins + 31) / 32, 256, 0, st>>>(
+    reduce_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
         P, grid, x, y, t, v, n, smax, ws, wt, peel,
         reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
     STIF_CUDA(cudaGetLastError());
@@ -1136,7 +1142,7 @@ extern "C" int stif_variogram_sampled_dev(stif_ctx *c, const double *x, const do
     sampled_kernel<<<grid, VT, smem, st>>>(P, Q);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[2], st));
-    reduce_kernel<<<(n_bins + 31) / 32, 256, 0, st>>>(
+    reduce_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
         P, grid, x, y, t, v, n, smax, ws, wt, 0, reinterpret_cast<unsigned long long *>(counts_dev),
         sums_dev);
     STIF_CUDA(cudaGetLastError());

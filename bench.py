@@ -267,8 +267,8 @@ def run_b200(args):
         "kernel_ms": pair_ms_avg,
         "pairs_evaluated_frac": stats["pairs_evaluated"] * world / pairs,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full on this
-        # workload (profiles/r01_ncu_pair_v9_summary.txt); = the 32 B/observation
-        "traffic": (3240704 if (workload == "c2" and world == 1) else None),
+        # workload (profiles/r01_ncu_pair_v12_summary.txt); = the 32 B/observation
+        "traffic": (3241216 if (workload == "c2" and world == 1) else None),
         "traffic_unit": "bytes per launch (ncu capture, C2)",
         "note": "achieved/frac follow SURVEY 8(d): 7 + 8 f_binned FP64 lane-instructions per "
                 "ALGORITHMIC pair (all n(n-1)/2).  The kernel executes far fewer: tile pairs "
@@ -281,11 +281,11 @@ def run_b200(args):
     }
     # What the kernel actually executes, against the resources that bound it.  Warp-instruction
     # and wavefront counts per launch are ncu counters of this workload (smsp__inst_executed.sum,
-    # l1tex__data_pipe_lsu_wavefronts.sum; profiles/r01_ncu_pair_v9_summary.txt), the duration is
+    # l1tex__data_pipe_lsu_wavefronts.sum; profiles/r01_ncu_pair_v12_summary.txt), the duration is
     # this run's.
     if workload == "c2" and world == 1:
         sm_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
-        winstr, lsu_wavefronts = 949883251, 271423898  # shared 1.796e8 + global f64 REDs 0.919e8
+        winstr, lsu_wavefronts = 892825597, 270843000  # shared 1.790e8 + global f64 REDs 0.919e8
         roofline["executed"] = {
             "prefilter_pair_tests": stats["pairs_evaluated"],
             "fp64_exact_pairs": stats["pairs_in_window"],
@@ -293,7 +293,7 @@ def run_b200(args):
             "issue_slot_frac": winstr / (pair_ms_avg * 1e-3) / (148 * 4 * sm_hz),
             "lsu_wavefronts_per_launch": lsu_wavefronts,
             "lsu_pipe_frac": lsu_wavefronts / (pair_ms_avg * 1e-3) / (148 * sm_hz),
-            "source": "ncu counters of one launch (profiles/r01_ncu_pair_v9_summary.txt) / this "
+            "source": "ncu counters of one launch (profiles/r01_ncu_pair_v12_summary.txt) / this "
                       "run's kernel time; peaks: 1 warp-instr/clk/SMSP, 1 wavefront/clk/SM",
         }
 

@@ -66,7 +66,12 @@ int stif_sm_count(stif_ctx *ctx);
  *                          and bins with a true division instead of the reciprocal
  *                          multiply used for every other pair;
  *         STIF_VARIO_NO_CULL  visit every tile pair (disables the time-sorted tile
- *                          culling; results are identical, only slower).
+ *                          culling; results are identical, only slower);
+ *         STIF_VARIO_SPACE_SORT / STIF_VARIO_TIME_SORT  force / forbid the space-time sort
+ *                          mode (observations ordered by time slab and space cell, tile
+ *                          pairs culled by their bounding boxes in space and time; default:
+ *                          used from 2^18 observations).  Counts are identical in every
+ *                          mode, the sums differ by the summation order only.
  * part / nparts: this call accumulates only the work items of partition `part` of
  *         `nparts` (multi-GPU: one partition per rank; the caller sums the partial
  *         histograms, e.g. with one NCCL all-reduce).  The PEEL fix-up is applied by
@@ -74,6 +79,8 @@ int stif_sm_count(stif_ctx *ctx);
  */
 #define STIF_VARIO_PEEL 1
 #define STIF_VARIO_NO_CULL 2
+#define STIF_VARIO_SPACE_SORT 4
+#define STIF_VARIO_TIME_SORT 8
 
 int stif_variogram_dev(stif_ctx *ctx, const double *x, const double *y, const double *t,
                        const double *v, int64_t n, double space_dist_max,

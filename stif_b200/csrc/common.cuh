@@ -87,6 +87,7 @@ struct stif_ctx {
     stif::DevBuf v_keys, v_keys_out, v_idx, v_idx_out, v_cubtmp;  // time sort
     stif::DevBuf v_pts;                                            // sorted AoS double4
     stif::DevBuf v_tileinfo;   // per i-tile j-range + prefix (work list)
+    stif::DevBuf v_bb, v_items; // space-time sort mode: sub-tile boxes, explicit item list
     stif::DevBuf v_partial;    // per-block partial histograms
     stif::DevBuf v_stats;      // device counters
     stif::DevBuf v_stage;      // staging for host entry point

@@ -92,6 +92,8 @@ int stif_ctx_destroy(stif_ctx *c)
     c->v_cubtmp.release();
     c->v_pts.release();
     c->v_tileinfo.release();
+    c->v_bb.release();
+    c->v_items.release();
     c->v_partial.release();
     c->v_stats.release();
     c->v_stage.release();

@@ -81,6 +81,9 @@ struct Params {
     float guard;          // distance from an integer below which the float guess is re-checked
     int sorted;           // observations are time-sorted (culling on)
     const FilterConst *filter;
+    // space-time sort mode: explicit item list (I << 16 | J) and the sub-tiles' bounding boxes
+    const unsigned *items;   // nullptr: items are the j-ranges of item_prefix / item_jbeg
+    const double *bb;        // [nJ][6] {xlo, xhi, ylo, yhi, tlo, thi} of every j-sub-tile
 };
 
 __global__ void pack_keys_kernel(const double *t, int64_t n, double *keys, unsigned *idx)
@@ -250,6 +253,164 @@ __global__ void scan_kernel(const int *count, int nI, int *prefix)
         __syncthreads();
     }
     if (threadIdx.x == 0) prefix[nI] = s_carry;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Space-time sort mode (large n).  Any order of the observations gives the same histogram (the
+// pair set is unordered; the peeled pair is fixed up from the caller's arrays), so the order is
+// free to serve the culling: observations are sorted by (time slab of width tmax / 2, Morton code
+// of a 256 x 256 grid over the bounding box), which makes every 256-observation sub-tile compact
+// in time AND space.  A tile pair is visited only if the boxes of the two tiles can hold a pair
+// inside both cut-offs; the test uses the reference's own rounded arithmetic on the box edges
+// and is therefore exact: rn(a - b), rn(d * d) and fma(d, d, c) are monotone, so the smallest
+// possible lag of a tile pair bounds every pair's computed lag from below.
+// ---------------------------------------------------------------------------------------------
+
+// Bounding box of the raw input (same encoding as gather_kernel's).
+__global__ void bbox_kernel(const double *x, const double *y, const double *t, int64_t n,
+                            unsigned long long *ext)
+{
+    unsigned long long e[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double px = x[k], py = y[k], pz = t[k];
+        if (px == px) { e[0] = max(e[0], ord_enc(px)); e[1] = max(e[1], ord_enc(-px)); }
+        if (py == py) { e[2] = max(e[2], ord_enc(py)); e[3] = max(e[3], ord_enc(-py)); }
+        if (pz == pz) { e[4] = max(e[4], ord_enc(pz)); e[5] = max(e[5], ord_enc(-pz)); }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const unsigned hi = (unsigned)(e[c] >> 32), lo = (unsigned)e[c];
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const unsigned long long m = ((unsigned long long)mh << 32) | ml;
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(&ext[c], m);
+    }
+}
+
+__device__ __forceinline__ unsigned spread8(unsigned v)   // abcdefgh -> 0a0b0c0d0e0f0g0h
+{
+    v = (v | (v << 4)) & 0x0f0fu;
+    v = (v | (v << 2)) & 0x3333u;
+    v = (v | (v << 1)) & 0x5555u;
+    return v;
+}
+
+// key = time slab << 16 | Morton(cell x, cell y).  Only the ORDER depends on these keys, never a
+// result, so their arithmetic needs no care beyond being defined for every input (NaN / inf).
+__global__ void spacetime_keys_kernel(const double *x, const double *y, const double *t, int64_t n,
+                                      const unsigned long long *ext, double tmax, unsigned *keys,
+                                      unsigned *idx)
+{
+    double lo[3], inv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool any = ext[2 * a] != 0ull;
+        const double hi = any ? ord_dec(ext[2 * a]) : 0.0;
+        lo[a] = any ? -ord_dec(ext[2 * a + 1]) : 0.0;
+        const double range = hi - lo[a];
+        double w = range / 256.0;                        // x, y: 256 cells over the box
+        if (a == 2) {
+            w = 0.5 * fabs(tmax);                        // t: slabs of tmax / 2 ...
+            if (!(range / w < 65535.0)) w = range / 65535.0;   // ... unless that needs > 2^16 slabs
+        }
+        inv[a] = (isfinite(lo[a]) && isfinite(w) && w > 0.0) ? 1.0 / w : 0.0;
+        if (!isfinite(lo[a]) || !isfinite(inv[a])) { lo[a] = 0.0; inv[a] = 0.0; }
+    }
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double fx = (x[i] - lo[0]) * inv[0], fy = (y[i] - lo[1]) * inv[1], ft = (t[i] - lo[2]) * inv[2];
+    // fmin / fmax drop NaN: NaN coordinates land in cell 255 / slab 65535
+    const unsigned cx = (unsigned)fmin(fmax(fx == fx ? fx : 255.0, 0.0), 255.0);
+    const unsigned cy = (unsigned)fmin(fmax(fy == fy ? fy : 255.0, 0.0), 255.0);
+    const unsigned sl = (unsigned)fmin(fmax(ft == ft ? ft : 65535.0, 0.0), 65535.0);
+    keys[i] = (sl << 16) | (spread8(cy) << 1) | spread8(cx);
+    idx[i] = (unsigned)i;
+}
+
+// One warp per j-sub-tile: box of its non-NaN coordinates (empty: lo = +inf, hi = -inf).
+__global__ void tile_bbox_kernel(const double4 *pts, int nJ, double *bb)
+{
+    const int J = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (J >= nJ) return;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int e = lane; e < TJ; e += 32) {
+        const double4 p = pts[(size_t)J * TJ + e];
+        lo[0] = fmin(lo[0], p.x); hi[0] = fmax(hi[0], p.x);   // fmin / fmax ignore NaN
+        lo[1] = fmin(lo[1], p.y); hi[1] = fmax(hi[1], p.y);
+        lo[2] = fmin(lo[2], p.z); hi[2] = fmax(hi[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            bb[(size_t)J * 6 + 2 * a] = lo[a];
+            bb[(size_t)J * 6 + 2 * a + 1] = hi[a];
+        }
+    }
+}
+
+// Smallest |a - b| the reference can compute for a in [alo, ahi], b in [blo, bhi] (0 if the
+// intervals overlap): rn(blo - ahi) or rn(alo - bhi), rounding is monotone.  NaN (inf - inf)
+// compares false everywhere below, i.e. "cannot be culled".
+__device__ __forceinline__ double box_gap(double alo, double ahi, double blo, double bhi)
+{
+    double g = 0.0;
+    const double g1 = __dsub_rn(blo, ahi), g2 = __dsub_rn(alo, bhi);
+    if (g1 > g) g = g1;
+    if (g2 > g) g = g2;
+    return g;
+}
+
+// Work list of the space-time mode, one warp per i-tile: sub-tile J >= I * JPI is an item unless
+// every pair of (I, J) is provably outside the time window or the space cut-off.
+//   d2 >= fma(gy, gy, rn(gx gx))  (utils.py:155-160 as executed),  |dt| >= gt  (utils.py:163-165)
+// FILL = false: count[I]; FILL = true: items[prefix[I] + rank] = I << 16 | J, J ascending.
+template <bool FILL>
+__global__ void items_kernel(const double *bb, int nI, int nJ, double tcut, double tmax,
+                             int *count, const int *prefix, unsigned *items)
+{
+    const int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (I >= nI) return;
+    double ilo[3] = {INFINITY, INFINITY, INFINITY}, ihi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int q = 0; q < JPI; ++q) {
+        const int J = I * JPI + q;
+        if (J < nJ) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                ilo[a] = fmin(ilo[a], bb[(size_t)J * 6 + 2 * a]);
+                ihi[a] = fmax(ihi[a], bb[(size_t)J * 6 + 2 * a + 1]);
+            }
+        }
+    }
+    int total = 0;
+    const int base = FILL ? prefix[I] : 0;
+    for (int J0 = I * JPI; J0 < nJ; J0 += 32) {
+        const int J = J0 + lane;
+        bool keep = false;
+        if (J < nJ) {
+            keep = true;
+            if (J >= I * JPI + JPI) {
+                const double *b = bb + (size_t)J * 6;
+                const double gx = box_gap(ilo[0], ihi[0], b[0], b[1]);
+                const double gy = box_gap(ilo[1], ihi[1], b[2], b[3]);
+                const double gt = box_gap(ilo[2], ihi[2], b[4], b[5]);
+                const double d2min = __fma_rn(gy, gy, __dmul_rn(gx, gx));
+                if (d2min > tcut || gt > tmax) keep = false;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (FILL && keep) items[base + total + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)I << 16) | (unsigned)J;
+        total += __popc(bal);
+    }
+    if (!FILL && lane == 0) count[I] = total;
 }
 
 struct Smem {
@@ -516,14 +677,21 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
     for (long long k = blockIdx.x;;) {
         const long long w = k * P.nparts + P.part;
         if (w >= M) break;
-        // item -> (I, J): largest I with prefix[I] <= w
-        int lo = 0, hi = P.nI - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (P.item_prefix[mid] <= w) lo = mid; else hi = mid - 1;
+        int I, J;
+        if (P.items) {   // space-time mode: explicit list
+            const unsigned it = P.items[w];
+            I = (int)(it >> 16);
+            J = (int)(it & 0xffffu);
+        } else {
+            // item -> (I, J): largest I with prefix[I] <= w
+            int lo = 0, hi = P.nI - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (P.item_prefix[mid] <= w) lo = mid; else hi = mid - 1;
+            }
+            I = lo;
+            J = P.item_jbeg[I] + (int)(w - P.item_prefix[I]);
         }
-        const int I = lo;
-        const int J = P.item_jbeg[I] + (int)(w - P.item_prefix[I]);
 
         __syncthreads();  // previous item finished with the tiles
         const double4 *gi = P.pts + (size_t)I * TI;
@@ -560,7 +728,17 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
         int variant = 1;
         if (J < I * JPI + JPI)
             variant = 0;
-        else if (P.sorted &&
+        else if (P.items) {
+            // largest lag the two boxes allow: rn(thi_J - tlo_I) and rn(thi_I - tlo_J)
+            double ilo = INFINITY, ihi = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < JPI; ++q) {
+                ilo = fmin(ilo, P.bb[(size_t)(I * JPI + q) * 6 + 4]);
+                ihi = fmax(ihi, P.bb[(size_t)(I * JPI + q) * 6 + 5]);
+            }
+            const double jlo = P.bb[(size_t)J * 6 + 4], jhi = P.bb[(size_t)J * 6 + 5];
+            if (__dsub_rn(jhi, ilo) <= P.tmax && __dsub_rn(ihi, jlo) <= P.tmax) variant = 2;
+        } else if (P.sorted &&
                  __dsub_rn(coarse_hi(S.s_jtv[TJ - 1].x), coarse_lo(S.s_itv[0].x)) <= P.tmax &&
                  __dsub_rn(coarse_hi(S.s_itv[TI - 1].x), coarse_lo(S.s_jtv[0].x)) <= P.tmax)
             variant = 2;
@@ -889,14 +1067,43 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
 
     const int64_t n_pad = (n + TI - 1) / TI * TI;
     const int nI = (int)(n_pad / TI), nJ = (int)(n_pad / TJ);
+    // space-time sort mode: pays once a time slab holds many sub-tiles (auto: n >= 2^18); the
+    // explicit item list is sized by its upper bound (every J >= I * JPI), 4 bytes per item
+    const int64_t items_max = (int64_t)nI * nJ - (int64_t)JPI * nI * (nI - 1) / 2;
+    bool spatial = cull && !(flags & STIF_VARIO_TIME_SORT) &&
+                   ((flags & STIF_VARIO_SPACE_SORT) || n >= (1 << 18));
+    if (nJ > 65535 || items_max > (1ll << 27)) spatial = false;
+    unsigned long long *ext = c->v_stats.as<unsigned long long>() + 4;
+    FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 6);
 
-    // 1. sort indices by time
+    // 1. sort indices by time (or by time slab and space cell)
     STIF_TRY(c->v_idx.reserve(sizeof(unsigned) * n));
     STIF_TRY(c->v_idx_out.reserve(sizeof(unsigned) * n));
     const int tb = 256;
     const unsigned nb_n = (unsigned)((n + tb - 1) / tb);
     const unsigned *order = nullptr;
-    if (cull) {
+    if (spatial) {
+        if (c->v_wait_upload) {   // the keys need x and y as well
+            STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_ev, 0));
+            c->v_wait_upload = false;
+        }
+        STIF_TRY(c->v_keys.reserve(sizeof(double) * n));
+        STIF_TRY(c->v_keys_out.reserve(sizeof(double) * n));
+        bbox_kernel<<<c->sm_count * 4, tb, 0, st>>>(x, y, t, n, ext);
+        spacetime_keys_kernel<<<nb_n, tb, 0, st>>>(x, y, t, n, ext, tmax, c->v_keys.as<unsigned>(),
+                                                   c->v_idx.as<unsigned>());
+        size_t tmp_bytes = 0;
+        STIF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->v_keys.as<unsigned>(),
+                                                  c->v_keys_out.as<unsigned>(),
+                                                  c->v_idx.as<unsigned>(),
+                                                  c->v_idx_out.as<unsigned>(), (int)n, 0, 32, st));
+        STIF_TRY(c->v_cubtmp.reserve(tmp_bytes));
+        STIF_CUDA(cub::DeviceRadixSort::SortPairs(c->v_cubtmp.p, tmp_bytes, c->v_keys.as<unsigned>(),
+                                                  c->v_keys_out.as<unsigned>(),
+                                                  c->v_idx.as<unsigned>(),
+                                                  c->v_idx_out.as<unsigned>(), (int)n, 0, 32, st));
+        order = c->v_idx_out.as<unsigned>();
+    } else if (cull) {
         STIF_TRY(c->v_keys.reserve(sizeof(double) * n));
         STIF_TRY(c->v_keys_out.reserve(sizeof(double) * n));
         pack_keys_kernel<<<nb_n, tb, 0, st>>>(t, n, c->v_keys.as<double>(), c->v_idx.as<unsigned>());
@@ -917,8 +1124,6 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     }
     // 2. gather into sorted, padded AoS
     STIF_TRY(c->v_pts.reserve(sizeof(double4) * n_pad));
-    unsigned long long *ext = c->v_stats.as<unsigned long long>() + 4;
-    FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 6);
     if (c->v_wait_upload) {   // host entry point: x, y, v arrive on the copy stream under the sort
         STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_ev, 0));
         c->v_wait_upload = false;
@@ -931,9 +1136,23 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     int *count = c->v_tileinfo.as<int>();
     int *jbeg = count + nI;
     int *prefix = jbeg + nI;
-    tile_range_kernel<<<(nI + 127) / 128, 128, 0, st>>>(c->v_pts.as<double4>(), n, nI, nJ, tmax,
-                                                        cull ? 1 : 0, count, jbeg);
-    scan_kernel<<<1, 1024, 0, st>>>(count, nI, prefix);
+    const double tcut = sqrt_cut_threshold(smax);
+    unsigned *items = nullptr;
+    double *bb = nullptr;
+    if (spatial) {
+        STIF_TRY(c->v_bb.reserve(sizeof(double) * 6 * (size_t)nJ));
+        STIF_TRY(c->v_items.reserve(sizeof(unsigned) * (size_t)items_max));
+        bb = c->v_bb.as<double>();
+        items = c->v_items.as<unsigned>();
+        tile_bbox_kernel<<<(nJ + 3) / 4, 128, 0, st>>>(c->v_pts.as<double4>(), nJ, bb);
+        items_kernel<false><<<(nI + 3) / 4, 128, 0, st>>>(bb, nI, nJ, tcut, tmax, count, nullptr, nullptr);
+        scan_kernel<<<1, 1024, 0, st>>>(count, nI, prefix);
+        items_kernel<true><<<(nI + 3) / 4, 128, 0, st>>>(bb, nI, nJ, tcut, tmax, nullptr, prefix, items);
+    } else {
+        tile_range_kernel<<<(nI + 127) / 128, 128, 0, st>>>(c->v_pts.as<double4>(), n, nI, nJ, tmax,
+                                                            cull ? 1 : 0, count, jbeg);
+        scan_kernel<<<1, 1024, 0, st>>>(count, nI, prefix);
+    }
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[1], st));
 
@@ -949,7 +1168,9 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     P.mode = mode;
     P.part = part;
     P.nparts = nparts;
-    P.tcut = sqrt_cut_threshold(smax);
+    P.tcut = tcut;
+    P.items = items;
+    P.bb = bb;
     P.tmax = tmax;
     const double ws = smax / (double)ns, wt = tmax / (double)nt;  // utils.py:146-147
     P.inv_ws = 1.0 / ws;
@@ -958,7 +1179,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     P.stats = c->v_stats.as<unsigned long long>();
     P.inv_ws_f = (float)P.inv_ws;
     P.guard = (float)ns * 1.9073486328125e-06f;  // 2^-19 * ns (ns <= 8192: < 0.016)
-    P.sorted = cull ? 1 : 0;
+    P.sorted = (cull && !spatial) ? 1 : 0;
     P.filter = filter;
     P.use_thr = (P.inv_ws > 0.0 && isfinite(P.inv_ws) && isfinite((double)P.inv_ws_f)) ? 1 : 0;
     if (!P.use_thr) P.guard = 2.0f;  // no pair trusts the float guess

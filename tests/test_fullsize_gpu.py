@@ -65,6 +65,12 @@ def test_c2_culled_equals_unculled(ctx, c2):
     assert np.array_equal(counts, counts2)
     assert_sums_close(sums, sums2)
     assert 0.030 < counts.sum() / (100_000 * 99_999 // 2) < 0.036  # 3.34 % binned
+    # space-time sort mode (not the default at this size): a third work list, same histogram
+    counts3, sums3 = vario(ctx, x, y, t, v, flags=_native.VARIO_PEEL | _native.VARIO_SPACE_SORT)
+    st3 = ctx.variogram_stats()
+    assert st3["pairs_evaluated"] != st["pairs_evaluated"]           # (not smaller at 100k)
+    assert np.array_equal(counts, counts3)
+    assert_sums_close(sums, sums3)
 
 
 def test_c2_permutation_and_power_of_two_scaling(ctx, c2):
@@ -114,6 +120,14 @@ def test_c3_partitions_and_permutation(ctx):
     counts, sums = vario(ctx, x, y, t, v, flags=0)
     pairs = 1_000_000 * 999_999 // 2
     assert 0.030 < counts.sum() / pairs < 0.036
+    st = ctx.variogram_stats()
+    # 1M observations run in the space-time sort mode by default; the time-sorted work list
+    # visits about twice the pairs and must give the same histogram
+    c_t, s_t = vario(ctx, x, y, t, v, flags=_native.VARIO_TIME_SORT)
+    st_t = ctx.variogram_stats()
+    assert st["pairs_evaluated"] < 0.7 * st_t["pairs_evaluated"]
+    assert np.array_equal(c_t, counts)
+    assert_sums_close(s_t, sums)
     acc_c = np.zeros_like(counts)
     acc_s = np.zeros_like(sums)
     for part in range(8):

@@ -25,6 +25,9 @@ def check(ctx, space, t, v, smax, tmax, ns, nt, mode=0, flags=_native.VARIO_PEEL
     counts, sums = ctx.variogram_host(x, y, t, v, smax, tmax, ns, nt, mode=mode, mean=mean, flags=flags)
     h, c = ov.raw(space, t, v, smax, tmax, ns, nt, mode=mode)
     assert np.array_equal(counts.astype(np.float64), c), "bin pair counts must be bit-exact"
+    if not flags & (_native.VARIO_NO_CULL | _native.VARIO_SPACE_SORT):
+        # the space-time sort mode (default from 2^18 observations) is held to the same bar
+        check(ctx, space, t, v, smax, tmax, ns, nt, mode=mode, flags=flags | _native.VARIO_SPACE_SORT)
     scale = np.maximum(np.abs(h), 1e-300)
     if mode == 0:
         assert np.all(np.abs(sums - h) <= RTOL_SUMS * scale)
@@ -221,3 +224,50 @@ def test_bad_arguments(ctx):
         ctx.variogram_host(z, z, z, z, 1.0, 1.0, 200, 200)
     with pytest.raises(ValueError):
         ctx.variogram_host(z, z, z, z, 1.0, 1.0, 3, 3, part=2, nparts=2)
+
+
+def _both_sort_modes(ctx, x, y, t, v, smax, tmax, ns, nt):
+    a, sa = ctx.variogram_host(x, y, t, v, smax, tmax, ns, nt, flags=_native.VARIO_PEEL | _native.VARIO_TIME_SORT)
+    b, sb = ctx.variogram_host(x, y, t, v, smax, tmax, ns, nt, flags=_native.VARIO_PEEL | _native.VARIO_SPACE_SORT)
+    assert np.array_equal(a, b), "space-time sort mode changes the bin counts"
+    assert np.allclose(sa, sb, rtol=1e-12, atol=0.0)
+    return a
+
+
+def test_space_sort_clustered_and_degenerate_extents(ctx):
+    """Space-time sort mode: clustered stations (many tiles culled in space), a single time
+    stamp, a single location, one coordinate constant, windows larger than the data."""
+    rng = np.random.default_rng(77)
+    n = 30000
+    centres = rng.uniform(0, 1000, (12, 2))
+    k = rng.integers(0, 12, n)
+    x = centres[k, 0] + rng.normal(scale=4.0, size=n)
+    y = centres[k, 1] + rng.normal(scale=4.0, size=n)
+    t = rng.uniform(0, 2000, n)
+    v = rng.normal(size=n)
+    c = _both_sort_modes(ctx, x, y, t, v, 25.0, 40.0, 12, 9)
+    assert c.sum() > 0
+    space = np.stack([x, y], axis=1)[:6000]
+    check(ctx, space, t[:6000], v[:6000], 25.0, 40.0, 12, 9)
+    _both_sort_modes(ctx, x, y, np.full(n, 17.0), v, 25.0, 40.0, 12, 9)            # one time stamp
+    _both_sort_modes(ctx, np.full(n, 3.0), np.full(n, -8.0), t, v, 25.0, 40.0, 12, 9)  # one location
+    _both_sort_modes(ctx, x, np.zeros(n), t, v, 25.0, 40.0, 12, 9)                 # y constant
+    _both_sort_modes(ctx, x, y, t, v, 1e9, 1e9, 7, 5)                               # nothing to cull
+    _both_sort_modes(ctx, x, y, t, v, 25.0, 1e-3, 12, 9)                            # > 2^16 slabs
+
+
+def test_space_sort_nan_inf(ctx):
+    """NaN / infinite coordinates and times in the space-time sort mode: same counts as the
+    time-sorted mode (which is checked against the oracle elsewhere)."""
+    rng = np.random.default_rng(78)
+    n = 9000
+    x = rng.uniform(0, 100, n); y = rng.uniform(0, 100, n)
+    t = rng.uniform(0, 100, n); v = rng.normal(size=n)
+    for arr in (x, y, t):
+        arr[rng.integers(0, n, 40)] = np.nan
+        arr[rng.integers(0, n, 5)] = np.inf
+        arr[rng.integers(0, n, 5)] = -np.inf
+    _both_sort_modes(ctx, x, y, t, v, 20.0, 15.0, 10, 8)
+    x[:] = np.nan
+    c = _both_sort_modes(ctx, x, y, t, v, 20.0, 15.0, 10, 8)
+    assert c.sum() == 0

@@ -300,7 +300,7 @@ __device__ __forceinline__ unsigned spread8(unsigned v)   // abcdefgh -> 0a0b0c0
 // key = time slab << 16 | Morton(cell x, cell y).  Only the ORDER depends on these keys, never a
 // result, so their arithmetic needs no care beyond being defined for every input (NaN / inf).
 __global__ void spacetime_keys_kernel(const double *x, const double *y, const double *t, int64_t n,
-                                      const unsigned long long *ext, double tmax, unsigned *keys,
+                                      const unsigned long long *ext, double slab_w, unsigned *keys,
                                       unsigned *idx)
 {
     double lo[3], inv[3];
@@ -312,7 +312,7 @@ __global__ void spacetime_keys_kernel(const double *x, const double *y, const do
         const double range = hi - lo[a];
         double w = range / 256.0;                        // x, y: 256 cells over the box
         if (a == 2) {
-            w = 0.5 * fabs(tmax);                        // t: slabs of tmax / 2 ...
+            w = slab_w;                                  // t: slabs of tmax / 2 ...
             if (!(range / w < 65535.0)) w = range / 65535.0;   // ... unless that needs > 2^16 slabs
         }
         inv[a] = (isfinite(lo[a]) && isfinite(w) && w > 0.0) ? 1.0 / w : 0.0;
@@ -1089,8 +1089,9 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         }
         STIF_TRY(c->v_keys.reserve(sizeof(double) * n));
         STIF_TRY(c->v_keys_out.reserve(sizeof(double) * n));
+        const double slab_w = fabs(tmax) * (getenv("STIF_VARIO_SLAB") ? atof(getenv("STIF_VARIO_SLAB")) : 0.5);
         bbox_kernel<<<c->sm_count * 4, tb, 0, st>>>(x, y, t, n, ext);
-        spacetime_keys_kernel<<<nb_n, tb, 0, st>>>(x, y, t, n, ext, tmax, c->v_keys.as<unsigned>(),
+        spacetime_keys_kernel<<<nb_n, tb, 0, st>>>(x, y, t, n, ext, slab_w, c->v_keys.as<unsigned>(),
                                                    c->v_idx.as<unsigned>());
         size_t tmp_bytes = 0;
         STIF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->v_keys.as<unsigned>(),

@@ -38,7 +38,10 @@ namespace vario {
 constexpr int VT = 256;        // threads per block
 constexpr int VR = 2;          // i-points per thread (registers)
 constexpr int TI = VT * VR;    // i-tile: 512 observations
-constexpr int TJ = 256;        // j-sub-tile: 256 observations
+#ifndef STIF_VARIO_TJ
+#define STIF_VARIO_TJ 256
+#endif
+constexpr int TJ = STIF_VARIO_TJ;  // j-sub-tile: 256 observations
 constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
 constexpr int QW = 512;        // entries (uint32) of a warp's circular queue
 #ifndef STIF_VARIO_NB

@@ -3,6 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from stif_b200 import _native
+if os.environ.get("STIF_LIB"):
+    _native.LIB_PATH = os.path.abspath(os.environ["STIF_LIB"])
 ctx = _native.Context(0)
 for n in [int(a) for a in os.environ.get("NS", "100000,300000,1000000").split(",")]:
     rng = np.random.default_rng(20261019)

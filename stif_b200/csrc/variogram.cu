@@ -25,6 +25,9 @@
 //      binned in dense batches of 32 with the reference's exact FP64 arithmetic: cut-off
 //      tests, bins, shared-memory count atomics, global (L2) f64 sum atomics.
 //   5. deterministic fixed-order reduction of the per-block partial histograms.
+// From 2^18 observations steps 1-3 run in the SPACE-TIME SORT MODE instead (see the block comment
+// above bbox_kernel): order by (time slab, Morton cell), bounding boxes of the sub-tiles, explicit
+// item list from exact box-gap tests in space and time.  Same kernel, same histogram.
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>

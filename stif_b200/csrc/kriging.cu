@@ -198,11 +198,12 @@ struct GridDims {
 };
 
 constexpr double GRID_SUB = 2.0;   // cells per search radius (finer cells: fewer candidates examined)
+constexpr double GRID_SUB_X = 8.0; // ... along x, where the cells of a stencil row are one contiguous run
 
 // Decide grid geometry on the device (no host round trip): cells are >= radius*(1+1e-9)
 // wide and the total number of cells is capped at max_cells by widening them.
 __global__ void grid_dims_kernel(const double *bbox_enc, double smax, double tmax, int64_t max_cells,
-                                 GridDims *out)
+                                 double sub_x, double sub_y, double sub_t, GridDims *out)
 {
     const unsigned long long *bb = reinterpret_cast<const unsigned long long *>(bbox_enc);
     double lo[3], hi[3];
@@ -215,14 +216,24 @@ __global__ void grid_dims_kernel(const double *bbox_enc, double smax, double tma
         }
     }
     const double radius[3] = {smax, smax, tmax};
+    const double sub[3] = {sub_x, sub_y, sub_t};
     double cell[3], n[3];
     bool valid[3];
     for (int d = 0; d < 3; ++d) {
         valid[d] = radius[d] > 0.0 && !isinf(radius[d]);
-        cell[d] = valid[d] ? radius[d] / GRID_SUB : (hi[d] - lo[d]) + 1.0;
+        cell[d] = valid[d] ? radius[d] / sub[d] : (hi[d] - lo[d]) + 1.0;
         cell[d] *= (1.0 + 1e-9);
         n[d] = floor((hi[d] - lo[d]) / cell[d]) + 2.0;  // one spare cell at the upper edge
         if (!(n[d] >= 2.0)) n[d] = 2.0;
+    }
+    // the x axis may be finer than the others (its cells are contiguous in memory, so a finer x
+    // costs no extra runs): halve its subdivision while the grid does not fit the cap
+    for (double sx = sub_x; valid[0] && sx > sub_y && n[0] * n[1] * n[2] > (double)max_cells;) {
+        sx *= 0.5;
+        if (sx < sub_y) sx = sub_y;
+        cell[0] = radius[0] / sx * (1.0 + 1e-9);
+        n[0] = floor((hi[0] - lo[0]) / cell[0]) + 2.0;
+        if (!(n[0] >= 2.0)) n[0] = 2.0;
     }
     // cap: widen all cells by a common factor until the product fits
     for (int it = 0; it < 64 && n[0] * n[1] * n[2] > (double)max_cells; ++it) {
@@ -1520,7 +1531,9 @@ int ensure_grid(stif_ctx *c, double smax, double tmax, cudaStream_t st)
     if (nb > c->sm_count * 8) nb = c->sm_count * 8;
     if (nb < 1) nb = 1;
     bbox_kernel<<<nb, tb, 0, st>>>(ox, oy, ot, n, bbox);
-    grid_dims_kernel<<<1, 1, 0, st>>>(bbox, smax, tmax, max_cells, gd);
+    double sub[3] = {GRID_SUB_X, GRID_SUB, GRID_SUB};
+    if (const char *e = getenv("STIF_GRID_SUB")) sscanf(e, "%lf,%lf,%lf", &sub[0], &sub[1], &sub[2]);
+    grid_dims_kernel<<<1, 1, 0, st>>>(bbox, smax, tmax, max_cells, sub[0], sub[1], sub[2], gd);
     const unsigned nbn = (unsigned)((n + tb - 1) / tb);
     unsigned *keys = c->k_scratch[S_OKEYS].as<unsigned>(), *idx = c->k_scratch[S_OIDX].as<unsigned>();
     unsigned *keys_s = c->k_scratch[S_OKEYS_S].as<unsigned>(), *idx_s = c->k_scratch[S_OIDX_S].as<unsigned>();

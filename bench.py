@@ -272,7 +272,7 @@ def run_b200(args):
         "traffic_unit": "bytes per launch (ncu capture, C2)",
         "note": "achieved/frac follow SURVEY 8(d): 7 + 8 f_binned FP64 lane-instructions per "
                 "ALGORITHMIC pair (all n(n-1)/2).  The kernel executes far fewer: tile pairs "
-                "outside the time window (from 2^18 observations also: outside the space cut-off, "
+                "outside the time window (from 160k observations also: outside the space cut-off, "
                 "space-time sort mode) are never visited (pairs_evaluated_frac), and visited "
                 "pairs are tested by a float pre-filter with a rigorous error band (5-7 FP32 "
                 "instructions); only the pairs it cannot rule out (= the in-window pairs, to "

@@ -70,7 +70,7 @@ int stif_sm_count(stif_ctx *ctx);
  *         STIF_VARIO_SPACE_SORT / STIF_VARIO_TIME_SORT  force / forbid the space-time sort
  *                          mode (observations ordered by time slab and space cell, tile
  *                          pairs culled by their bounding boxes in space and time; default:
- *                          used from 2^18 observations).  Counts are identical in every
+ *                          used from 163 840 observations).  Counts are identical in every
  *                          mode, the sums differ by the summation order only.
  * part / nparts: this call accumulates only the work items of partition `part` of
  *         `nparts` (multi-GPU: one partition per rank; the caller sums the partial

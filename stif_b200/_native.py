@@ -20,7 +20,7 @@ STIF_ENONFINITE = -5
 
 VARIO_PEEL = 1
 VARIO_NO_CULL = 2
-VARIO_SPACE_SORT = 4   # force the space-time sort mode (default: from 2^18 observations)
+VARIO_SPACE_SORT = 4   # force the space-time sort mode (default: from 163 840 observations)
 VARIO_TIME_SORT = 8    # forbid it
 KRIG_F32_STORAGE = 1
 KRIG_FORCE_LU = 2

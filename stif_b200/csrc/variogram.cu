@@ -25,7 +25,7 @@
 //      binned in dense batches of 32 with the reference's exact FP64 arithmetic: cut-off
 //      tests, bins, shared-memory count atomics, global (L2) f64 sum atomics.
 //   5. deterministic fixed-order reduction of the per-block partial histograms.
-// From 2^18 observations steps 1-3 run in the SPACE-TIME SORT MODE instead (see the block comment
+// From 163 840 observations steps 1-3 run in the SPACE-TIME SORT MODE instead (see the block comment
 // above bbox_kernel): order by (time slab, Morton cell), bounding boxes of the sub-tiles, explicit
 // item list from exact box-gap tests in space and time.  Same kernel, same histogram.
 #include "common.cuh"
@@ -1099,11 +1099,12 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
 
     const int64_t n_pad = (n + TI - 1) / TI * TI;
     const int nI = (int)(n_pad / TI), nJ = (int)(n_pad / TJ);
-    // space-time sort mode: pays once a time slab holds many sub-tiles (auto: n >= 2^18); the
+    // space-time sort mode: pays once a time slab holds many sub-tiles (auto: n >= 160 x 1024,
+    // measured break-even incl. the longer prepare phase ~150k at the C2 / C3 densities); the
     // explicit item list is sized by its upper bound (every J >= I * JPI), 4 bytes per item
     const int64_t items_max = (int64_t)nI * nJ - (int64_t)JPI * nI * (nI - 1) / 2;
     bool spatial = cull && !(flags & STIF_VARIO_TIME_SORT) &&
-                   ((flags & STIF_VARIO_SPACE_SORT) || n >= (1 << 18));
+                   ((flags & STIF_VARIO_SPACE_SORT) || n >= 160 * 1024);
     if (nJ > 65535 || items_max > (1ll << 27)) spatial = false;
     unsigned long long *ext = c->v_stats.as<unsigned long long>() + 4;
     FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 6);

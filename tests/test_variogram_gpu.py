@@ -26,7 +26,7 @@ def check(ctx, space, t, v, smax, tmax, ns, nt, mode=0, flags=_native.VARIO_PEEL
     h, c = ov.raw(space, t, v, smax, tmax, ns, nt, mode=mode)
     assert np.array_equal(counts.astype(np.float64), c), "bin pair counts must be bit-exact"
     if not flags & (_native.VARIO_NO_CULL | _native.VARIO_SPACE_SORT):
-        # the space-time sort mode (default from 2^18 observations) is held to the same bar
+        # the space-time sort mode (default from 160k observations) is held to the same bar
         check(ctx, space, t, v, smax, tmax, ns, nt, mode=mode, flags=flags | _native.VARIO_SPACE_SORT)
     scale = np.maximum(np.abs(h), 1e-300)
     if mode == 0:

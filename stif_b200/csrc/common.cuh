@@ -78,6 +78,7 @@ struct stif_ctx {
     cudaStream_t last_stream = nullptr; // stream the last call was enqueued on
     cudaStream_t stream2 = nullptr;     // copy stream of the chunked host pipeline
     cudaEvent_t v_upload_ev = nullptr;  // variogram host call: x, y, v uploaded (stream2)
+    cudaEvent_t v_upload_xy_ev = nullptr;  // ... x and y uploaded (the space-time sort keys need them)
     bool v_wait_upload = false;         // stif_variogram_dev waits for it before the gather
     cudaEvent_t *ev_override = nullptr; // phase events of the chunk being enqueued (pipeline)
     bool keep_stats = false;            // pipeline: accumulate the statistics over the chunks

@@ -113,6 +113,7 @@ int stif_ctx_destroy(stif_ctx *c)
     for (auto e : c->chunk_ev) cudaEventDestroy(e);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->v_upload_ev) cudaEventDestroy(c->v_upload_ev);
+    if (c->v_upload_xy_ev) cudaEventDestroy(c->v_upload_xy_ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return STIF_OK;

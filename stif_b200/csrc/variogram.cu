@@ -1116,10 +1116,8 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     const unsigned nb_n = (unsigned)((n + tb - 1) / tb);
     const unsigned *order = nullptr;
     if (spatial) {
-        if (c->v_wait_upload) {   // the keys need x and y as well
-            STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_ev, 0));
-            c->v_wait_upload = false;
-        }
+        if (c->v_wait_upload)     // the keys need x and y as well (v still travels under the sort)
+            STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_xy_ev, 0));
         STIF_TRY(c->v_keys.reserve(sizeof(double) * n));
         STIF_TRY(c->v_keys_out.reserve(sizeof(double) * n));
         const double slab_w = fabs(tmax) * (getenv("STIF_VARIO_SLAB") ? atof(getenv("STIF_VARIO_SLAB")) : 0.5);
@@ -1312,9 +1310,11 @@ extern "C" int stif_variogram_host(stif_ctx *c, const double *x, const double *y
         // staging buffers because every host call ends with a stream synchronisation
         if (!c->stream2) STIF_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         if (!c->v_upload_ev) STIF_CUDA(cudaEventCreateWithFlags(&c->v_upload_ev, cudaEventDisableTiming));
+        if (!c->v_upload_xy_ev) STIF_CUDA(cudaEventCreateWithFlags(&c->v_upload_xy_ev, cudaEventDisableTiming));
         STIF_CUDA(cudaMemcpyAsync(dt, t, in_bytes, cudaMemcpyHostToDevice, st));
         STIF_CUDA(cudaMemcpyAsync(dx, x, in_bytes, cudaMemcpyHostToDevice, c->stream2));
         STIF_CUDA(cudaMemcpyAsync(dy, y, in_bytes, cudaMemcpyHostToDevice, c->stream2));
+        STIF_CUDA(cudaEventRecord(c->v_upload_xy_ev, c->stream2));
         STIF_CUDA(cudaMemcpyAsync(dv, v, in_bytes, cudaMemcpyHostToDevice, c->stream2));
         STIF_CUDA(cudaEventRecord(c->v_upload_ev, c->stream2));
         c->v_wait_upload = true;

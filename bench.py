@@ -332,9 +332,11 @@ def run_b200(args):
             "parallelism": f"tile-pair partition x{world}",
         },
         "clocks": clocks, "e2e": e2e,
-        # own kernels per step: pack_keys, gather, filter_setup, tile_range, scan, pair, reduce
+        # own kernels per step, time-sorted mode: pack_keys, gather, filter_setup, tile_range, scan,
+        # pair, reduce; space-time sort mode (from 163 840 observations): bbox, spacetime_keys,
+        # gather, filter_setup, tile_bbox, items (count), scan, items (fill), pair, reduce
         # (the CUB radix-sort passes in between are library launches and not counted)
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": (10 if n >= 160 * 1024 else 7) * args.steps,
         "roofline": roofline, "wall_s_bracket": wall_bracket,
     }
 

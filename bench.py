@@ -4,19 +4,28 @@
     python bench.py --gpus 1 --steps K --warmup W              # N = 1
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W  # N > 1, one rank per GPU
-    python bench.py --impl reference ...                        # CPU oracle port of the reference
+    python bench.py --impl reference ...                        # the reference's numba CPU path
 
-Prints ONE JSON line (rank 0).  The headline metric is BASELINE.json's first half --
-all-pairs space-time variogram pairs/s -- on configs[1] (C2: 100k observations, 30x30 bins)
-at N = 1 and on configs[2] (C3: 1M observations, tile pairs sharded over ranks + one NCCL
-all-reduce of the histograms) at N > 1.  The second half -- kriging predictions/s, k = 50,
-configs[3] (C4) -- is reported in the same line under "kriging" with the same sub-keys.
+Prints ONE JSON line (rank 0).
+
+Headline (top-level keys): BASELINE.json's first metric -- all-pairs space-time variogram
+pairs/s -- on configs[2] (C3: 1M observations, 499 999 500 000 pairs, 30x30 lag bins) at EVERY
+N (`scaling: strong`: the pair tiles are sharded over the ranks and the histograms meet in one
+NCCL all-reduce), so the driver's 1 -> 8 curve is one workload.  The result of every run is
+compared with the oracle's whole-workload golden (tests/golden/variogram_c3.npz): counts
+bit-exact, sums 1e-12.  Further blocks of the same line, each with its own value / e2e /
+roofline / cpu_baseline:
+    "c2"          configs[1]: 100k observations x 365 days, single B200 (N = 1 only)
+    "kriging"     configs[3] share: 1M observations, 1.25M targets per GPU, k = 50, sum_metric
+    "kriging_c5"  configs[4] share: 2M observations (indicator residuals), 125k targets per GPU,
+                  k = 100, product_sum
 
 A "step" is one pass of the hot path over the whole synthetic workload.  `value` has the
-inputs resident in HBM; `e2e` goes through the C ABI's host-pointer entry point with pinned
-host buffers (H2D + D2H inside the timed region).
+inputs resident in HBM; `e2e` goes through the public entry point with pinned HOST buffers
+(H2D + D2H inside the timed region).
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -32,14 +41,26 @@ if ROOT not in sys.path:
 C2_N = 100_000
 C3_N = 1_000_000
 VARIO = dict(space_dist_max=30.0, time_dist_max=30.0, n_space_bins=30, n_time_bins=30)
-C4_OBS = 1_000_000
-C4_TARGETS_PER_GPU = 1_250_000       # 10M targets over 8 GPUs
-C4_MODEL = ("sum_metric", "spherical", "spherical", "spherical")
-C4_PARAMS = [400, 60, 500, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0]
-C4_K = 50
-C4_RADII = (30.0, 30.0)
 FP64_PER_PAIR = 7.0                  # dx dy mul fma cmp dt cmp
 FP64_PER_BINNED = 8.0
+
+KRIG = {
+    "c4": dict(
+        name="kriging", seed=20261020, n_obs=1_000_000, targets_per_gpu=1_250_000, k=50,
+        model=("sum_metric", "spherical", "spherical", "spherical"),
+        params=[400, 60, 500, 0.4, 0.2, 0.3, 0.03, 0.03, 0.03, 5.0], radii=(30.0, 30.0), f_gamma=42.0,
+        indicator=False, cpu_targets=1000, cpu_batch=200,
+        workload="C4 share: 1M observations (replicated), 1.25M targets per GPU (10M over 8), k=50, "
+                 "sum_metric/spherical, radii 30/30, float32-storage emulation on"),
+    "c5": dict(
+        name="kriging_c5", seed=20261021, n_obs=2_000_000, targets_per_gpu=125_000, k=100,
+        model=("product_sum", "spherical", "spherical", "spherical"),
+        params=[300, 60, 0.8, 0.7, 0.15, 0.10, 0.4], radii=(30.0, 30.0), f_gamma=27.0,
+        indicator=True, cpu_targets=300, cpu_batch=100,
+        workload="C5 share: 2M observations (presence/absence residuals, replicated), 125k targets per "
+                 "GPU (1M over 8; BASELINE.json gives no target count), k=100, product_sum/spherical, "
+                 "radii 30/30, float32-storage emulation on"),
+}
 
 
 def synth_variogram(n):
@@ -52,14 +73,19 @@ def synth_variogram(n):
     return x, y, t, v
 
 
-def synth_kriging(n_obs, n_targets, rank=0):
-    """SURVEY 8(d) C4 generator (targets drawn per rank so shards differ)."""
-    rng = np.random.default_rng(20261020)
+def synth_kriging(n_obs, n_targets, rank=0, seed=20261020, indicator=False):
+    """SURVEY 8(d) C4 / C5 generators (targets drawn per rank so shards differ)."""
+    rng = np.random.default_rng(seed)
     x = rng.uniform(0, 1000, n_obs)
     y = rng.uniform(0, 1000, n_obs)
     t = rng.uniform(0, 365, n_obs)
-    z = np.sin(x / 150) + np.cos(y / 200) + 0.5 * np.sin(t / 30) + 0.3 * rng.normal(size=n_obs)
-    trng = np.random.default_rng(20261020 + 1000 + rank)
+    field = np.sin(x / 150) + np.cos(y / 200) + 0.5 * np.sin(t / 30)
+    if indicator:       # presence = U(0,1) < sigmoid(2 field); residual = presence - mean (no covariates)
+        presence = rng.uniform(size=n_obs) < 1.0 / (1.0 + np.exp(-2.0 * field))
+        z = presence.astype(np.float64) - presence.mean()
+    else:
+        z = field + 0.3 * rng.normal(size=n_obs)
+    trng = np.random.default_rng(seed + 1000 + rank)
     tx = trng.uniform(0, 1000, n_targets)
     ty = trng.uniform(0, 1000, n_targets)
     tt = trng.uniform(30, 365, n_targets)
@@ -71,8 +97,8 @@ def workload_name(workload):
     if workload == "c2":
         return ("C2: synthetic 100k observations x 365 days, all-pairs space-time variogram, "
                 "30x30 lag bins, smax=30 tmax=30")
-    return ("C3: synthetic 1M observations, all-pairs variogram, 30x30 lag bins, tile pairs "
-            "sharded over ranks + NCCL all-reduce of the histograms")
+    return ("C3: synthetic 1M observations, all-pairs space-time variogram (499999500000 pairs), 30x30 lag "
+            "bins, smax=30 tmax=30; pair tiles sharded over the ranks + one NCCL all-reduce of the histograms")
 
 
 def measured_hbm_gbs():
@@ -85,9 +111,32 @@ def measured_hbm_gbs():
         return 6551.4
 
 
-def kriging_flops(k, cbar, f_gamma=42.0):
-    """algorithmic FP64 flops per prediction (FMA = 2)."""
-    return cbar * f_gamma + k * (k - 1) / 2 * f_gamma + (k + 1) ** 3 / 3 + 2 * (k + 1) ** 2 + 4 * k
+def kriging_flops(k, cbar, f_gamma):
+    """algorithmic FP64 flops per prediction (FMA = 2, sqrt = 1).  Returns
+    (search share = the gamma-vector over the in-window candidates, assemble + solve share)."""
+    search = cbar * f_gamma
+    solve = k * (k - 1) / 2 * f_gamma + (k + 1) ** 3 / 3 + 2 * (k + 1) ** 2 + 4 * k
+    return search, solve
+
+
+def library_digest():
+    """Digest of the CUDA sources the loaded library was built from (stif_b200/build.py stamp)."""
+    try:
+        with open(os.path.join(ROOT, "stif_b200", "libstif_b200.so.stamp")) as f:
+            return f.read().strip()[:16]
+    except OSError:
+        return None
+
+
+def ncu_counters(kernel_key):
+    """Counters of one launch from a committed ncu capture (profiles/r02_kernel_counters.json,
+    written by tools/ncu_counters.py).  Returned with `build` = digest of the sources the capture
+    was taken on, so a reader sees whether it matches the library that ran (`library_digest`)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_kernel_counters.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -159,226 +208,233 @@ def pinned(a):
 # ----------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from stif_b200 import _native, parallel
+class Env:
+    """Process-wide state of one rank."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from stif_b200 import _native
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference "
-                         "for the CPU oracle port)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = _native.Context(local_rank)
-    # a dedicated (non-default) torch stream: the kernels, the NCCL all-reduce and the timing
-    # events all go to it (the C ABI treats a NULL stream as "the context's own stream")
-    bench_stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(bench_stream)
-    stream = bench_stream.cuda_stream
-    assert stream != 0
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference "
+                             "for the reference's CPU path)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = _native.Context(self.local_rank)
+        # a dedicated (non-default) torch stream: the kernels, the NCCL collectives and the timing
+        # events all go to it (the C ABI treats a NULL stream as "the context's own stream")
+        self.bench_stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.bench_stream)
+        self.stream = self.bench_stream.cuda_stream
+        assert self.stream != 0
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+        # measured FP64 issue peak (MEASURED_PEAKS.json has HBM and bf16 only)
+        self.ctx.bench_dfma(1024)
+        self.dfma_rate, _ = self.ctx.bench_dfma(8192)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(v):
-        if world == 1:
+    def max_over_ranks(self, v):
+        if self.world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    def flush_l2(self):
+        self.flush_buf.fill_(1)
 
-    def flush_l2():
-        flush_buf.fill_(1)
 
-    # measured FP64 issue peak (MEASURED_PEAKS.json has HBM and bf16 only)
-    ctx.bench_dfma(1024)
-    dfma_rate, _ = ctx.bench_dfma(8192)
-
-    # ---------------- variogram ----------------
-    workload = args.workload
-    if workload == "auto":
-        workload = "c2" if world == 1 else "c3"
+def bench_variogram(env, workload, steps, warmup):
+    """One variogram workload: device-resident value, e2e, roofline of the pair kernel, and the
+    comparison of the result with the oracle's whole-workload golden."""
+    torch, dist = env.torch, env.dist
+    from stif_b200 import _native, parallel
+    ctx, rank, world, dev = env.ctx, env.rank, env.world, env.dev
     n = C2_N if workload == "c2" else C3_N
     x, y, t, v = synth_variogram(n)
     pairs = n * (n - 1) // 2
     ns, nt = VARIO["n_space_bins"], VARIO["n_time_bins"]
+    nb = ns * nt
     dx, dy, dt_, dv = (torch.from_numpy(a).to(dev) for a in (x, y, t, v))
-    counts = torch.zeros(ns * nt, dtype=torch.int64, device=dev)
-    sums = torch.zeros(ns * nt, dtype=torch.float64, device=dev)
+    # one float64 buffer [counts | sums]: the histograms of all ranks meet in ONE all-reduce
+    fused = torch.zeros(2 * nb, dtype=torch.float64, device=dev)
+    flags = _native.VARIO_PEEL | _native.VARIO_COUNTS_F64
 
     def vario_step():
         ctx.variogram_dev(dx.data_ptr(), dy.data_ptr(), dt_.data_ptr(), dv.data_ptr(), n,
                           VARIO["space_dist_max"], VARIO["time_dist_max"], ns, nt,
-                          counts.data_ptr(), sums.data_ptr(), part=rank, nparts=world, stream=stream)
+                          fused.data_ptr(), fused.data_ptr() + 8 * nb, flags=flags, part=rank, nparts=world,
+                          stream=env.stream)
         if world > 1:
-            dist.all_reduce(counts)     # the path's one real exchange: 14.4 KB of histograms
-            dist.all_reduce(sums)
+            dist.all_reduce(fused)      # the path's one real exchange: 14.4 KB of histograms
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         vario_step()
-    barrier()
-    sampler = ClockSampler(local_rank).start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    pair_ms = 0.0
+    env.barrier()
+    sampler = ClockSampler(env.local_rank).start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    pair_ms = prep_ms = 0.0
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush_l2()
+    for i in range(steps):
+        env.flush_l2()
         if world > 1:
             dist.barrier()
         starts[i].record()
         vario_step()
         ends[i].record()
         ends[i].synchronize()
-        pair_ms += ctx.last_phase_ms()[1]
-    barrier()
+        ph = ctx.last_phase_ms()
+        prep_ms += ph[0]
+        pair_ms += ph[1]
+    env.barrier()
     wall_bracket = time.perf_counter() - wall0
     clocks = sampler.stop()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = max_over_ranks(sum(step_ms))
-    ms_per_step = total_ms / args.steps
+    total_ms = env.max_over_ranks(sum(step_ms))
+    ms_per_step = total_ms / steps
     value = pairs / (ms_per_step * 1e-3)
     stats = ctx.variogram_stats()
-    binned_total = int(counts.sum().item())
+    res = fused.cpu().numpy()
+    counts_dev, sums_dev = res[:nb].astype(np.int64), res[nb:].copy()
+    binned_total = int(counts_dev.sum())
+
+    # ---- the result against the oracle's full run over the same workload ----
+    golden_path = os.path.join(ROOT, "tests", "golden", f"variogram_{workload}.npz")
+    g = np.load(golden_path)
+    counts_ok = bool(np.array_equal(counts_dev, g["counts"].ravel()))
+    sums_rel = float(np.max(np.abs(sums_dev - g["sums"].ravel()) / np.abs(g["sums"].ravel())))
+    assert counts_ok, f"{workload}: bin counts differ from the oracle golden at N={world}"
+    assert sums_rel <= 1e-12, f"{workload}: sums differ from the oracle golden by {sums_rel:.3e} at N={world}"
+
     f_binned = binned_total / pairs
     lane_instr_per_pair = FP64_PER_PAIR + FP64_PER_BINNED * f_binned
-    pair_ms_avg = max_over_ranks(pair_ms) / args.steps
+    pair_ms_avg = env.max_over_ranks(pair_ms) / steps
     achieved = pairs * lane_instr_per_pair / world / (pair_ms_avg * 1e-3)   # per GPU
+    cnt = ncu_counters(f"pair_kernel_{workload}") if world == 1 else None
     roofline = {
         "bound": "fp64_issue", "kernel": "stif::vario::pair_kernel",
-        "achieved": achieved, "peak": dfma_rate, "unit": "FP64 lane-instr/s per GPU",
-        "frac": achieved / dfma_rate,
+        "achieved": achieved, "peak": env.dfma_rate, "unit": "FP64 lane-instr/s per GPU",
+        "frac": achieved / env.dfma_rate,
         "peak_source": "measured live: register-resident DFMA microbenchmark (stif_bench_dfma); "
                        "nominal 148 SM x 64 lanes x 1.965 GHz = 1.861e13",
         "frac_of_nominal": achieved / 1.861e13,
         "algorithmic_lane_instr_per_pair": lane_instr_per_pair,
-        "kernel_ms": pair_ms_avg,
+        "kernel_ms": pair_ms_avg, "prepare_ms": env.max_over_ranks(prep_ms) / steps,
         "pairs_evaluated_frac": stats["pairs_evaluated"] * world / pairs,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full on this
-        # workload (profiles/r01_ncu_pair_v12_summary.txt); = the 32 B/observation
-        "traffic": (3241216 if (workload == "c2" and world == 1) else None),
-        "traffic_unit": "bytes per launch (ncu capture, C2)",
-        "note": "achieved/frac follow SURVEY 8(d): 7 + 8 f_binned FP64 lane-instructions per "
-                "ALGORITHMIC pair (all n(n-1)/2).  The kernel executes far fewer: tile pairs "
-                "outside the time window (from 160k observations also: outside the space cut-off, "
-                "space-time sort mode) are never visited (pairs_evaluated_frac), and visited "
-                "pairs are tested by a float pre-filter with a rigorous error band (5-7 FP32 "
-                "instructions); only the pairs it cannot rule out (= the in-window pairs, to "
-                "1e-6) are evaluated in FP64, exactly as the reference does.  frac > 1 is "
-                "therefore expected; what bounds the kernel now is instruction issue and the "
-                "shared-memory pipe, see `executed`.",
+        "prefilter_pair_tests": stats["pairs_evaluated"], "fp64_exact_pairs": stats["pairs_in_window"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full of this workload)
+        "traffic": (cnt or {}).get("dram_bytes"),
+        "traffic_unit": "bytes per launch; algorithmic = 32 B per observation in + 16 B per bin out = "
+                        f"{32 * n + 16 * nb}",
+        "note": "achieved / frac follow SURVEY 8(d): 7 + 8 f_binned FP64 lane-instructions per "
+                "ALGORITHMIC pair (all n(n-1)/2).  The kernel executes far fewer: tile pairs provably "
+                "outside the window are never visited (pairs_evaluated_frac) and visited pairs go "
+                "through a float pre-filter with a rigorous error band; only the pairs it cannot rule "
+                "out are evaluated in FP64, exactly as the reference does.  frac > 1 is therefore "
+                "expected and is an accounting figure, not a utilisation; `executed` is the utilisation.",
     }
-    # What the kernel actually executes, against the resources that bound it.  Warp-instruction
-    # and wavefront counts per launch are ncu counters of this workload (smsp__inst_executed.sum,
-    # l1tex__data_pipe_lsu_wavefronts.sum; profiles/r01_ncu_pair_v12_summary.txt), the duration is
-    # this run's.
-    if workload == "c2" and world == 1:
+    if cnt:
+        # what the kernel executes, against the resources that bound it: counters of ONE launch from
+        # the committed ncu capture named in `source`, divided by THIS run's kernel time
         sm_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
-        winstr, lsu_wavefronts = 892825597, 270843000  # shared 1.790e8 + global f64 REDs 0.919e8
         roofline["executed"] = {
-            "prefilter_pair_tests": stats["pairs_evaluated"],
-            "fp64_exact_pairs": stats["pairs_in_window"],
-            "warp_instr_per_launch": winstr,
-            "issue_slot_frac": winstr / (pair_ms_avg * 1e-3) / (148 * 4 * sm_hz),
-            "lsu_wavefronts_per_launch": lsu_wavefronts,
-            "lsu_pipe_frac": lsu_wavefronts / (pair_ms_avg * 1e-3) / (148 * sm_hz),
-            "source": "ncu counters of one launch (profiles/r01_ncu_pair_v12_summary.txt) / this "
-                      "run's kernel time; peaks: 1 warp-instr/clk/SMSP, 1 wavefront/clk/SM",
+            "warp_instr_per_launch": cnt.get("warp_instr"),
+            "issue_slot_frac": cnt["warp_instr"] / (pair_ms_avg * 1e-3) / (148 * 4 * sm_hz),
+            "lsu_wavefronts_per_launch": cnt.get("lsu_wavefronts"),
+            "lsu_pipe_frac": cnt["lsu_wavefronts"] / (pair_ms_avg * 1e-3) / (148 * sm_hz),
+            "source": cnt.get("source"), "capture_build": cnt.get("build"), "library_build": library_digest(),
+            "static": "counts are from the capture, not from this run; valid while the two builds match",
         }
 
-    # e2e through the host-pointer C ABI with pinned buffers
+    # ---- e2e: the call a user makes, host buffers in, host histograms out ----
     (hx, _kx), (hy, _ky), (ht, _kt), (hv, _kv) = pinned(x), pinned(y), pinned(t), pinned(v)
 
     def vario_e2e():
-        c, s = ctx.variogram_host(hx, hy, ht, hv, VARIO["space_dist_max"], VARIO["time_dist_max"], ns, nt,
-                                  part=rank, nparts=world)
-        return parallel.allreduce_histograms(c, s)
+        if world == 1:
+            return ctx.variogram_host(hx, hy, ht, hv, VARIO["space_dist_max"], VARIO["time_dist_max"], ns, nt)
+        return parallel.variogram_all_ranks(ctx, hx, hy, ht, hv, VARIO["space_dist_max"],
+                                            VARIO["time_dist_max"], ns, nt, 0, 0.0)
 
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(max(1, min(warmup, 3))):
         vario_e2e()
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         c_host, s_host = vario_e2e()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    assert int(c_host.sum()) == binned_total
+    env.barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0) / steps
+    assert np.array_equal(c_host.astype(np.int64).ravel(), g["counts"].ravel()), "e2e counts differ from the golden"
+    h2d = 4 * 8 * n if world == 1 else 4 * 8 * ((n + world - 1) // world)
     e2e = {"value": pairs / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 16 * ns * nt}
-
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 * nb,
+           "path": ("stif_variogram_host (pinned host arrays)" if world == 1 else
+                    "stif_b200.parallel.variogram_all_ranks: each rank uploads 1/N of the observations, "
+                    "NCCL all-gather over NVLink, stif_variogram_dev on its tile partition, one fused "
+                    "all-reduce, 14.4 KB read-back; h2d_bytes_per_step is per rank")}
+    spatial = n >= 160 * 1024
     out = {
         "metric": "variogram_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "strong" if workload == "c3" else "weak",
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": workload_name(workload),
             "n_obs": n, "pairs": pairs, "binned_pairs": binned_total,
             "l2": "256 MB device write between steps (outside the per-step CUDA-event pairs); "
                   "inputs (32 B/obs) are L2-resident by design",
-            "timing": "per-step CUDA events on torch's current stream, summed; max over ranks",
+            "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
             "parallelism": f"tile-pair partition x{world}",
+            "golden_check": {"file": f"tests/golden/variogram_{workload}.npz (oracle over all pairs)",
+                             "counts_bit_exact": counts_ok, "sums_max_rel_err": sums_rel},
         },
         "clocks": clocks, "e2e": e2e,
         # own kernels per step, time-sorted mode: pack_keys, gather, filter_setup, tile_range, scan,
         # pair, reduce; space-time sort mode (from 163 840 observations): bbox, spacetime_keys,
         # gather, filter_setup, tile_bbox, items (count), scan, items (fill), pair, reduce
         # (the CUB radix-sort passes in between are library launches and not counted)
-        "gpu_launches": (10 if n >= 160 * 1024 else 7) * args.steps,
+        "gpu_launches": (10 if spatial else 7) * steps,
         "roofline": roofline, "wall_s_bracket": wall_bracket,
     }
-
-    # ---------------- kriging (C4 share per GPU) ----------------
-    if not args.no_kriging:
-        out["kriging"] = run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier,
-                                          max_over_ranks, flush_l2, dfma_rate)
-
-    # ---------------- CPU baseline (rank 0, N = 1) ----------------
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_variogram_baseline(x, y, t, v, n)
-        if "kriging" in out:
-            out["kriging"]["cpu_baseline"] = cpu_kriging_baseline()
-    if rank == 0:
-        emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    del dx, dy, dt_, dv
+    return out, (x, y, t, v)
 
 
-def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, max_over_ranks, flush_l2,
-                     dfma_rate):
-    import torch
-    n_t = args.kriging_targets or C4_TARGETS_PER_GPU
-    steps = max(1, min(args.steps, args.kriging_steps))
-    (ox, oy, ot, oz), (tx, ty, tt) = synth_kriging(C4_OBS, n_t, rank)
+def bench_kriging(env, cfg, steps, warmup, n_targets=0):
+    torch = env.torch
+    ctx, rank, world, dev = env.ctx, env.rank, env.world, env.dev
+    n_t = n_targets or cfg["targets_per_gpu"]
+    k, (smax, tmax) = cfg["k"], cfg["radii"]
+    (ox, oy, ot, oz), (tx, ty, tt) = synth_kriging(cfg["n_obs"], n_t, rank, cfg["seed"], cfg["indicator"])
     ctx.kriging_set_obs(ox, oy, ot, oz)
-    ctx.kriging_set_model(*C4_MODEL, C4_PARAMS)
+    ctx.kriging_set_model(*cfg["model"], cfg["params"])
     dtx, dty, dtt = (torch.from_numpy(a).to(dev) for a in (tx, ty, tt))
     mean = torch.zeros(n_t, dtype=torch.float64, device=dev)
     std = torch.zeros(n_t, dtype=torch.float64, device=dev)
 
     def step():
-        ctx.kriging_predict_dev(dtx.data_ptr(), dty.data_ptr(), dtt.data_ptr(), n_t, 1, C4_K,
-                                C4_RADII[0], C4_RADII[1], mean.data_ptr(), std.data_ptr(), stream=stream)
+        ctx.kriging_predict_dev(dtx.data_ptr(), dty.data_ptr(), dtt.data_ptr(), n_t, 1, k,
+                                smax, tmax, mean.data_ptr(), std.data_ptr(), stream=env.stream)
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(warmup, 3))):
         step()
-    barrier()
-    sampler = ClockSampler(local_rank).start()
+    env.barrier()
+    sampler = ClockSampler(env.local_rank).start()
     tot_ms, search_ms, solve_ms = 0.0, 0.0, 0.0
     for _ in range(steps):
-        flush_l2()
+        env.flush_l2()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         step()
@@ -388,143 +444,175 @@ def run_kriging_b200(args, ctx, rank, local_rank, world, dev, stream, barrier, m
         ph = ctx.last_phase_ms()
         search_ms += ph[1]
         solve_ms += ph[2]
-    barrier()
+    env.barrier()
     clocks = sampler.stop()
-    ms_per_step = max_over_ranks(tot_ms) / steps
+    ms_per_step = env.max_over_ranks(tot_ms) / steps
     st = ctx.kriging_stats()
+    ss = ctx.kriging_solver_stats()
     cbar = st["candidates_in_window"] / n_t
-    flops = kriging_flops(C4_K, cbar)
-    solve_ms_avg = max_over_ranks(solve_ms) / steps
-    achieved = n_t * flops / (solve_ms_avg * 1e-3) / 1e12
-    peak_tf = 2 * dfma_rate / 1e12
+    f_search, f_solve = kriging_flops(k, cbar, cfg["f_gamma"])
+    solve_ms_avg = env.max_over_ranks(solve_ms) / steps
+    search_ms_avg = env.max_over_ranks(search_ms) / steps
+    # the assemble + solve kernel alone: its own flops (the gamma-vector work is the search kernel's)
+    achieved = n_t * f_solve / (solve_ms_avg * 1e-3) / 1e12
+    peak_tf = 2 * env.dfma_rate / 1e12
+    chol = bool(ss["cholesky_enabled"])
+    kname = "stif::krig::solve_chol_kernel" if chol else "stif::krig::solve_blk_kernel (pivoted LU)"
+    cnt = ncu_counters(("solve_chol_" if chol else "solve_lu_") + cfg["name"]) if world == 1 else None
 
     (hx, _a), (hy, _b), (ht, _c) = pinned(tx), pinned(ty), pinned(tt)
     (hm, _d), (hs, _e) = pinned(np.zeros(n_t)), pinned(np.zeros(n_t))      # pinned result buffers
-    ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1], out_mean=hm, out_std=hs)
-    barrier()
+    ctx.kriging_predict_host(hx, hy, ht, 1, k, smax, tmax, out_mean=hm, out_std=hs)
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        m_host, s_host = ctx.kriging_predict_host(hx, hy, ht, 1, C4_K, C4_RADII[0], C4_RADII[1],
-                                                  out_mean=hm, out_std=hs)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / steps
-    return {
+        m_host, s_host = ctx.kriging_predict_host(hx, hy, ht, 1, k, smax, tmax, out_mean=hm, out_std=hs)
+    env.barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0) / steps
+    out = {
         "metric": "kriging_predictions_per_s", "value": n_t * world / (ms_per_step * 1e-3),
         "unit": "predictions/s", "n_gpus": world, "steps": steps, "ms_per_step": ms_per_step,
-        "scaling": "weak", "dtype": "f64",
-        "config": {"workload": "C4 share: 1M observations (replicated), 1.25M targets per GPU, k=50, "
-                               "sum_metric/spherical, radii 30/30, float32-storage emulation on",
-                   "n_obs": C4_OBS, "targets_per_gpu": n_t, "k": C4_K,
+        "scaling": "weak", "dtype": "f64", "higher_is_better": True,
+        "config": {"workload": cfg["workload"], "n_obs": cfg["n_obs"], "targets_per_gpu": n_t, "k": k,
+                   "model": "/".join(cfg["model"]),
                    "candidates_per_target": cbar,
                    "candidates_examined_per_target": st["candidates_examined"] / n_t,
+                   "targets_rank_deficient": st["targets_singular"],
+                   "solver": "covariance-form Cholesky" if chol else "pivoted LU of the bordered system",
                    "l2": "256 MB device write between steps"},
-        "phases_ms": {"search": max_over_ranks(search_ms) / steps, "solve": solve_ms_avg},
+        "phases_ms": {"search": search_ms_avg, "solve": solve_ms_avg},
         "e2e": {"value": n_t * world / e2e_s, "unit": "predictions/s", "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t},
-        "gpu_launches": 5 * steps,
-        "roofline": {"bound": "fp64", "kernel": "stif::krig::solve_chol_kernel", "achieved": achieved,
+                "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t,
+                "path": "stif_kriging_predict_host (pinned host arrays), per rank"},
+        "gpu_launches": 6 * steps,     # target_keys, search, solve (Cholesky and/or LU), min-norm, stats
+        "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s per GPU", "frac": achieved / peak_tf,
-                     "flops_per_prediction": flops, "kernel_ms": solve_ms_avg,
-                     # dram read + write of one launch over 1.25M targets, ncu --set full
-                     # (profiles/r01_ncu_bench_v4_chol_summary.txt): selection scratch + gathers
-                     "traffic": (1261838848 if n_t == C4_TARGETS_PER_GPU else None),
-                     "traffic_unit": "bytes per launch (ncu capture, 1.25M targets)",
-                     "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)",
-                     "frac_incl_search": (n_t * flops / (ms_per_step * 1e-3) / 1e12) / peak_tf},
+                     "flops_per_prediction": f_solve,
+                     "flops_note": "SURVEY 8(d) assemble + solve share: k(k-1)/2 F_gamma + (k+1)^3/3 + 2(k+1)^2 "
+                                   "+ 4k (FMA = 2, sqrt = 1; an LU gets no credit for its extra n^3/3); the "
+                                   "gamma-vector share Cbar F_gamma belongs to the search kernel",
+                     "kernel_ms": solve_ms_avg,
+                     "frac_incl_search": (n_t * (f_search + f_solve) / (ms_per_step * 1e-3) / 1e12) / peak_tf,
+                     "flops_per_prediction_incl_search": f_search + f_solve,
+                     "traffic": (cnt or {}).get("dram_bytes"),
+                     "traffic_unit": "bytes per launch (ncu capture of this workload); algorithmic = 40 B "
+                                     f"per target = {40 * n_t}",
+                     "traffic_source": (cnt or {}).get("source"),
+                     "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)"},
         # neighbour search: candidates examined per second and the L2/HBM read rate
-        # that implies (32 B per candidate; the 32 MB observation set is L2-resident)
+        # that implies (bytes per candidate record x candidates; the observation set is L2-resident)
         "search": {"kernel": "stif::krig::search_kernel",
-                   "candidates_examined_per_s": st["candidates_examined"] / (max_over_ranks(search_ms) / steps * 1e-3),
-                   "read_GBps": 32.0 * st["candidates_examined"] / (max_over_ranks(search_ms) / steps * 1e-3) / 1e9,
+                   "candidates_examined_per_s": st["candidates_examined"] / (search_ms_avg * 1e-3),
+                   "read_GBps": 32.0 * st["candidates_examined"] / (search_ms_avg * 1e-3) / 1e9,
                    "hbm_peak_GBps": measured_hbm_gbs()},
         "clocks": clocks,
         "checksum": {"mean_sum": float(np.nansum(m_host)), "nan": int(np.isnan(m_host).sum())},
     }
+    del dtx, dty, dtt, mean, std
+    return out
+
+
+def run_b200(args):
+    env = Env(args)
+    out, vdata = bench_variogram(env, "c3", args.steps, args.warmup)
+    if env.world == 1 and not args.no_c2:
+        c2, c2data = bench_variogram(env, "c2", args.steps, args.warmup)
+        for key in ("n_gpus", "steps", "warmup", "higher_is_better", "vs_baseline", "dtype", "data", "wall_s_bracket"):
+            c2.pop(key, None)
+        out["c2"] = c2
+    if not args.no_kriging:
+        ksteps = max(1, min(args.steps, args.kriging_steps))
+        out["kriging"] = bench_kriging(env, KRIG["c4"], ksteps, args.warmup, args.kriging_targets)
+        out["kriging_c5"] = bench_kriging(env, KRIG["c5"], ksteps, args.warmup)
+    # ---------------- CPU baseline (rank 0, N = 1): the reference's numba path ----------------
+    if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_variogram_baseline(C3_N, 30_000)
+        if "c2" in out:
+            out["c2"]["cpu_baseline"] = dict(out["cpu_baseline"], note="same measurement as the C3 block: "
+                                             "the reference's rate per pair does not depend on n")
+        if "kriging" in out:
+            out["kriging"]["cpu_baseline"] = cpu_kriging_baseline(KRIG["c4"])
+            out["kriging_c5"]["cpu_baseline"] = cpu_kriging_baseline(KRIG["c5"])
+    if env.rank == 0:
+        emit(out)
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------
-# CPU oracle port (cpu_baseline leg and --impl reference)
+# The reference's CPU path (cpu_baseline leg and --impl reference): the unmodified numba package
+# vendored under oracle/_ref (oracle/refarm.py; falls back to the C port if it cannot be imported)
 # ----------------------------------------------------------------------------------------
-def cpu_variogram_baseline(x, y, t, v, n, target_pairs=1.2e9):
-    from oracle import variogram as ov
-    rows = int(min(n, max(1, target_pairs // n)))
-    space = np.column_stack([x, y])
-    ov.raw(space[:2000], t[:2000], v[:2000], 30.0, 30.0, 30, 30)          # warm
-    t0 = time.perf_counter()
-    h, c = ov.raw(space, t, v, VARIO["space_dist_max"], VARIO["time_dist_max"], 30, 30, i_begin=0, i_end=rows)
-    dt = time.perf_counter() - t0
-    sample_pairs = rows * n - rows * (rows + 1) // 2
-    return {"value": sample_pairs / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
-            "sample": f"rows 0..{rows} of the {n}-observation upper triangle = {sample_pairs} pairs in "
-                      f"{dt:.1f} s (the reference loop is serial: 1 core)",
-            "host_cores": os.cpu_count()}
+def cpu_variogram_baseline(n, n_sub, repeats=3):
+    from oracle import refarm
+    x, y, t, v = synth_variogram(n)
+    r = refarm.variogram_sample(x, y, t.astype(np.int64), v, n_sub, VARIO["space_dist_max"], 30, 30, 30,
+                                repeats=repeats)
+    total = sum(r["times"])
+    return {"value": r["pairs"] * repeats / total, "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
+            "what": r["what"], "jit_s": r["jit_s"], "host_cores": os.cpu_count(),
+            "sample": f"{repeats} x all {r['pairs']} pairs of the first {n_sub} of the {n} observations "
+                      f"(int64 days, the reference's dtypes) in {total:.1f} s; the rate per pair does not "
+                      "depend on n"}
 
 
-def cpu_kriging_baseline(n_targets=8000):
-    from oracle import kriging as ok
-    (ox, oy, ot, oz), (tx, ty, tt) = synth_kriging(C4_OBS, n_targets, 0)
-    space = np.column_stack([ox, oy])
-    tsp = np.column_stack([tx, ty])
-    threads = os.cpu_count() or 1
-    ok.predict(space[:5000], ot[:5000], oz[:5000], tsp[:16], tt[:16], C4_MODEL, C4_PARAMS, 1, C4_K, 30.0, 30.0)
-    t0 = time.perf_counter()
-    ok.predict(space, ot, oz, tsp, tt, C4_MODEL, C4_PARAMS, 1, C4_K, C4_RADII[0], C4_RADII[1], n_threads=threads)
-    dt = time.perf_counter() - t0
-    return {"value": n_targets / dt, "unit": "predictions/s", "cores": threads, "kind": "port",
-            "sample": f"{n_targets} targets against all 1M observations (dense filter like "
-                      f"Data.get_kriging_idxs, dgelsd solve) in {dt:.1f} s"}
+def cpu_kriging_baseline(cfg):
+    from oracle import refarm
+    obs, tg = synth_kriging(cfg["n_obs"], cfg["cpu_targets"], 0, cfg["seed"], cfg["indicator"])
+    r = refarm.kriging_sample(obs, tg, cfg["model"], cfg["params"], cfg["k"], cfg["radii"][0], cfg["radii"][1],
+                              batch_size=cfg["cpu_batch"])
+    return {"value": r["n"] / r["time"], "unit": "predictions/s", "cores": r["cores"], "kind": r["kind"],
+            "what": r["what"], "jit_s": r["jit_s"], "host_cores": os.cpu_count(),
+            "sample": f"{r['n']} targets against all {cfg['n_obs']} observations, k={cfg['k']}, in {r['time']:.1f} s"}
 
 
 def run_reference(args):
-    """--impl reference: the CPU oracle port of the reference's path on the host cores."""
+    """--impl reference: the reference's own numba implementation of the path on the host cores,
+    on the B200 arm's config / metric / unit; every step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    workload = args.workload
-    if workload == "auto":
-        workload = "c2" if world == 1 else "c3"
-    n = C2_N if workload == "c2" else C3_N
+    from oracle import refarm
+    n = C3_N
     x, y, t, v = synth_variogram(n)
-    from oracle import variogram as ov
-    space = np.column_stack([x, y])
-    per_step_pairs = 3e8 if args.steps > 3 else 1e9
-    rows = int(max(1, per_step_pairs // n))
-    for _ in range(min(args.warmup, 2)):
-        ov.raw(space, t, v, 30.0, 30.0, 30, 30, i_begin=0, i_end=max(1, rows // 10))
-    t0 = time.perf_counter()
+    ti = t.astype(np.int64)
+    n_sub = 20_000 if args.steps > 3 else 40_000       # 2e8 / 8e8 pairs per step: ~1.6 / 6.4 s
+    w = refarm.variogram_sample(x, y, ti, v, 2000, VARIO["space_dist_max"], 30, 30, 30, repeats=max(1, args.warmup))
+    times, pairs_done = [], 0
     for s in range(args.steps):
-        b = (s * rows) % max(1, n // 2)
-        ov.raw(space, t, v, VARIO["space_dist_max"], VARIO["time_dist_max"], 30, 30, i_begin=b, i_end=b + rows)
-    dt = time.perf_counter() - t0
-    sample_pairs = 0
-    for s in range(args.steps):
-        b = (s * rows) % max(1, n // 2)
-        sample_pairs += sum(n - 1 - i for i in range(b, min(b + rows, n)))
-    rate = sample_pairs / dt
+        # a different window of the observations every step
+        b = (s * n_sub) % (n - n_sub)
+        r = refarm.variogram_sample(x[b:], y[b:], ti[b:], v[b:], n_sub, VARIO["space_dist_max"], 30, 30, 30)
+        times.append(r["times"][0])
+        pairs_done += r["pairs"]
+    dt = sum(times)
+    rate = pairs_done / dt
     pairs = n * (n - 1) // 2
     out = {
         "impl": "reference", "metric": "variogram_pairs_per_s", "value": rate, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": pairs / rate * 1e3, "higher_is_better": True,
-        "scaling": "strong" if workload == "c3" else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": workload_name(workload),
-                   "n_obs": n, "pairs": pairs,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name("c3"), "n_obs": n, "pairs": pairs,
                    "note": "ms_per_step is the full workload extrapolated from the measured per-pair "
-                           "rate (rate is N-independent); each timed step is a bounded sample"},
-        "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": 1, "kind": "port",
-                         "sample": f"{args.steps} steps x {rows} rows of the upper triangle "
-                                   f"({sample_pairs} pairs, {dt:.1f} s); serial like the reference loop"},
+                           "rate (the rate does not depend on n); each timed step is a bounded sample"},
+        "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
+                         "jit_s": w["jit_s"], "host_cores": os.cpu_count(),
+                         "sample": f"{args.steps} steps x all pairs of {n_sub} consecutive observations of the "
+                                   f"workload ({pairs_done} pairs, {dt:.1f} s)"},
         "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if not args.no_kriging:
-        kb = cpu_kriging_baseline(n_targets=8000)
-        out["kriging"] = {"impl": "reference", "metric": "kriging_predictions_per_s", "value": kb["value"],
-                          "unit": "predictions/s", "cpu_baseline": kb,
-                          "e2e": {"value": kb["value"], "unit": "predictions/s", "h2d_bytes_per_step": 0,
-                                  "d2h_bytes_per_step": 0}}
+        for key in ("c4", "c5"):
+            cfg = KRIG[key]
+            kb = cpu_kriging_baseline(cfg)
+            out[cfg["name"]] = {"impl": "reference", "metric": "kriging_predictions_per_s", "value": kb["value"],
+                                "unit": "predictions/s", "higher_is_better": True,
+                                "config": {"workload": cfg["workload"]}, "cpu_baseline": kb,
+                                "e2e": {"value": kb["value"], "unit": "predictions/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0}}
     emit(out)
 
 
@@ -554,7 +642,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"])
+    ap.add_argument("--no-c2", action="store_true", help="skip the C2 block (N = 1)")
     ap.add_argument("--no-kriging", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kriging-steps", type=int, default=3)

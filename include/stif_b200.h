@@ -35,6 +35,9 @@ extern "C" {
 #define STIF_ENOMEM (-3)     /* device allocation failed          -> MemoryError       */
 #define STIF_ESTATE (-4)     /* call-order misuse (no obs/model)  -> ValueError        */
 #define STIF_ENONFINITE (-5) /* non-finite kriging system         -> LinAlgError       */
+/* STIF_ENONFINITE is returned by stif_kriging_predict_host when a kriging system holds NaN or
+ * Inf: the reference's lstsq raises np.linalg.LinAlgError there (stif/predictor.py:587, numba's
+ * _check_finite_matrix).  The outputs are still written (NaN for the affected targets). */
 
 typedef struct stif_ctx stif_ctx;
 
@@ -81,6 +84,9 @@ int stif_sm_count(stif_ctx *ctx);
 #define STIF_VARIO_NO_CULL 2
 #define STIF_VARIO_SPACE_SORT 4
 #define STIF_VARIO_TIME_SORT 8
+#define STIF_VARIO_COUNTS_F64 16 /* _dev only: counts_dev receives float64 values (exact below 2^53,
+                                    the dtype of the reference's own `norm`), so that counts and sums
+                                    of all ranks meet in ONE all-reduce of one float64 buffer */
 
 int stif_variogram_dev(stif_ctx *ctx, const double *x, const double *y, const double *t,
                        const double *v, int64_t n, double space_dist_max,
@@ -217,7 +223,8 @@ int stif_kriging_predict_dev(stif_ctx *ctx, const double *tx, const double *ty,
 /* Statistics of the last kriging call (after a synchronise):
  * out[0] = candidates examined by the neighbour search, out[1] = candidates inside the
  * search window, out[2] = targets with fewer than min_pts candidates,
- * out[3] = targets whose system was flagged singular / non-finite (NaN result). */
+ * out[3] = targets whose system was rank-deficient (duplicate / co-located observations with a
+ *          zero total nugget): they are solved by the minimum-norm path. */
 int stif_kriging_stats(stif_ctx *ctx, uint64_t out[4]);
 
 /* out[0] = targets of the last call that the covariance-form Cholesky kernel handed to the
@@ -230,6 +237,13 @@ int stif_kriging_solver_stats(stif_ctx *ctx, uint64_t out[2]);
  * kriging: [0]=grid build [1]=neighbour search [2]=assemble+solve [3]=epilogue.
  * Synchronises the stream. */
 int stif_last_phase_ms(stif_ctx *ctx, float out[4]);
+
+/* Test hook: the device implementation of numpy's pairwise row summation that the float32-storage
+ * epilogue uses for np.sum(kriging_weights * residuals[idx], axis=1) and
+ * np.sum(kriging_weights * kriging_vectors, axis=1) (stif/predictor.py:900-905), applied to n_rows
+ * rows of k elements (host pointers; float32 if is_f32 else float64; k <= 128).  Lets the tests
+ * compare the DEVICE code with np.sum bit for bit. */
+int stif_debug_numpy_row_sum(stif_ctx *ctx, const void *rows, int n_rows, int k, int is_f32, void *out);
 
 /* ---- measurement helpers ------------------------------------------------------ */
 

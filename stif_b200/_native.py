@@ -22,6 +22,7 @@ VARIO_PEEL = 1
 VARIO_NO_CULL = 2
 VARIO_SPACE_SORT = 4   # force the space-time sort mode (default: from 163 840 observations)
 VARIO_TIME_SORT = 8    # forbid it
+VARIO_COUNTS_F64 = 16  # variogram_dev: counts written as float64 (one fused all-reduce buffer)
 KRIG_F32_STORAGE = 1
 KRIG_FORCE_LU = 2
 KRIG_TRY_CHOL = 4
@@ -75,6 +76,7 @@ SIGNATURES = {
     "stif_kriging_predict_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                                 ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "stif_debug_numpy_row_sum": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "stif_kriging_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "stif_kriging_solver_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "stif_last_phase_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -344,6 +346,17 @@ class Context:
         out = (ctypes.c_uint64 * 2)()
         _check(self._lib.stif_kriging_solver_stats(self._h, out), "stif_kriging_solver_stats")
         return {"cholesky_to_lu": int(out[0]), "cholesky_enabled": bool(out[1])}
+
+    def debug_numpy_row_sum(self, rows):
+        """np.sum(rows, axis=1) by the DEVICE summation code of the float32-storage epilogue."""
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype not in (np.float32, np.float64) or rows.ndim != 2:
+            raise ValueError("rows must be a 2-D float32 or float64 array")
+        out = np.empty(rows.shape[0], dtype=rows.dtype)
+        _check(self._lib.stif_debug_numpy_row_sum(self._h, _ptr(rows), rows.shape[0], rows.shape[1],
+                                                  int(rows.dtype == np.float32), _ptr(out)),
+               "stif_debug_numpy_row_sum")
+        return out
 
     # ---- measurement -------------------------------------------------------------
     def last_phase_ms(self):

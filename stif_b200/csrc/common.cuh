@@ -110,6 +110,7 @@ struct stif_ctx {
     stif::DevBuf k_scratch[16];
     stif::DevBuf k_stats;
     uint64_t k_stats_host[4] = {0, 0, 0, 0};
+    unsigned long long *k_stats_pinned = nullptr;   // [8] statistics of the last host call (pinned)
     int k_chol_enabled = 0;    // last predict call tried the covariance-form kernel
     // grid cache key
     double grid_smax = -1, grid_tmax = -1;

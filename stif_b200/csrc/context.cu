@@ -106,6 +106,7 @@ int stif_ctx_destroy(stif_ctx *c)
     c->k_pairs_cnt.release();
     c->k_fit.release();
     if (c->fit_out_host) cudaFreeHost(c->fit_out_host);
+    if (c->k_stats_pinned) cudaFreeHost(c->k_stats_pinned);
     c->k_stats.release();
     for (auto &b : c->k_scratch) b.release();
     for (int i = 0; i < 6; ++i)

@@ -758,7 +758,9 @@ struct SolveParams {
     float *w_out, *g_out;        // nullable, [n_targets][k]
     unsigned *idx_out;           // nullable
     int *nused_out;              // nullable
-    unsigned *singular;          // [n] chunk-local flag
+    unsigned *singular;          // [n] chunk-local flag (bit 0 rank-deficient, bit 1 non-finite)
+    unsigned *sing_list;         // rank-deficient targets (chunk-local ids) for the minimum-norm kernel
+    unsigned *sing_count;
     const unsigned *count;       // nullable: number of entries of `order` to process (device)
     const double4 *obs4;         // observations {x, y, t, resid}, original order
     const unsigned *pairtab;     // pair e -> a | b << 8 | ... (b < a), see CholParams::pairtab
@@ -794,6 +796,14 @@ __device__ T numpy_row_sum(const T *a, int n)
         for (; i < n; ++i) res = res + a[i];
     }
     return (T)0 + res;
+}
+
+// Test hook (stif_debug_numpy_row_sum): one thread per row runs the device summation.
+template <typename T>
+__global__ void row_sum_kernel(const T *rows, int n_rows, int k, T *out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) out[r] = numpy_row_sum<T>(rows + (size_t)r * k, k);
 }
 
 // ---- solve: shared pieces ------------------------------------------------------------
@@ -859,8 +869,9 @@ struct LuPrefetch {
 // Returns m (neighbours used); m <= 0 means the outputs were written (zeros) and the CTA is done.
 template <int NT, int LUV>
 __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, const LuPrefetch &F, int64_t tg,
-                           int tid, int nr, int nc)
+                           int tid, int nr, int nc, bool &nonfinite)
 {
+    nonfinite = false;
     const int k = P.k, ld = P.ld;
     double *A = S.A;
     const int m = F.m;
@@ -902,6 +913,9 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, const LuPre
     // gamma matrix, predictor.py:573-575 (diagonal = gamma(0,0), no special case)
     const double gdiag = gamma_st(P.M, 0.0, 0.0);
     double amax = fmax(fabs(gdiag), 1.0);   // largest |entry| (the border holds ones)
+    // NaN / Inf anywhere in [A | b]: the reference's lstsq raises LinAlgError (numba
+    // _check_finite_matrix, predictor.py:587); flagged here, reported by the host entry point
+    bool bad = !(fabs(gdiag) < INFINITY) || (tid < m && !(fabs(F.g) < INFINITY));
     for (int e = tid; e < m; e += NT) A[e * ld + e] = gdiag;
     const int npairs = m * (m - 1) / 2;
     for (int e = tid; e < npairs; e += NT) {
@@ -924,12 +938,13 @@ __device__ int solve_setup(const SolveParams &P, const SolveSmem &S, const LuPre
         A[a * ld + b] = g;
         A[b * ld + a] = g;
         amax = fmax(amax, fabs(g));         // fmax ignores NaN
+        bad = bad || !(fabs(g) < INFINITY);
     }
     {
         const unsigned long long wm = warp_max_u64((unsigned long long)__double_as_longlong(amax));
         if ((tid & 31) == 0) atomicMax(S.scale, wm);
     }
-    __syncthreads();
+    nonfinite = __syncthreads_or(bad ? 1 : 0) != 0;
     return m;
 }
 
@@ -999,7 +1014,7 @@ __device__ void solve_epilogue(const SolveParams &P, const double *sol, const do
 // Back substitution of the LU (warp 0; column oriented: x_j = b_j * (1/U_jj), then
 // b_r -= U_rj x_j for r < j), then the epilogue.
 __device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, unsigned tl, int64_t tg,
-                             int lane, bool singular)
+                             int lane, bool singular, bool nonfinite)
 {
     const int ld = P.ld, n = m + 1;
     double *A = S.A, *sol = S.sol;
@@ -1009,7 +1024,11 @@ __device__ void solve_finish(const SolveParams &P, const SolveSmem &S, int m, un
         if (lane == 0) sol[j] = xj;
         __syncwarp();
     }
-    if (lane == 0 && singular) P.singular[tl] = 1u;
+    // bit 0: rank-deficient (a pivot below the tolerance); bit 1: NaN / Inf in the system
+    if (lane == 0 && (singular || nonfinite)) {
+        P.singular[tl] = nonfinite ? 2u : 1u;
+        if (!nonfinite) P.sing_list[atomicAdd(P.sing_count, 1u)] = tl;
+    }
     solve_epilogue(P, sol, S.g0, S.ids, nullptr, S.xs, reinterpret_cast<float *>(S.ys),
                    reinterpret_cast<float *>(S.ts), m, tg, lane);
 }
@@ -1071,7 +1090,8 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
         const int64_t tg = P.c0 + tl;
         has_next = slot + (int)gridDim.x < n_work;
         if (has_next) N.tl = P.order[slot + gridDim.x];
-        const int m = solve_setup<NT, LUV>(P, S, F, tg, tid, nr, nc);
+        bool nonfinite = false;
+        const int m = solve_setup<NT, LUV>(P, S, F, tg, tid, nr, nc, nonfinite);
         fetch_ids();
         if (m <= 0) {
             fetch_obs();
@@ -1196,38 +1216,187 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
             __syncthreads();
         }
         fetch_obs();
-        if (warp == 0) solve_finish(P, S, m, tl, tg, lane, singular);
+        if (warp == 0) solve_finish(P, S, m, tl, tg, lane, singular, nonfinite);
+    }
+}
+
+// ---- minimum-norm solve of rank-deficient systems ------------------------------------------
+// The reference solves every system with np.linalg.lstsq = LAPACK dgelsd (SVD, rcond = eps),
+// which returns the MINIMUM-NORM solution when [Gamma 1; 1' 0] is rank-deficient -- duplicate or
+// co-located observations make two rows equal whatever the nugget, because the reference puts
+// gamma(0, 0) on the diagonal (stif/predictor.py:573-587).  Targets the pivoted LU flags (a pivot
+// below n * 8 eps * max|entry|) are re-solved here the same way: one-sided Jacobi (Hestenes) SVD
+// of the symmetric matrix, G = A V with orthogonal columns g_j = sigma_j u_j, then
+//      x = sum over sigma_j > thr * sigma_max of  v_j (g_j . b) / sigma_j^2.
+// One CTA per target; G lives in shared memory (column-major), V in a global scratch slab.
+// A rare path (statistics out[3] counts it): clarity over speed.
+constexpr int MN_THREADS = 128;
+
+__global__ void __launch_bounds__(MN_THREADS) solve_minnorm_kernel(SolveParams P, double *vscratch)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    constexpr int NW = MN_THREADS / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = P.k, nmax = k + 1;
+    double *G = smem_d;                       // [n][n] column-major
+    double *xs = G + (size_t)nmax * nmax, *ys = xs + nmax, *ts = ys + nmax, *rs = ts + nmax;
+    double *g0 = rs + nmax, *bv = g0 + nmax, *sol = bv + nmax, *coef = sol + nmax, *alpha = coef + nmax;
+    double *sc64 = alpha + nmax;
+    float *sc32 = reinterpret_cast<float *>(sc64 + nmax);
+    unsigned *ids = reinterpret_cast<unsigned *>(sc32 + 2 * nmax);
+    double *V = vscratch + (size_t)blockIdx.x * nmax * nmax;
+    const int n_work = (int)*P.sing_count;
+    const double gdiag = gamma_st(P.M, 0.0, 0.0);
+    for (int slot = blockIdx.x; slot < n_work; slot += gridDim.x) {
+        __syncthreads();
+        const unsigned tl = P.sing_list[slot];
+        const int64_t tg = P.c0 + tl;
+        const int m = P.sel_n[tl];
+        if (m <= 0) continue;
+        const int n = m + 1;
+        for (int e = tid; e < m; e += MN_THREADS) {
+            const unsigned id = P.sel_idx[(size_t)tl * k + e];
+            const double4 o = P.obs4[id];
+            ids[e] = id;
+            xs[e] = o.x;
+            ys[e] = o.y;
+            ts[e] = o.z;
+            rs[e] = o.w;
+            g0[e] = P.sel_gamma[(size_t)tl * k + e];
+            bv[e] = g0[e];
+        }
+        if (tid == 0) bv[m] = 1.0;
+        __syncthreads();
+        // the reference's matrix verbatim (predictor.py:573-580, utils.py:19-22, :40-44)
+        for (int e = tid; e < n * n; e += MN_THREADS) {
+            const int c = e / n, r = e - c * n;
+            double val;
+            if (r == m || c == m) val = (r == c) ? 0.0 : 1.0;
+            else if (r == c) val = gdiag;
+            else {
+                const double dx = xs[r] - xs[c], dy = ys[r] - ys[c];
+                val = gamma_st(P.M, sqrt(dx * dx + dy * dy), fabs(ts[r] - ts[c]));
+            }
+            G[e] = val;
+            V[e] = (r == c) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        double fro2 = 0.0;
+        for (int e = tid; e < n * n; e += MN_THREADS) fro2 = __fma_rn(G[e], G[e], fro2);
+        for (int off = 16; off > 0; off >>= 1) fro2 += __shfl_xor_sync(FULL, fro2, off);
+        if (lane == 0) alpha[warp] = fro2;
+        __syncthreads();
+        fro2 = 0.0;
+        for (int w = 0; w < NW; ++w) fro2 += alpha[w];
+        __syncthreads();
+        const int ne = n + (n & 1), half = ne >> 1;
+        for (int sweep = 0; sweep < 60; ++sweep) {
+            bool rotated = false;
+            for (int round = 0; round < ne - 1; ++round) {
+                for (int i = warp; i < half; i += NW) {      // round-robin tournament: disjoint pairs
+                    int p = (i == 0) ? ne - 1 : (round + i) % (ne - 1);
+                    int q = (i == 0) ? round : (round + (ne - 1) - i) % (ne - 1);
+                    if (p >= n || q >= n) continue;
+                    if (p > q) { const int tmp = p; p = q; q = tmp; }
+                    double *gp = G + (size_t)p * n, *gq = G + (size_t)q * n;
+                    double a = 0.0, b = 0.0, g = 0.0;
+                    for (int r = lane; r < n; r += 32) {
+                        const double u = gp[r], v = gq[r];
+                        a = __fma_rn(u, u, a);
+                        b = __fma_rn(v, v, b);
+                        g = __fma_rn(u, v, g);
+                    }
+                    for (int off = 16; off > 0; off >>= 1) {
+                        a += __shfl_xor_sync(FULL, a, off);
+                        b += __shfl_xor_sync(FULL, b, off);
+                        g += __shfl_xor_sync(FULL, g, off);
+                    }
+                    if (!(fabs(g) > 8e-15 * sqrt(a * b)) || !(fabs(g) > 1e-31 * fro2)) continue;
+                    rotated = true;
+                    const double zeta = (b - a) / (2.0 * g);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    double *vp = V + (size_t)p * n, *vq = V + (size_t)q * n;
+                    for (int r = lane; r < n; r += 32) {
+                        const double u = gp[r], v = gq[r];
+                        gp[r] = cs * u - sn * v;
+                        gq[r] = sn * u + cs * v;
+                        const double vu = vp[r], vv = vq[r];
+                        vp[r] = cs * vu - sn * vv;
+                        vq[r] = sn * vu + cs * vv;
+                    }
+                }
+                __syncthreads();
+            }
+            if (!__syncthreads_or(rotated ? 1 : 0)) break;
+        }
+        // sigma_j^2 and g_j . b
+        for (int j = warp; j < n; j += NW) {
+            const double *gj = G + (size_t)j * n;
+            double a = 0.0, d = 0.0;
+            for (int r = lane; r < n; r += 32) {
+                a = __fma_rn(gj[r], gj[r], a);
+                d = __fma_rn(gj[r], bv[r], d);
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                a += __shfl_xor_sync(FULL, a, off);
+                d += __shfl_xor_sync(FULL, d, off);
+            }
+            if (lane == 0) {
+                alpha[j] = a;
+                coef[j] = d;
+            }
+        }
+        __syncthreads();
+        double amax = 0.0;
+        for (int j = 0; j < n; ++j) amax = fmax(amax, alpha[j]);
+        const double thr = 1.8e-15 * (double)n;               // the LU's rank tolerance
+        const double cut = amax * thr * thr;
+        __syncthreads();
+        for (int j = tid; j < n; j += MN_THREADS) coef[j] = (alpha[j] > cut) ? coef[j] / alpha[j] : 0.0;
+        __syncthreads();
+        for (int r = tid; r < m; r += MN_THREADS) {
+            double acc = 0.0;
+            for (int j = 0; j < n; ++j) acc = __fma_rn(V[(size_t)j * n + r], coef[j], acc);
+            sol[r] = acc;
+        }
+        __syncthreads();
+        if (warp == 0)
+            solve_epilogue(P, sol, g0, ids, rs, sc64, sc32, sc32 + nmax, m, tg, lane);
     }
 }
 
 #include "krig_chol.cuh"
 
-// stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += sum(singular),
-// [4] += targets the covariance-form kernel handed to the pivoted LU
+// stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += #(rank-deficient),
+// [4] += targets the covariance-form kernel handed to the pivoted LU, [5] += #(non-finite systems)
 __global__ void stats_kernel(const unsigned *exam_n, const unsigned *cand_n, const int *sel_n,
                              const unsigned *singular, int n, const unsigned *fail_count,
                              unsigned long long *stats)
 {
     if (fail_count && blockIdx.x == 0 && threadIdx.x == 0 && *fail_count)
         atomicAdd(&stats[4], (unsigned long long)*fail_count);
-    unsigned long long a = 0, b = 0, c = 0, d = 0;
+    unsigned long long a = 0, b = 0, c = 0, d = 0, f = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         a += exam_n[i];
         b += cand_n[i];
         c += sel_n[i] < 0 ? 1 : 0;
-        d += singular[i];
+        d += singular[i] & 1u;
+        f += (singular[i] >> 1) & 1u;
     }
     for (int off = 16; off > 0; off >>= 1) {
         a += __shfl_xor_sync(FULL, a, off);
         b += __shfl_xor_sync(FULL, b, off);
         c += __shfl_xor_sync(FULL, c, off);
         d += __shfl_xor_sync(FULL, d, off);
+        f += __shfl_xor_sync(FULL, f, off);
     }
     if ((threadIdx.x & 31) == 0) {
         if (a) atomicAdd(&stats[0], a);
         if (b) atomicAdd(&stats[1], b);
         if (c) atomicAdd(&stats[2], c);
         if (d) atomicAdd(&stats[3], d);
+        if (f) atomicAdd(&stats[5], f);
     }
 }
 
@@ -1481,7 +1650,7 @@ namespace {
 
 enum Scratch {
     S_GRIDHDR = 0, S_OKEYS, S_OIDX, S_OKEYS_S, S_OIDX_S, S_CUB, S_OBS_SORTED, S_CELL_START,
-    S_TKEYS, S_TFLAGS, S_SEL_IDX, S_SEL_GAMMA, S_STAGE, S_EVAL, S_FAIL
+    S_TKEYS, S_TFLAGS, S_SEL_IDX, S_SEL_GAMMA, S_STAGE, S_EVAL, S_FAIL, S_MINNORM
 };
 
 int check_ctx(stif_ctx *c, const char *who)
@@ -1494,6 +1663,30 @@ int check_ctx(stif_ctx *c, const char *who)
     if (e != cudaSuccess) {
         set_error("%s: cudaSetDevice(%d): %s", who, c->device, cudaGetErrorString(e));
         return STIF_ECUDA;
+    }
+    return STIF_OK;
+}
+
+// The call's statistics travel to a pinned host buffer behind the results (no extra round trip).
+int stats_to_host(stif_ctx *c, cudaStream_t st)
+{
+    if (!c->k_stats_pinned)
+        STIF_CUDA(cudaHostAlloc(&c->k_stats_pinned, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    STIF_CUDA(cudaMemcpyAsync(c->k_stats_pinned, c->k_stats.p, 8 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+    return STIF_OK;
+}
+
+// The reference raises np.linalg.LinAlgError when a kriging system holds NaN / Inf (numba's
+// lstsq checks the matrix, stif/predictor.py:587).  The outputs are complete (NaN for those
+// targets); the code tells the caller.
+int nonfinite_check(stif_ctx *c)
+{
+    const unsigned long long bad = c->k_stats_pinned ? c->k_stats_pinned[5] : 0ull;
+    if (bad) {
+        set_error("stif_kriging_predict: %llu kriging system(s) contain NaN or Inf "
+                  "(check the coordinates, the times and the variogram-model parameters)", bad);
+        return STIF_ENONFINITE;
     }
     return STIF_OK;
 }
@@ -1740,7 +1933,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     STIF_TRY(c->k_scratch[S_TFLAGS].reserve(4 * 4 * (size_t)chunk));
     STIF_TRY(c->k_scratch[S_SEL_IDX].reserve(4 * (size_t)chunk * k));
     STIF_TRY(c->k_scratch[S_SEL_GAMMA].reserve(8 * (size_t)chunk * k));
-    STIF_TRY(c->k_scratch[S_FAIL].reserve(4 * (size_t)(chunk + 1)));
+    STIF_TRY(c->k_scratch[S_FAIL].reserve(4 * (2 * (size_t)chunk + 2)));
     unsigned *tkeys = c->k_scratch[S_TKEYS].as<unsigned>();
     unsigned *tidx = tkeys + chunk, *tkeys_s = tidx + chunk, *tidx_s = tkeys_s + chunk;
     int *sel_n = c->k_scratch[S_TFLAGS].as<int>();
@@ -1823,6 +2016,9 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         // ---- covariance-form Cholesky (valid models), then the pivoted LU for the rest ----
         unsigned *fail_list = c->k_scratch[S_FAIL].as<unsigned>();
         unsigned *fail_count = fail_list + chunk;
+        QP.sing_list = fail_count + 1;
+        QP.sing_count = QP.sing_list + chunk;
+        STIF_CUDA(cudaMemsetAsync(QP.sing_count, 0, sizeof(unsigned), st));
         if (chol_var >= 0) {
             STIF_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(unsigned), st));
             CX.fail_list = fail_list;
@@ -1895,6 +2091,17 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
 #undef STIF_SOLVE_V
         }
         STIF_CUDA(cudaGetLastError());
+        {   // rank-deficient systems (flagged by the LU): minimum-norm solution like dgelsd
+            const int nmax = k + 1;
+            const size_t mn_smem = sizeof(double) * ((size_t)nmax * nmax + 10 * (size_t)nmax) +
+                                   sizeof(float) * 2 * (size_t)nmax + sizeof(unsigned) * (size_t)nmax;
+            int mn_grid = c->sm_count < nc ? c->sm_count : nc;
+            STIF_TRY(c->k_scratch[S_MINNORM].reserve(sizeof(double) * (size_t)mn_grid * nmax * nmax));
+            STIF_CUDA(cudaFuncSetAttribute(solve_minnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)mn_smem));
+            solve_minnorm_kernel<<<mn_grid, MN_THREADS, mn_smem, st>>>(QP, c->k_scratch[S_MINNORM].as<double>());
+            STIF_CUDA(cudaGetLastError());
+        }
         stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,
                                                  chol_var >= 0 ? fail_count : nullptr,
                                                  c->k_stats.as<unsigned long long>());
@@ -1988,6 +2195,7 @@ extern "C" int stif_kriging_predict_host(stif_ctx *c, const double *tx, const do
             if (ci > 0) rc = d2h(ci - 1);
         }
         if (rc == STIF_OK) rc = d2h(nchunk - 1);
+        if (rc == STIF_OK) rc = stats_to_host(c, st);
         cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
         for (int i = 0; i < nchunk; ++i) {
             cudaEventDestroy(ev_h[i]);
@@ -1997,7 +2205,7 @@ extern "C" int stif_kriging_predict_host(stif_ctx *c, const double *tx, const do
         STIF_CUDA(e1);
         STIF_CUDA(e2);
         STIF_CUDA(cudaGetLastError());
-        return STIF_OK;
+        return nonfinite_check(c);
     }
     STIF_CUDA(cudaMemcpyAsync(b + o_tx, tx, 8 * N, cudaMemcpyHostToDevice, st));
     STIF_CUDA(cudaMemcpyAsync(b + o_ty, ty, 8 * N, cudaMemcpyHostToDevice, st));
@@ -2015,7 +2223,31 @@ extern "C" int stif_kriging_predict_host(stif_ctx *c, const double *tx, const do
     if (gamma_out) STIF_CUDA(cudaMemcpyAsync(gamma_out, b + o_g, 4 * N * k, cudaMemcpyDeviceToHost, st));
     if (idx_out) STIF_CUDA(cudaMemcpyAsync(idx_out, b + o_idx, 4 * N * k, cudaMemcpyDeviceToHost, st));
     if (n_used_out) STIF_CUDA(cudaMemcpyAsync(n_used_out, b + o_nu, 4 * N, cudaMemcpyDeviceToHost, st));
+    STIF_TRY(stats_to_host(c, st));
     STIF_CUDA(cudaStreamSynchronize(st));
+    return nonfinite_check(c);
+}
+
+extern "C" int stif_debug_numpy_row_sum(stif_ctx *c, const void *rows, int n_rows, int k, int is_f32,
+                                        void *out)
+{
+    STIF_TRY(check_ctx(c, "stif_debug_numpy_row_sum"));
+    if (!rows || !out || n_rows < 1 || k < 1 || k > KMAX) {
+        set_error("stif_debug_numpy_row_sum: bad arguments (n_rows=%d, k=%d)", n_rows, k);
+        return STIF_EINVAL;
+    }
+    const size_t es = is_f32 ? 4 : 8, in_bytes = es * (size_t)n_rows * k, out_bytes = es * (size_t)n_rows;
+    STIF_TRY(c->k_scratch[S_EVAL].reserve(in_bytes + out_bytes + 256));
+    char *d_in = c->k_scratch[S_EVAL].as<char>(), *d_out = d_in + (in_bytes + 255) / 256 * 256;
+    STIF_CUDA(cudaMemcpyAsync(d_in, rows, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)((n_rows + 127) / 128);
+    if (is_f32)
+        row_sum_kernel<float><<<grid, 128, 0, c->stream>>>((const float *)d_in, n_rows, k, (float *)d_out);
+    else
+        row_sum_kernel<double><<<grid, 128, 0, c->stream>>>((const double *)d_in, n_rows, k, (double *)d_out);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    STIF_CUDA(cudaStreamSynchronize(c->stream));
     return STIF_OK;
 }
 

@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
 // Fixed-order reduction over the per-block partials + the reference's peeled first pair.
 __global__ void __launch_bounds__(1024) reduce_kernel(Params P, int nblocks, const double *x, const double *y,
                               const double *t, const double *v, int64_t n, double smax,
-                              double ws, double wt, int peel, unsigned long long *counts,
+                              double ws, double wt, int peel, int counts_f64, unsigned long long *counts,
                               double *sums)
 {
     // 1024 threads = 32 bins x 32 slices of the block list: slice s adds the partials of blocks
@@ -891,7 +891,10 @@ __global__ void __launch_bounds__(1024) reduce_kernel(Params P, int nblocks, con
             }
         }
     }
-    counts[b] = c;
+    // counts as float64 (exact below 2^53; the reference's own `norm` array is float64): lets a
+    // multi-GPU caller sum counts and sums with ONE all-reduce over one float64 buffer
+    if (counts_f64) reinterpret_cast<double *>(counts)[b] = (double)c;
+    else counts[b] = c;
     sums[b] = s;
 }
 
@@ -1250,7 +1253,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     // 5. reduce (+ peel fix-up on partition 0)
     const int peel = ((flags & STIF_VARIO_PEEL) && part == 0) ? 1 : 0;
     reduce_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
-        P, grid, x, y, t, v, n, smax, ws, wt, peel,
+        P, grid, x, y, t, v, n, smax, ws, wt, peel, (flags & STIF_VARIO_COUNTS_F64) ? 1 : 0,
         reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[3], st));
@@ -1398,7 +1401,7 @@ extern "C" int stif_variogram_sampled_dev(stif_ctx *c, const double *x, const do
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[2], st));
     reduce_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
-        P, grid, x, y, t, v, n, smax, ws, wt, 0, reinterpret_cast<unsigned long long *>(counts_dev),
+        P, grid, x, y, t, v, n, smax, ws, wt, 0, 0, reinterpret_cast<unsigned long long *>(counts_dev),
         sums_dev);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[3], st));

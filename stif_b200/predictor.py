@@ -19,6 +19,7 @@ Differences a user can observe (all opt-in or documented in DESIGN.md):
 """
 import pickle
 import types
+import warnings
 
 import numpy as np
 import sklearn.metrics  # noqa: F401  (parity with the reference's import surface)
@@ -74,6 +75,9 @@ class Predictor:
         self._device_fit_objective = device_fit_objective
         self._ctx = context
         self._obs_token = None
+        # self._residuals_version (see __setattr__) is bumped whenever self._residuals is assigned:
+        # the device copy is stale iff the counter moved (object identity is no key: CPython
+        # reuses the address of a freed array)
 
     # ---- device plumbing ---------------------------------------------------------
     @property
@@ -84,9 +88,8 @@ class Predictor:
 
     def _upload_observations(self):
         """Replicate (x, y, t, residual) of the training data on this rank's GPU."""
-        space = self._data.space_coords
         time = self._data.time_coords
-        token = (id(self._residuals), len(time))
+        token = (self._residuals_version, len(time))
         mine = getattr(self.context, "_obs_owner", None) is self
         if self._obs_token == token and mine:
             return
@@ -96,7 +99,7 @@ class Predictor:
             # per fold): keep the coordinates and the space-time grid on the device
             self.context.kriging_set_residuals(resid)
         else:
-            x, y = _native.split_space(space)
+            x, y = _native.split_space(self._data.space_coords)
             self.context.kriging_set_obs(x, y, time, resid)
         self.context._obs_owner = self
         self._obs_token = token
@@ -109,6 +112,13 @@ class Predictor:
     # ---- covariate regression (host) -----------------------------------------------
     def _prepare_geostatistics(self):
         self._residuals = self.get_residuals()
+
+    def __setattr__(self, name, value):
+        # every assignment of the residuals (here, by a subclass or by a test poking the
+        # attribute like the reference's own tests do) invalidates the device copy
+        if name == "_residuals":
+            object.__setattr__(self, "_residuals_version", getattr(self, "_residuals_version", 0) + 1)
+        object.__setattr__(self, name, value)
 
     def fit_covariate_model(self, train_idxs=slice(None)):
         X, y = self._X[train_idxs, :], self._y[train_idxs]
@@ -331,10 +341,16 @@ class Predictor:
         flags = _native.KRIG_F32_STORAGE if self._emulate_f32_storage else 0
 
         def run(b, e):
-            return self.context.kriging_predict_host(
+            out = self.context.kriging_predict_host(
                 tx[b:e], ty[b:e], tt[b:e], min_kriging_points, max_kriging_points, space_dist_max,
                 time_dist_max, leave_out=None if lo is None else lo[b:e], flags=flags,
                 want_weights=want_weights)
+            n_def = self.context.kriging_stats()["targets_singular"]
+            if n_def:
+                warnings.warn(f"{n_def} kriging system(s) were rank-deficient (duplicate or co-located "
+                              "observations); they received the minimum-norm solution, like the "
+                              "reference's np.linalg.lstsq", RuntimeWarning, stacklevel=3)
+            return out
         return parallel.kriging_all_ranks(run, len(tt))
 
     def _device_kriging_weights(self, kriging_vector, coords_spatial, coords_temporal):

@@ -8,6 +8,7 @@ import pandas as pd
 import pytest
 from sklearn.linear_model import LinearRegression
 
+from conftest import record_quantiles
 from oracle import kriging as ok
 from stif_b200 import Data, Predictor
 from stif_b200.utils import get_covariogram, get_variogram
@@ -67,6 +68,9 @@ def test_codegen_fingerprint_on_gpu(golden_dir, ctx):
         assert np.array_equal(norm, g["norm"][i, : ns * nt].reshape(ns, nt)), (i, g["kind"][i])
 
 
+STD_RTOL = {"c4": 2e-6, "c5": 2e-5, "gauss": 2e-6, "metric": 2e-6}
+
+
 @pytest.mark.parametrize("name", ["c4", "c5", "gauss", "metric"])
 def test_kriging_matches_reference_synth(golden_dir, ctx, name):
     g = load(golden_dir, "kriging_synth.npz")
@@ -91,7 +95,69 @@ def test_kriging_matches_reference_synth(golden_dir, ctx, name):
     assert np.mean(dm <= 1e-9 * mscale) > 0.8
     both = ~(np.isnan(std) | np.isnan(g[f"{name}_std"]))
     assert np.array_equal(np.isnan(std), np.isnan(g[f"{name}_std"])) or both.mean() > 0.95
-    assert np.allclose(std[both], g[f"{name}_std"][both], rtol=1e-4, atol=1e-6)
+    ds = np.abs(std[both] - g[f"{name}_std"][both]) / np.abs(g[f"{name}_std"][both])
+    record_quantiles(f"synth_{name}_f32_vs_reference", mean_over_scale=dm / mscale,
+                     mean_rel=dm / np.abs(g[f"{name}_mean"]), std_rel=ds,
+                     w_over_rowmax=(np.abs(w - g[f"{name}_w"]) / wscale).max(axis=1))
+    # std = sqrt_f32(sum_f32(w32 * gamma32)): a weight that lands on the other side of a float32
+    # rounding boundary moves the float32 sum by an ulp or two; the bound is the measured one
+    # (profiles/r02_parity_quantiles.jsonl) with a factor of ~4
+    assert ds.max() <= STD_RTOL[name], ds.max()
+
+
+# Bounds for the PM10 goldens (reference numba output, float32 storage).  `w`: max |dw| relative
+# to the row's largest weight; `mean`: max |dmean| relative to sum |w_i z_i|; `std`: max relative.
+# The sum_metric fit of the reference has marginal nuggets of -2.5e7, -1.4e7 and +3.9e7 that
+# cancel to ~30: gamma(h, t) itself carries ~1e-9 of relative rounding noise, and two CPU
+# implementations on the SAME LAPACK (the oracle and numba, which differ only in fast-math
+# re-association) already differ by 3.6e-8 of the scale in the mean (measured in
+# tests/test_oracle_cpu.py::test_kriging_pm10); the GPU is held to the same order of magnitude.
+PM10_BOUNDS = {
+    "sum_metric": dict(w=1e-6, mean=2e-7, std=2e-6),
+    "product_sum": dict(w=2.0 ** -21, mean=2.0 ** -21, std=2e-6),
+}
+
+
+@pytest.mark.parametrize("st", ["sum_metric", "product_sum"])
+def test_kriging_matches_reference_pm10(golden_dir, pm10, ctx, st):
+    """C1 kriging on the GPU against the unmodified reference: 400 PM10 targets, the reference's
+    own fitted parameter vectors, k = 50, leave-one-out (tests/test_predictor.py:291-324 shape)."""
+    g = load(golden_dir, "kriging_pm10.npz")
+    sel, k, smax, tmax = g["targets"], int(g["k"]), float(g["smax"]), float(g["tmax"])
+    data = Data(pm10, space_cols=["x", "y"], time_col="time", predictand_col="PM10")
+    p = Predictor(data, context=ctx)
+    p._variogram_bins_space = np.array([1.0])
+    p._variogram_bins_time = np.array([1.0])
+    p.set_variogram_model(g[f"{st}_params"], st)
+    space, t, z = data.space_coords, data.time_coords, pm10["PM10"].to_numpy()
+    w, gv, idx = p._get_kriging_weights(space[sel], t[sel], 1, k, smax, tmax, sel)
+    mean, std = p.get_kriging_prediction(space[sel], t[sel], 1, k, smax, tmax, sel)
+    r_idx, r_w, r_g = g[f"{st}_idx"], g[f"{st}_w"], g[f"{st}_gamma"]
+    r_mean, r_std = g[f"{st}_mean"], g[f"{st}_std"]
+    untied = g[f"{st}_tie"] == 0
+    assert untied.mean() > 0.5
+    n_used = (r_w != 0).sum(axis=1)
+    # identical neighbour SETS on untied rows (the reference's unstable argsort may order
+    # equal-gamma neighbours differently); on this fixture the order is identical as well
+    for i in np.nonzero(untied)[0]:
+        assert set(idx[i][: n_used[i]]) == set(r_idx[i][: n_used[i]]), i
+    rows = untied & np.all(idx == r_idx, axis=1)
+    assert rows.mean() > 0.99
+    assert np.all(np.abs(gv - r_g)[rows] <= np.spacing(np.abs(r_g[rows])))          # 1 float32 ulp
+    b = PM10_BOUNDS[st]
+    wscale = np.abs(r_w).max(axis=1, keepdims=True) + 1e-30
+    mscale = np.sum(np.abs(r_w.astype(np.float64)) * np.abs(z[r_idx.astype(np.int64)]), axis=1) + 1e-300
+    dw = (np.abs(w - r_w) / wscale)[rows]
+    dm = (np.abs(mean - r_mean) / mscale)[rows]
+    ds = (np.abs(std - r_std) / np.abs(r_std))[rows]
+    record_quantiles(f"pm10_{st}_f32_vs_reference", w_over_rowmax=dw.max(axis=1), mean_over_scale=dm,
+                     mean_rel=(np.abs(mean - r_mean) / np.abs(r_mean))[rows], std_rel=ds)
+    assert np.array_equal(np.isnan(std), np.isnan(r_std))
+    assert dw.max() <= b["w"], dw.max()
+    assert dm.max() <= b["mean"], dm.max()
+    assert np.nanmax(ds) <= b["std"], np.nanmax(ds)
+    if st == "product_sum":      # well-conditioned: most targets agree to 1e-9 of |mean| itself
+        assert np.quantile((np.abs(mean - r_mean) / np.abs(r_mean))[rows], 0.5) <= 1e-9
 
 
 def test_reference_test_kriging_prediction(pm10, ctx):

@@ -143,3 +143,51 @@ def test_two_rank_allreduce_and_gather():
         assert np.allclose(sums, h, rtol=1e-13)
         assert np.array_equal(m, np.arange(101) * 2.0)
         assert np.array_equal(idx, np.arange(303, dtype=np.uint32).reshape(101, 3))
+
+
+class _RecordingContext:
+    """Stand-in for _native.Context that records what reaches the device (no GPU needed)."""
+
+    def __init__(self):
+        self.resid = None
+        self.calls = []
+
+    def kriging_set_obs(self, x, y, t, resid):
+        self.calls.append("set_obs")
+        self.resid = np.array(resid, copy=True)
+
+    def kriging_set_residuals(self, resid):
+        self.calls.append("set_residuals")
+        self.resid = np.array(resid, copy=True)
+
+
+def test_residual_upload_follows_every_refresh():
+    """the device residual cache was keyed on id(self._residuals); CPython reuses the
+    address of a freed array, so two refreshes between kriging calls could leave stale residuals
+    on the GPU.  The key is now a version counter bumped on every assignment."""
+    from sklearn.linear_model import LinearRegression
+    df = _df(200)
+    df["z"] = 3.0 * df["x"] + np.random.default_rng(2).normal(size=200)
+    data = Data(df, space_cols=["x", "y"], time_col="time", predictand_col="z", covariate_cols=["x"])
+    ctx = _RecordingContext()
+    p = Predictor(data, LinearRegression(), context=ctx)
+    p.fit_covariate_model(np.arange(0, 100))
+    p._prepare_geostatistics()
+    p._upload_observations()
+    assert ctx.calls == ["set_obs"] and np.array_equal(ctx.resid, p._residuals)
+    p._upload_observations()                       # nothing changed: no transfer
+    assert ctx.calls == ["set_obs"]
+    for rows in (np.arange(100, 200), np.arange(50, 150), np.arange(0, 200)):
+        # refresh TWICE between predictions (predict -> refit -> variogram -> covariogram -> predict):
+        # the first refreshed array is freed, the second may land on its address
+        p.fit_covariate_model(rows)
+        p._prepare_geostatistics()
+        p._prepare_geostatistics()
+        p._upload_observations()
+        assert ctx.calls[-1] == "set_residuals"
+        assert np.array_equal(ctx.resid, p._residuals)
+        assert np.array_equal(ctx.resid, p.get_residuals())
+    n_calls = len(ctx.calls)
+    p._residuals = p._residuals.copy()             # direct assignment counts as a refresh too
+    p._upload_observations()
+    assert len(ctx.calls) == n_calls + 1

@@ -277,20 +277,74 @@ def test_fewer_observations_than_k(ctx):
     compare(g, o, z, False)
 
 
-def test_duplicate_observations_are_flagged_not_fatal(ctx):
-    """Two identical observations make the system exactly singular: dgelsd returns the
-    minimum-norm solution, the LU skips the zero pivot (documented best-effort parity).  The
-    call must succeed, flag the targets, and still honour sum(w) == 1."""
-    space, t, z, tsp, tt = synth(2000, 50, seed=4, extent=60.0)
+@pytest.mark.parametrize("models,params,k", [
+    (SUM_METRIC, P_SUM_METRIC, 20),
+    (SUM_METRIC, [400, 60, 500, 0.4, 0.2, 0.3, 0.0, 0.0, 0.0, 5.0], 33),      # zero total nugget
+    (PRODUCT_SUM, P_PRODUCT_SUM, 20),
+    (PRODUCT_SUM, P_PRODUCT_SUM, 70),
+])
+def test_duplicate_observations_minimum_norm_parity(ctx, models, params, k):
+    """Identical observations make [Gamma 1; 1' 0] exactly singular whatever the nugget (the
+    reference puts gamma(0, 0) on the diagonal): np.linalg.lstsq = dgelsd returns the
+    MINIMUM-NORM solution, which shares the weight equally between the copies.  The GPU path
+    flags those systems in the pivoted LU and re-solves them with a Jacobi SVD
+    (solve_minnorm_kernel): parity with the oracle's dgelsd, duplicates carrying DIFFERENT
+    residuals so that a wrong weight split shows in the mean."""
+    space, t, z, tsp, tt = synth(2000, 60, seed=4, extent=60.0)
     space[1000:] = space[:1000]
-    t[1000:] = t[:1000]
-    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 20, 30.0, 30.0, f32=False)
+    t[1000:] = t[:1000]                       # z[1000:] stays different from z[:1000]
+    space[1900:] = space[:100]                # some points exist three times
+    t[1900:] = t[:100]
+    g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=False)
     st = ctx.kriging_stats()
     assert st["targets_singular"] > 0
-    assert ctx.kriging_solver_stats()["cholesky_to_lu"] >= st["targets_singular"]
-    used = g["n_used"] > 0
-    assert np.all(np.isfinite(g["mean"][used]))
-    assert np.allclose(g["w"][used].sum(axis=1), 1.0, atol=1e-4)
+    o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32_storage=False)
+    deficient = (o["rank"] < o["n_used"] + 1) & (o["n_used"] > 0)
+    assert deficient.sum() > 0 and st["targets_singular"] >= deficient.sum()
+    rows = (o["tie"] == 0) & (o["n_used"] > 0)
+    assert rows.sum() > 10
+    assert np.array_equal(g["idx"][rows], o["idx"][rows])
+    wscale = np.abs(o["w"]).max(axis=1, keepdims=True) + 1e-30
+    assert np.all(np.abs(g["w"] - o["w"])[rows] <= 2.0 ** -21 * wscale[rows])
+    mscale = np.sum(np.abs(o["w"].astype(np.float64)) * np.abs(z[o["idx"].astype(np.int64)]), axis=1) + 1e-300
+    vscale = np.sum(np.abs(o["w"].astype(np.float64) * o["gamma"]), axis=1) + 1e-300
+    assert np.all(np.abs(g["mean"] - o["mean"])[rows] <= 1e-8 * mscale[rows])
+    assert np.all(np.abs(g["std"] ** 2 - o["std"] ** 2)[rows & ~np.isnan(o["std"])] <= 1e-8 * vscale[rows & ~np.isnan(o["std"])])
+    # copies of one observation share their weight equally (the minimum-norm property)
+    i = int(np.nonzero(deficient & rows)[0][0])
+    ids = o["idx"][i][: o["n_used"][i]].astype(np.int64)
+    key = np.round(space[ids, 0] * 1e6) + 1e9 * np.round(t[ids] * 1e3)
+    for kk in np.unique(key):
+        grp = np.nonzero(key == kk)[0]
+        if len(grp) > 1:
+            wg = g["w"][i][grp].astype(np.float64)
+            assert np.all(np.abs(wg - wg.mean()) <= 1e-6 * np.abs(wscale[i]))
+
+
+def test_non_finite_system_raises_linalg_error(ctx):
+    """The reference's lstsq raises np.linalg.LinAlgError when the kriging matrix holds NaN / Inf
+    (numba _check_finite_matrix, stif/predictor.py:587): STIF_ENONFINITE -> LinAlgError."""
+    space, t, z, tsp, tt = synth(3000, 40, seed=6, extent=60.0)
+    bad = [400, 60, 500, 0.4, 0.2, 0.3, 0.03, np.inf, 0.03, 5.0]      # infinite nugget: gamma = inf
+    with pytest.raises(np.linalg.LinAlgError):
+        gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, bad, 1, 12, 30.0, 30.0, f32=False)
+    nanp = [300, 60, np.nan, 0.7, 0.15, 0.10, 0.4]
+    with pytest.raises(np.linalg.LinAlgError):
+        gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, nanp, 1, 12, 30.0, 30.0, f32=True)
+    # and the context stays usable
+    g = gpu_predict(ctx, space, t, z, tsp, tt, SUM_METRIC, P_SUM_METRIC, 1, 12, 30.0, 30.0, f32=False)
+    assert np.all(np.isfinite(g["mean"]))
+
+
+def test_device_numpy_row_sum_is_numpys(ctx):
+    """The DEVICE summation code of the float32-storage epilogue (csrc/kriging.cu numpy_row_sum)
+    against np.sum(axis=1), bit for bit, for every row length the kernel supports."""
+    rng = np.random.default_rng(0)
+    for k in range(1, 129):
+        a64 = rng.normal(size=(96, k)) * 10.0 ** rng.uniform(-3, 3, size=(96, 1))
+        a32 = a64.astype(np.float32)
+        assert np.array_equal(ctx.debug_numpy_row_sum(a64), np.sum(a64, axis=1)), k
+        assert np.array_equal(ctx.debug_numpy_row_sum(a32), np.sum(a32, axis=1)), k
 
 
 def test_huge_radii_streaming_select(ctx):

@@ -84,6 +84,10 @@ int stif_sm_count(stif_ctx *ctx);
 #define STIF_VARIO_NO_CULL 2
 #define STIF_VARIO_SPACE_SORT 4
 #define STIF_VARIO_TIME_SORT 8
+#define STIF_VARIO_DETERMINISTIC 32 /* bit-reproducible sums: every term is added as a 62-bit fixed-point
+                                    integer (quantum = 2^-60 of the largest possible term) into integer
+                                    histograms instead of FP64 atomics, whose order -- hence the last
+                                    bits of the sums -- depends on the scheduling.  ~25 % slower. */
 #define STIF_VARIO_COUNTS_F64 16 /* _dev only: counts_dev receives float64 values (exact below 2^53,
                                     the dtype of the reference's own `norm`), so that counts and sums
                                     of all ranks meet in ONE all-reduce of one float64 buffer */

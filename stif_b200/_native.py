@@ -22,6 +22,7 @@ VARIO_PEEL = 1
 VARIO_NO_CULL = 2
 VARIO_SPACE_SORT = 4   # force the space-time sort mode (default: from 163 840 observations)
 VARIO_TIME_SORT = 8    # forbid it
+VARIO_DETERMINISTIC = 32  # bit-reproducible fixed-point sums (slower)
 VARIO_COUNTS_F64 = 16  # variogram_dev: counts written as float64 (one fused all-reduce buffer)
 KRIG_F32_STORAGE = 1
 KRIG_FORCE_LU = 2

@@ -42,6 +42,28 @@ def _digest():
     return h.hexdigest()
 
 
+def build_variant(out_path, extra_flags):
+    """Development aid: build another copy of the library with extra nvcc flags (e.g.
+    -DSTIF_VARIO_TJ=256) for A/B timing through tools/*.py's STIF_LIB switch."""
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build", "variant_" + hashlib.sha256(" ".join(extra_flags).encode()).hexdigest()[:8])
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+                           "-o", out_path] + objs)
+    return out_path
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library. Returns its path."""
     stamp = LIB_PATH + ".stamp"
@@ -78,4 +100,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:      # python -m stif_b200.build --variant out.so -DSTIF_VARIO_TJ=256 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(os.path.abspath(sys.argv[i + 1]), sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -9,24 +9,34 @@
 // monotone; found on the host); bins are trunc(sqrt_rn(d2)*(1/ws)), trunc(|dt|*(1/wt)).
 //
 // Pipeline (all on one stream, no host synchronisation):
-//   1. pack time keys, radix-sort observation indices by the top 32 bits of the time key
-//      (CUB; plumbing)
-//   2. gather into a time-sorted AoS double4 {x,y,t,v} array, NaN-padded to a tile multiple;
-//      bounding box of (x,y,t) -> constants of the float pre-filter (filter_setup_kernel)
-//   3. per i-tile (512 obs) find the last j-sub-tile (256 obs) that can still be inside
-//      the time window -> work list of (i-tile, j-sub-tile) items; every other tile pair
-//      is provably outside |dt| <= tmax and is never visited ("culling")
-//   4. persistent pair kernel: grid = SMs x resident CTAs; a block starts with item
-//      blockIdx.x of its partition and then claims the next unclaimed one.  Per item each
-//      thread keeps 2 i-points in registers AS CENTRED FLOATS and sweeps the 256 j-points
-//      broadcast from shared memory through a float pre-filter with a rigorous error band
-//      (no false negatives; 5-7 FP32 instructions per pair).  Pairs it cannot rule out are
-//      appended (ballot compaction, 8-pair mask entries) to the warp's circular queue and
-//      binned in dense batches of 32 with the reference's exact FP64 arithmetic: cut-off
-//      tests, bins, shared-memory count atomics, global (L2) f64 sum atomics.
-//   5. deterministic fixed-order reduction of the per-block partial histograms.
-// From 163 840 observations steps 1-3 run in the SPACE-TIME SORT MODE instead (see the block comment
-// above bbox_kernel): order by (time slab, Morton cell), bounding boxes of the sub-tiles, explicit
+//   1. bounding box of (x, y, t, v) -> constants of the float pre-filter and of the fixed-point
+//      sums (filter_setup_kernel); radix-sort of the observation indices by the top 32 bits of the
+//      time key, or by (time slab, Hilbert cell) in the space-time sort mode (CUB; plumbing)
+//   2. gather into sorted SUB-TILE RECORDS of TJ observations, laid out exactly as the pair kernel
+//      wants them in shared memory ({x,y}[TJ] | {t,v}[TJ] | float x-cx [TJ] | y-cy | t-ct; NaN
+//      padded), so that a tile is staged by ONE bulk copy (cp.async.bulk, the TMA engine) instead
+//      of per-thread loads, conversions and stores
+//   3. work list of (i-tile, j-sub-tile) items: time-sorted mode: per i-tile (512 obs) the last
+//      j-sub-tile that can still be inside the time window; space-time mode: explicit list from
+//      exact box-gap tests in space and time.  Every other tile pair is provably outside the
+//      window and is never visited ("culling")
+//   4. persistent pair kernel: grid = SMs x resident CTAs.  A block claims CHUNKS of consecutive
+//      items (same i-tile): the i-tile is bulk-copied once per chunk, the j-sub-tiles stream
+//      through a two-stage ring of shared-memory buffers (mbarrier "full" barriers armed with the
+//      expected byte count; the last warp to finish a buffer issues the bulk copy of the
+//      next-but-one item into it), so the warps of a block never wait for each other inside a
+//      chunk.  Per item each thread keeps 2 i-points in registers AS CENTRED FLOATS and sweeps the
+//      j-points broadcast from shared memory through a float pre-filter with a rigorous error band
+//      (no false negatives; 5-7 FP32 instructions per pair, issued as packed f32x2).  Pairs it
+//      cannot rule out are appended (ballot compaction, 8-pair mask entries) to the warp's
+//      circular queue and binned in dense batches of 32 with the reference's exact FP64
+//      arithmetic: cut-off tests, bins, and shared-memory histograms of counts and of the sums AS
+//      62-BIT FIXED-POINT INTEGERS in three 21-bit limbs (native 32-bit shared atomics, carries
+//      on wrap-around): integer addition is associative, so the sums are bit-reproducible from
+//      run to run and independent of which block binned which item.
+//   5. exact 128-bit integer reduction of the per-block limb histograms, ONE rounding to float64.
+// From 163 840 observations steps 1-3 run in the SPACE-TIME SORT MODE (see the block comment
+// above bbox_kernel): order by (time slab, Hilbert cell), bounding boxes of the sub-tiles, explicit
 // item list from exact box-gap tests in space and time.  Same kernel, same histogram.
 #include "common.cuh"
 
@@ -46,7 +56,10 @@ constexpr int TI = VT * VR;    // i-tile: 512 observations
 #endif
 constexpr int TJ = STIF_VARIO_TJ;  // j-sub-tile: 256 observations
 constexpr int JPI = TI / TJ;   // j-sub-tiles per i-tile
-constexpr int QW = 512;        // entries (uint32) of a warp's circular queue
+#ifndef STIF_VARIO_QW
+#define STIF_VARIO_QW 256
+#endif
+constexpr int QW = STIF_VARIO_QW;  // entries (uint32) of a warp's circular queue
 #ifndef STIF_VARIO_NB
 #define STIF_VARIO_NB 8
 #endif
@@ -55,18 +68,53 @@ constexpr int JV = NB / VR;    // j-points per queue entry
 constexpr int LVR = VR == 4 ? 2 : 1, LJV = (NB == 16 ? 4 : 3) - LVR;
 constexpr int MINB = VR == 4 ? 3 : 4;  // resident CTAs per SM the kernel is compiled for
 constexpr int VG = JV > 4 ? JV : 4;  // j-points between queue checks
-constexpr int MAX_BINS = 8192; // histogram limit (4 B of shared memory per bin)
+constexpr int MAX_BINS = 8192; // histogram limit (16 B of shared memory per bin)
 constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x TI*TJ (<= 2^18) pairs < 2^32: u32 counts are safe
+// Items a block claims at once (runs over the same i-tile stream their j-sub-tiles through the
+// two-stage ring without a block barrier).  Measured on B200 (profiles/r02_notes.md): chunks of
+// 8 / 16 / 32 items are 1-8 % SLOWER than single items at 300k and 1M observations -- with four
+// resident CTAs per SM the item barrier of one block is covered by the warps of the others, while
+// coarser claims lengthen the tail -- so the default is 1 and the ring then serves as the landing
+// buffer of the bulk copies only.
+#ifndef STIF_VARIO_CHUNK
+#define STIF_VARIO_CHUNK 1
+#endif
+constexpr int CHUNK_MAX = STIF_VARIO_CHUNK;
+#ifndef STIF_VARIO_NSTAGE
+#define STIF_VARIO_NSTAGE (STIF_VARIO_CHUNK > 1 ? 2 : 1)
+#endif
+constexpr int NSTAGE = STIF_VARIO_NSTAGE;      // j-sub-tile buffers in flight
+
+// A sub-tile record in global memory == its image in shared memory.
+constexpr int REC_XY = 0;                    // double2 {x, y} [TJ]
+constexpr int REC_TV = 16 * TJ;              // double2 {t, v} [TJ]
+constexpr int REC_F = 32 * TJ;               // float x - cx [TJ] | y - cy [TJ] | t - ct [TJ]
+constexpr int REC_BYTES = 44 * TJ;           // 11 264 B at TJ = 256
+constexpr int REC_D_BYTES = 32 * TJ;         // the FP64 part (what an i-tile needs)
+
+// Fixed-point sums: a term val is added as x = rn(val * 2^e) + bias, 0 <= x < 2^62, split into
+// limbs of 21 + 21 + 20 bits that are accumulated in uint32 shared-memory counters.  A counter
+// that wraps carries 2^32 = 2^11 units of the next limb; wraps of the top counter are counted in
+// a per-block uint32 in global memory (a wrap there takes >= 2^12 binned pairs of one bin).
+constexpr int LIMB_BITS = 21;
+constexpr unsigned LIMB_MASK = (1u << LIMB_BITS) - 1u;
+constexpr unsigned LIMB_CARRY = 1u << (32 - LIMB_BITS);   // 2048
+constexpr unsigned POISON = 0x80000000u;     // a non-finite term reached this bin: the sum is NaN
 
 // Constants of the float pre-filter, written by filter_setup_kernel.
 struct FilterConst {
     double cx, cy, ct;  // centre of the bounding box (subtracted before the float conversion)
     float thi;          // d2f > thi  => the pair is certainly outside the space cut-off
     float tmaxf;        // |dtf| > tmaxf => certainly outside the time cut-off
+    // fixed-point sums: x = rn(val * fx_scale) + fx_bias for |val| <= fx_rmax (else: poison)
+    double fx_scale;    // 2^e
+    double fx_inv;      // 2^-e
+    double fx_rmax;     // bound on |val| of finite inputs
+    long long fx_bias;  // 0 (variogram: val >= 0) or 2^60 (covariogram: val of either sign)
 };
 
 struct Params {
-    const double4 *pts;   // sorted, padded observations
+    const unsigned char *recs;   // sorted, padded observations as sub-tile records (REC_BYTES each)
     const int *item_prefix;  // [nI+1] exclusive prefix of items per i-tile
     const int *item_jbeg;    // [nI]  (= I*JPI)
     int nI;
@@ -77,9 +125,11 @@ struct Params {
     double tmax;     // time_dist_max
     double inv_ws, inv_wt;
     double mean;
-    double *partial_sum;           // [grid][n_bins]
+    double *partial_sum;              // [grid][n_bins] FP64 sums (default mode: L2 atomics)
+    unsigned *partial_limb;           // [grid][4][n_bins] deterministic mode: limbs c0, c1, c2 and the
+                                      // wrap count / poison flag
     unsigned long long *partial_cnt;  // [grid][n_bins]
-    unsigned long long *stats;     // [0] items claimed beyond the first round, [2] pairs inside
+    unsigned long long *stats;     // [0] chunks claimed beyond the first round, [2] pairs inside
                                    // the window, [3] items visited
     const double *thr;    // [n_space_bins + 2] d2 thresholds: bin b <=> thr[b] <= d2 < thr[b+1]
     int use_thr;          // 0: evaluate sqrt/mul/trunc per binned pair (degenerate widths)
@@ -91,6 +141,16 @@ struct Params {
     const unsigned *items;   // nullptr: items are the j-ranges of item_prefix / item_jbeg
     const double *bb;        // [nJ][6] {xlo, xhi, ylo, yhi, tlo, thi} of every j-sub-tile
 };
+
+// element k of the sorted order inside the record array
+__device__ __forceinline__ const double2 *rec_xy(const unsigned char *recs, int64_t k)
+{
+    return reinterpret_cast<const double2 *>(recs + (size_t)(k / TJ) * REC_BYTES + REC_XY) + (k % TJ);
+}
+__device__ __forceinline__ const double2 *rec_tv(const unsigned char *recs, int64_t k)
+{
+    return reinterpret_cast<const double2 *>(recs + (size_t)(k / TJ) * REC_BYTES + REC_TV) + (k % TJ);
+}
 
 __global__ void pack_keys_kernel(const double *t, int64_t n, double *keys, unsigned *idx)
 {
@@ -120,38 +180,30 @@ __device__ __forceinline__ double ord_dec(unsigned long long e)
     return __longlong_as_double((long long)u);
 }
 
-// Gather into the sorted AoS array; also the bounding box of (x, y, t) for the float pre-filter:
-// ext[0..5] = max of enc(x), enc(-x), enc(y), enc(-y), enc(t), enc(-t) over the non-NaN values.
+// Gather into the sorted sub-tile records (FP64 halves + the centred float copy the sweep reads).
+// Padding (k >= n): NaN coordinates never pass d2 <= tcut.
 __global__ void gather_kernel(const double *x, const double *y, const double *t, const double *v,
-                              const unsigned *idx, int64_t n, int64_t n_pad, double4 *pts,
-                              unsigned long long *ext)
+                              const unsigned *idx, int64_t n, int64_t n_pad, unsigned char *recs,
+                              const FilterConst *filter)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long e[6] = {0, 0, 0, 0, 0, 0};
-    if (k < n_pad) {
-        double4 p;
-        if (k < n) {
-            unsigned i = idx[k];
-            p = make_double4(x[i], y[i], t[i], v[i]);
-            if (p.x == p.x) { e[0] = ord_enc(p.x); e[1] = ord_enc(-p.x); }
-            if (p.y == p.y) { e[2] = ord_enc(p.y); e[3] = ord_enc(-p.y); }
-            if (p.z == p.z) { e[4] = ord_enc(p.z); e[5] = ord_enc(-p.z); }
-        } else {
-            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-            p = make_double4(qnan, qnan, qnan, 0.0);  // NaN never passes d2 <= tcut
-        }
-        pts[k] = p;
+    if (k >= n_pad) return;
+    double4 p;
+    if (k < n) {
+        unsigned i = idx[k];
+        p = make_double4(x[i], y[i], t[i], v[i]);
+    } else {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        p = make_double4(qnan, qnan, qnan, 0.0);
     }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        // warp maximum of a 64-bit key with two 32-bit REDUX: high words, then the low words
-        // of the lanes that hold the maximal high word
-        const unsigned hi = (unsigned)(e[c] >> 32), lo = (unsigned)e[c];
-        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-        const unsigned long long m = ((unsigned long long)mh << 32) | ml;
-        if ((threadIdx.x & 31) == 0 && m) atomicMax(&ext[c], m);
-    }
+    unsigned char *rec = recs + (size_t)(k / TJ) * REC_BYTES;
+    const int e = (int)(k % TJ);
+    reinterpret_cast<double2 *>(rec + REC_XY)[e] = make_double2(p.x, p.y);
+    reinterpret_cast<double2 *>(rec + REC_TV)[e] = make_double2(p.z, p.w);
+    float *f = reinterpret_cast<float *>(rec + REC_F);
+    f[e] = __double2float_rn(__dsub_rn(p.x, filter->cx));
+    f[TJ + e] = __double2float_rn(__dsub_rn(p.y, filter->cy));
+    f[2 * TJ + e] = __double2float_rn(__dsub_rn(p.z, filter->ct));
 }
 
 // Constants of the float pre-filter (one thread).  Coordinates are centred on the bounding box
@@ -163,7 +215,7 @@ __global__ void gather_kernel(const double *x, const double *y, const double *t,
 // everything else is decided exactly, in FP64, by the drain.  Same for the time lag.
 // Non-finite extents or bounds make thi / tmaxf infinite: the filter passes everything.
 __global__ void filter_setup_kernel(const unsigned long long *ext, double smax, double tmax,
-                                    FilterConst *F)
+                                    int mode, double mean, FilterConst *F)
 {
     double lo[3], hi[3], c[3], h[3];
     for (int a = 0; a < 3; ++a) {
@@ -185,6 +237,30 @@ __global__ void filter_setup_kernel(const unsigned long long *ext, double smax, 
     F->ct = c[2];
     F->thi = (isfinite(thi) && thi < 1e37) ? __double2float_ru(thi) : inf;
     F->tmaxf = (isfinite(tm) && tm < 1e37) ? __double2float_ru(tm) : inf;
+    // Fixed-point scale of the sums.  ext[6], ext[7] = enc(max v), enc(max -v) over the non-NaN
+    // values.  Variogram: val = rn(rn(vi - vj)^2) <= rn(rn(vmax - vmin)^2) (rounding is monotone);
+    // covariogram: |val| = |rn(rn(vi - mean) rn(vj - mean))| <= max |v - mean|^2.  With
+    // R = f 2^p, f in [0.5, 1), the scale 2^(60 - p) puts every |rn(val * scale)| below 2^60, and
+    // one term is quantised to 2^-60 of the largest possible term (a relative 1e-18).
+    double R = 0.0;
+    if (ext[6] != 0ull) {
+        const double vhi = ord_dec(ext[6]), vlo = -ord_dec(ext[7]);
+        if (mode == 0) {
+            const double d = __dsub_rn(vhi, vlo);
+            R = __dmul_rn(d, d);
+        } else {
+            const double a = fmax(fabs(__dsub_rn(vhi, mean)), fabs(__dsub_rn(vlo, mean)));
+            R = __dmul_rn(a, a);
+        }
+    }
+    if (!(R < 1.79e308)) R = 1.79e308;          // infinite values: their terms are poison
+    if (!(R > 1e-290)) R = 1e-290;              // all values equal (or denormal spread)
+    int ex;
+    frexp(R, &ex);                              // R = f 2^ex, f in [0.5, 1)
+    F->fx_scale = ldexp(1.0, 60 - ex);
+    F->fx_inv = ldexp(1.0, ex - 60);
+    F->fx_rmax = R;
+    F->fx_bias = mode == 0 ? 0ll : (1ll << 60);
 }
 
 // The observations are radix-sorted by the TOP 32 BITS of the order-preserving time key only
@@ -207,7 +283,7 @@ __device__ __forceinline__ double coarse_hi(double t)
 // One thread per i-tile: last j-sub-tile that may hold a pair with rn(tj - ti) <= tmax.
 // The smallest lag between i-tile I and sub-tile J (beyond the diagonal) is at least
 // rn(coarse_lo(t[J*TJ]) - coarse_hi(t_last(I))), and rounding is monotone.
-__global__ void tile_range_kernel(const double4 *pts, int64_t n, int nI, int nJ, double tmax,
+__global__ void tile_range_kernel(const unsigned char *recs, int64_t n, int nI, int nJ, double tmax,
                                   int cull, int *count, int *jbeg)
 {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,12 +293,12 @@ __global__ void tile_range_kernel(const double4 *pts, int64_t n, int nI, int nJ,
     if (cull) {
         int64_t last = (int64_t)I * TI + TI - 1;
         if (last > n - 1) last = n - 1;
-        const double ti_max = coarse_hi(pts[last].z);
+        const double ti_max = coarse_hi(rec_tv(recs, last)->x);
         // first J in (jb+JPI-1, nJ) with lag > tmax; all later ones are also outside
         int lo = jb + JPI, hi = nJ;  // search in [lo, hi)
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            double lag = __dsub_rn(coarse_lo(pts[(int64_t)mid * TJ].z), ti_max);
+            double lag = __dsub_rn(coarse_lo(rec_tv(recs, (int64_t)mid * TJ)->x), ti_max);
             if (lag > tmax) hi = mid; else lo = mid + 1;
         }
         jend = lo - 1;
@@ -273,20 +349,30 @@ __global__ void scan_kernel(const int *count, int nI, int *prefix)
 // possible lag of a tile pair bounds every pair's computed lag from below.
 // ---------------------------------------------------------------------------------------------
 
-// Bounding box of the raw input (same encoding as gather_kernel's).
-__global__ void bbox_kernel(const double *x, const double *y, const double *t, int64_t n,
-                            unsigned long long *ext)
+// Bounding box of the raw input: ext[0..7] = max of enc(x), enc(-x), enc(y), enc(-y), enc(t),
+// enc(-t), enc(v), enc(-v) over the non-NaN values (v == nullptr: coordinates only, called first
+// by the space-time sort mode whose keys do not need the values).
+__global__ void bbox_kernel(const double *x, const double *y, const double *t, const double *v,
+                            int64_t n, unsigned long long *ext)
 {
-    unsigned long long e[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool coords = x != nullptr;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
          k += (int64_t)gridDim.x * blockDim.x) {
-        const double px = x[k], py = y[k], pz = t[k];
-        if (px == px) { e[0] = max(e[0], ord_enc(px)); e[1] = max(e[1], ord_enc(-px)); }
-        if (py == py) { e[2] = max(e[2], ord_enc(py)); e[3] = max(e[3], ord_enc(-py)); }
-        if (pz == pz) { e[4] = max(e[4], ord_enc(pz)); e[5] = max(e[5], ord_enc(-pz)); }
+        if (coords) {
+            const double px = x[k], py = y[k], pz = t[k];
+            if (px == px) { e[0] = max(e[0], ord_enc(px)); e[1] = max(e[1], ord_enc(-px)); }
+            if (py == py) { e[2] = max(e[2], ord_enc(py)); e[3] = max(e[3], ord_enc(-py)); }
+            if (pz == pz) { e[4] = max(e[4], ord_enc(pz)); e[5] = max(e[5], ord_enc(-pz)); }
+        }
+        if (v) {
+            const double pv = v[k];
+            if (pv == pv) { e[6] = max(e[6], ord_enc(pv)); e[7] = max(e[7], ord_enc(-pv)); }
+        }
     }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < 8; ++c) {
+        if (c < 6 ? !coords : v == nullptr) continue;
         const unsigned hi = (unsigned)(e[c] >> 32), lo = (unsigned)e[c];
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
         const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
@@ -362,16 +448,17 @@ __global__ void spacetime_keys_kernel(const double *x, const double *y, const do
 }
 
 // One warp per j-sub-tile: box of its non-NaN coordinates (empty: lo = +inf, hi = -inf).
-__global__ void tile_bbox_kernel(const double4 *pts, int nJ, double *bb)
+__global__ void tile_bbox_kernel(const unsigned char *recs, int nJ, double *bb)
 {
     const int J = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (J >= nJ) return;
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int e = lane; e < TJ; e += 32) {
-        const double4 p = pts[(size_t)J * TJ + e];
-        lo[0] = fmin(lo[0], p.x); hi[0] = fmax(hi[0], p.x);   // fmin / fmax ignore NaN
-        lo[1] = fmin(lo[1], p.y); hi[1] = fmax(hi[1], p.y);
-        lo[2] = fmin(lo[2], p.z); hi[2] = fmax(hi[2], p.z);
+        const double2 pxy = *rec_xy(recs, (int64_t)J * TJ + e);
+        const double pz = rec_tv(recs, (int64_t)J * TJ + e)->x;
+        lo[0] = fmin(lo[0], pxy.x); hi[0] = fmax(hi[0], pxy.x);   // fmin / fmax ignore NaN
+        lo[1] = fmin(lo[1], pxy.y); hi[1] = fmax(hi[1], pxy.y);
+        lo[2] = fmin(lo[2], pz); hi[2] = fmax(hi[2], pz);
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -446,34 +533,29 @@ __global__ void items_kernel(const double *bb, int nI, int nJ, double tcut, doub
 }
 
 struct Smem {
-    double *g_sum;           // [n_bins] this block's partial sums in GLOBAL memory (L2 f64 atomics)
-    // tiles split into 16-byte halves: a random-index LDS.128 then spreads over all eight
-    // 16-byte bank groups (a 32-byte AoS stride uses only four: 2-way conflicts at best)
-    double2 *s_ixy, *s_itv;  // [TI] {x,y}, {t,v}
-    double2 *s_jxy, *s_jtv;  // [TJ]
-    float *s_jf;             // [3][TJ] x-cx, y-cy, t-ct in float (SoA): the sweep's copy
-    unsigned *q;             // [VT/32][QW] one circular queue per warp
-    unsigned *s_cnt;         // [n_bins]
+    double *g_sum;           // [n_bins] GLOBAL: this block's partial FP64 sums (default mode)
+    unsigned *s_cnt;         // [n_bins] pair counts of this block
+    unsigned *s_lim;         // [3][n_bins] limbs of the fixed-point sums (deterministic mode)
+    unsigned *g_wrap;        // [n_bins] GLOBAL: wraps of the top limb counter | POISON
     double *s_thr;           // [n_space_bins + 2]
+    int n_bins;
+    double fx_scale, fx_rmax;
+    long long fx_bias;
 };
+
+// byte offsets into dynamic shared memory
+constexpr unsigned O_I = 0;                               // i-tile: FP64 parts of its JPI records
+constexpr unsigned O_J = O_I + JPI * REC_D_BYTES;         // NSTAGE j-sub-tile records
+constexpr unsigned O_Q = O_J + NSTAGE * REC_BYTES;        // [VT/32][QW] one circular queue per warp
+constexpr unsigned O_BAR = O_Q + (VT / 32) * QW * 4;      // mbarriers, counters
+constexpr unsigned O_THR = O_BAR + 64;                    // s_thr, then s_cnt, s_lim
+// O_BAR + 0: full barrier of the i-tile; + 8 (1 + s): full barrier of j stage s;
+// + 32 + 4 s: warps done with stage s; + 48: next chunk (long long)
 
 __device__ __forceinline__ void st_shared_u32(unsigned addr, unsigned v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-
-// Bin one queued pair per lane: j-point j and i-point ii of the staged tiles, everything in
-// FP64 exactly as the reference executes it.  The queue holds every pair the float pre-filter
-// could not rule out, so the reference's two cut-off tests are applied here.  Returns whether
-// the pair is inside the window (statistics).
-//
-// Histogram update: the count is a native shared-memory atomic (ATOMS.POPC.INC).  The FP64 sum
-// goes to the block's partial histogram in GLOBAL memory with a native L2 atomic
-// (REDG.E.ADD.F64, fire and forget): on sm_100a a shared-memory f64 add is a compare-and-swap
-// loop (ATOMS.CAST.SPIN.64, 2.95 tries per warp on C2) and was 16 % of the kernel's stall
-// samples; the block's 7.2 KB of partial sums stay in L2.  A warp-aggregated variant (match_any
-// + shuffle reduction per distinct bin) was measured 2x SLOWER on C2 (profiles/r01_notes.md): a
-// warp's 32 pairs spread over ~25 distinct bins, so there is little to aggregate.
 __device__ __forceinline__ double2 lds_d2(unsigned addr)
 {
     double2 v;
@@ -487,16 +569,82 @@ __device__ __forceinline__ double lds_d(unsigned addr)
     return v;
 }
 
-template <int MODE>
-__device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigned sbase, int j,
-                                         int ii, bool have)
+// ---- mbarrier + bulk copy (the TMA engine; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-    // byte offsets of the tile halves from the start of dynamic shared memory (= sbase)
-    constexpr unsigned O_IXY = 0, O_ITV = 16 * TI, O_JXY = 32 * TI, O_JTV = 32 * TI + 16 * TJ;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy, completion counted in bytes on `bar` (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// One term of a bin's sum, as a 62-bit fixed-point integer in three shared-memory limb counters.
+// The three adds are independent native ATOMS.ADD; a counter that wraps (the returned old value
+// shows it) carries into the next one -- once per >= 2048 adds.  Integer addition is associative:
+// the total does not depend on the order in which warps, blocks or GPUs bin their pairs.
+__device__ __forceinline__ void add_fixed(const Smem &S, int bin, double val)
+{
+    if (fabs(val) <= S.fx_rmax) {          // false for NaN / Inf
+        const long long x = __double2ll_rn(__dmul_rn(val, S.fx_scale)) + S.fx_bias;   // 0 <= x < 2^62
+        const unsigned l0 = (unsigned)x & LIMB_MASK;
+        const unsigned l1 = (unsigned)(x >> LIMB_BITS) & LIMB_MASK;
+        const unsigned l2 = (unsigned)(x >> (2 * LIMB_BITS));
+        unsigned *c0 = S.s_lim + bin, *c1 = c0 + S.n_bins, *c2 = c1 + S.n_bins;
+        const unsigned o0 = atomicAdd(c0, l0), o1 = atomicAdd(c1, l1), o2 = atomicAdd(c2, l2);
+        unsigned w1 = (o0 + l0 < o0) ? 1u : 0u, w2 = (o1 + l1 < o1) ? 1u : 0u, w3 = (o2 + l2 < o2) ? 1u : 0u;
+        if (w1 | w2 | w3) {
+            if (w1) {
+                const unsigned o = atomicAdd(c1, LIMB_CARRY);
+                w2 += (o + LIMB_CARRY < o) ? 1u : 0u;
+            }
+            for (; w2; --w2) {
+                const unsigned o = atomicAdd(c2, LIMB_CARRY);
+                w3 += (o + LIMB_CARRY < o) ? 1u : 0u;
+            }
+            if (w3) atomicAdd(S.g_wrap + bin, w3);
+        }
+    } else {
+        atomicOr(S.g_wrap + bin, POISON);
+    }
+}
+
+// Bin one queued pair per lane: j-point j of the stage at byte offset jbase and i-point ii of
+// the i-tile, everything in FP64 exactly as the reference executes it.  The queue holds every
+// pair the float pre-filter could not rule out, so the reference's two cut-off tests are applied
+// here.  Returns whether the pair is inside the window (statistics).
+// Histogram update: the count is a native shared-memory atomic (ATOMS.POPC.INC).  The sum goes,
+//   FX = false (default): to the block's partial histogram in GLOBAL memory with a native L2 FP64
+//     atomic (REDG.E.ADD.F64, fire and forget; a shared-memory f64 add is a CAS loop on sm_100a).
+//     The order of the adds -- hence the last bits of the sums -- depends on the scheduling.
+//   FX = true (STIF_VARIO_DETERMINISTIC): as a fixed-point integer into shared-memory limb
+//     counters (add_fixed): bit-reproducible, ~25 more instructions per binned pair.
+template <int MODE, bool FX>
+__device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigned sbase, unsigned jbase,
+                                         int j, int ii, bool have)
+{
     bool inside = false;
     if (have) {
-        const double2 ixy = lds_d2(sbase + O_IXY + 16u * ii), itv = lds_d2(sbase + O_ITV + 16u * ii);
-        const double2 jxy = lds_d2(sbase + O_JXY + 16u * j), jtv = lds_d2(sbase + O_JTV + 16u * j);
+        const unsigned ia = sbase + O_I + (unsigned)(ii / TJ) * REC_D_BYTES + 16u * (unsigned)(ii % TJ);
+        const unsigned ja = sbase + jbase + 16u * (unsigned)j;
+        const double2 ixy = lds_d2(ia + REC_XY), itv = lds_d2(ia + REC_TV);
+        const double2 jxy = lds_d2(ja + REC_XY), jtv = lds_d2(ja + REC_TV);
         const double dx = __dsub_rn(ixy.x, jxy.x);
         const double dy = __dsub_rn(ixy.y, jxy.y);
         const double d2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
@@ -536,7 +684,8 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
                     val = __dmul_rn(__dsub_rn(itv.y, P.mean), __dsub_rn(jtv.y, P.mean));
                 }
                 const int bin = bs * P.n_time_bins + bt;
-                atomicAdd(&S.g_sum[bin], val);
+                if (FX) add_fixed(S, bin, val);
+                else atomicAdd(&S.g_sum[bin], val);
                 atomicAdd(&S.s_cnt[bin], 1u);
             }
         }
@@ -550,10 +699,10 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
 // entries with pairs left are re-queued at the tail (ballot compaction),
 // so every batch but an item's last is full whatever the hit density.  The queue is circular:
 // a batch frees 32 slots before it appends at most 32.
-template <int MODE>
-__device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned sbase, unsigned wq_addr, int warp_base,
-                                      int lane, unsigned lt, unsigned &head, unsigned &tail,
-                                      unsigned &npass, bool flush)
+template <int MODE, bool FX>
+__device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned sbase, unsigned jbase,
+                                      unsigned wq_addr, int warp_base, int lane, unsigned lt,
+                                      unsigned &head, unsigned &tail, unsigned &npass, bool flush)
 {
     while (tail - head >= 32u || (flush && tail != head)) {
         __syncwarp();
@@ -563,7 +712,7 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned s
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + (((head + lane) & (QW - 1)) << 2)) : "memory");
         const unsigned m = e >> 12;
         const unsigned b = (unsigned)__ffs((int)m) - 1u;  // lowest pending pair: row b % VR, j offset b / VR
-        npass += bin_pair<MODE>(S, P, sbase, ((e & 0x7fu) << LJV) | (b >> LVR),
+        npass += bin_pair<MODE, FX>(S, P, sbase, jbase, ((e & 0x7fu) << LJV) | (b >> LVR),
                                 (b & (VR - 1)) * VT + warp_base + ((e >> 7) & 31u), have) ? 1u : 0u;
         const unsigned m2 = m & (m - 1u);
         const bool left = have && m2 != 0u;
@@ -615,8 +764,9 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 // Float pre-filter of VR i-points x VG j-points per thread; pairs it cannot rule out are queued.
 //   DIAG: the sub-tile overlaps the i-tile, keep only j > i.   TCHK: the time test is needed
 //   (false when the whole item is provably inside the time window).
+//   s_jf: the float rows x - cx | y - cy | t - ct of the j-sub-tile's record in shared memory.
 template <bool DIAG, bool TCHK>
-__device__ __forceinline__ void sweep(const Smem &S, const f32x2 (&xf)[VR], const f32x2 (&yf)[VR],
+__device__ __forceinline__ void sweep(const float *s_jf, const f32x2 (&xf)[VR], const f32x2 (&yf)[VR],
                                       const f32x2 (&tf)[VR], const int (&ioff)[VR], float thi,
                                       float tmaxf, int jb, unsigned wq_addr, unsigned lt,
                                       unsigned tag, unsigned &tail)
@@ -628,12 +778,12 @@ __device__ __forceinline__ void sweep(const Smem &S, const f32x2 (&xf)[VR], cons
 #pragma unroll
         for (int h = 0; h < JV; h += 2) {
             // {j+h, j+h+1}: 8-byte aligned pairs of the SoA rows, the same for every lane
-            const float2 jx = *reinterpret_cast<const float2 *>(S.s_jf + j + h);
-            const float2 jy = *reinterpret_cast<const float2 *>(S.s_jf + TJ + j + h);
+            const float2 jx = *reinterpret_cast<const float2 *>(s_jf + j + h);
+            const float2 jy = *reinterpret_cast<const float2 *>(s_jf + TJ + j + h);
             const f32x2 jx2 = pack2(jx.x, jx.y), jy2 = pack2(jy.x, jy.y);
             f32x2 jt2 = 0;
             if (TCHK) {
-                const float2 jt = *reinterpret_cast<const float2 *>(S.s_jf + 2 * TJ + j + h);
+                const float2 jt = *reinterpret_cast<const float2 *>(s_jf + 2 * TJ + j + h);
                 jt2 = pack2(jt.x, jt.y);
             }
 #pragma unroll
@@ -667,142 +817,225 @@ __device__ __forceinline__ void sweep(const Smem &S, const f32x2 (&xf)[VR], cons
     }
 }
 
-template <int MODE>
+template <int MODE, bool FX>
 __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     Smem S;
-    S.s_ixy = reinterpret_cast<double2 *>(smem_raw);
-    S.s_itv = S.s_ixy + TI;
-    S.s_jxy = S.s_itv + TI;
-    S.s_jtv = S.s_jxy + TJ;
-    S.s_jf = reinterpret_cast<float *>(S.s_jtv + TJ);
-    S.q = reinterpret_cast<unsigned *>(S.s_jf + 4 * TJ);
-    S.s_thr = reinterpret_cast<double *>(S.q + (VT / 32) * QW);
+    S.s_thr = reinterpret_cast<double *>(smem_raw + O_THR);
     S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
+    S.s_lim = S.s_cnt + P.n_bins;
+    S.n_bins = P.n_bins;
+    unsigned *s_done = reinterpret_cast<unsigned *>(smem_raw + O_BAR + 32);
+    long long *s_next = reinterpret_cast<long long *>(smem_raw + O_BAR + 48);
+    const unsigned bar_i = sbase + O_BAR, bar_j = sbase + O_BAR + 8;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
-    for (int b = tid; b < P.n_bins; b += VT) S.s_cnt[b] = 0u;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int b = tid; b < (FX ? 4 : 1) * P.n_bins; b += VT) S.s_cnt[b] = 0u;   // counts (and the three limbs)
     for (int b = tid; b < P.n_space_bins + 2; b += VT) S.s_thr[b] = P.thr[b];
     unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
+    unsigned *my_limb = P.partial_limb + (size_t)blockIdx.x * 4 * P.n_bins;
     double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
     for (int b = tid; b < P.n_bins; b += VT) {
         my_cnt[b] = 0ull;
-        my_sum[b] = 0.0;
+        if (FX) my_limb[3 * P.n_bins + b] = 0u;
+        else my_sum[b] = 0.0;
     }
+    S.g_wrap = my_limb + 3 * P.n_bins;
     S.g_sum = my_sum;
     const FilterConst F = *P.filter;
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const unsigned wq_addr = (unsigned)__cvta_generic_to_shared(S.q + (tid >> 5) * QW);
+    S.fx_scale = F.fx_scale;
+    S.fx_rmax = F.fx_rmax;
+    S.fx_bias = F.fx_bias;
+    if (tid == 0) {
+        mbar_init(bar_i, 1);
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar_j + 8 * s, 1);
+            s_done[s] = 0u;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const unsigned wq_addr = sbase + O_Q + (unsigned)(tid >> 5) * QW * 4;
     const unsigned lt = (1u << lane) - 1u, tag = (unsigned)lane << 7;
+    unsigned ph_i = 0, ph_j[NSTAGE];
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) ph_j[s] = 0;
 
     const long long M = P.item_prefix[P.nI];  // total items
+    // Items are claimed in chunks of CH consecutive list entries (the list is ordered by i-tile,
+    // so a chunk is usually one run over the same i-tile).  CH is the same for every block and
+    // leaves each block >= 12 chunks, so the tail stays short.  This partition owns the chunks q
+    // with q % nparts == part; a block starts with chunk blockIdx.x of its partition and then
+    // takes the next unclaimed one (stats[0] counts the claims beyond the first round): items
+    // differ in cost.  Which block bins which item no longer matters to the result at all: the
+    // counts and the fixed-point sums are integers.
+    long long per = M / ((long long)gridDim.x * P.nparts * 12);
+    const int CH = per < 1 ? 1 : (per > CHUNK_MAX ? CHUNK_MAX : (int)per);
+    const long long NQ = (M + CH - 1) / CH;
     unsigned long long npass_total = 0;
     unsigned items_done = 0, items_total = 0;
-    // This partition owns items w with w % nparts == part.  A block starts with item blockIdx.x
-    // and then takes the next unclaimed one (stats[0] counts the claims beyond the first round):
-    // items differ in cost (diagonal, edge of the time window) and a static round-robin leaves
-    // ceil(M/grid) - M/grid of an item's time idle (12 % at C2 with 8.02 items per block).
-    // Which block bins which item only changes the order of the FP64 sums, which the atomics
-    // leave open anyway; the counts are exact.
-    __shared__ long long s_next;
-    for (long long k = blockIdx.x;;) {
-        const long long w = k * P.nparts + P.part;
-        if (w >= M) break;
-        int I, J;
-        if (P.items) {   // space-time mode: explicit list
-            const unsigned it = P.items[w];
-            I = (int)(it >> 16);
-            J = (int)(it & 0xffffu);
-        } else {
-            // item -> (I, J): largest I with prefix[I] <= w
-            int lo = 0, hi = P.nI - 1;
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (P.item_prefix[mid] <= w) lo = mid; else hi = mid - 1;
+    __syncthreads();
+    for (long long kq = blockIdx.x;;) {
+        const long long q = kq * P.nparts + P.part;
+        if (q >= NQ) break;
+        long long w = q * CH;
+        const long long wend = (w + CH < M) ? w + CH : M;
+        bool first_run = true;
+        while (w < wend) {
+            // ---- one run: items w .. w + L - 1 share the i-tile I ----
+            int I, J0 = 0, L;
+            if (P.items) {   // space-time mode: explicit list
+                I = (int)(P.items[w] >> 16);
+                L = 1;
+                while (w + L < wend && (int)(P.items[w + L] >> 16) == I) ++L;
+            } else {
+                // item -> (I, J): largest I with prefix[I] <= w
+                int lo = 0, hi = P.nI - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (P.item_prefix[mid] <= w) lo = mid; else hi = mid - 1;
+                }
+                I = lo;
+                J0 = P.item_jbeg[I] + (int)(w - P.item_prefix[I]);
+                const long long iend = P.item_prefix[I + 1];
+                L = (int)((iend < wend ? iend : wend) - w);
             }
-            I = lo;
-            J = P.item_jbeg[I] + (int)(w - P.item_prefix[I]);
-        }
+            auto item_J = [&](int c) -> int {
+                return P.items ? (int)(P.items[w + c] & 0xffffu) : J0 + c;
+            };
 
-        __syncthreads();  // previous item finished with the tiles
-        const double4 *gi = P.pts + (size_t)I * TI;
-        const double4 *gj = P.pts + (size_t)J * TJ;
-        f32x2 xf[VR], yf[VR], tf[VR];   // the i-points as centred floats, duplicated into both halves
-        int ioff[VR];
+            __syncthreads();  // every warp is done with the previous run's i-tile and j stages
+            if (items_done + (unsigned)L > FLUSH_ITEMS) {     // u32 counts could overflow: flush
+                for (int b = tid; b < P.n_bins; b += VT) {
+                    my_cnt[b] += S.s_cnt[b];
+                    S.s_cnt[b] = 0u;
+                }
+                items_done = 0;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                if (first_run) *s_next = (long long)gridDim.x + (long long)atomicAdd(&P.stats[0], 1ull);
+                // the i-tile: the FP64 parts of its JPI records; the first NSTAGE j-sub-tiles
+                mbar_expect_tx(bar_i, JPI * REC_D_BYTES);
 #pragma unroll
-        for (int r = 0; r < VR; ++r) {
-            const double4 p = gi[r * VT + tid];
-            S.s_ixy[r * VT + tid] = make_double2(p.x, p.y);
-            S.s_itv[r * VT + tid] = make_double2(p.z, p.w);
-            const float fx = __double2float_rn(__dsub_rn(p.x, F.cx));
-            const float fy = __double2float_rn(__dsub_rn(p.y, F.cy));
-            const float ft = __double2float_rn(__dsub_rn(p.z, F.ct));
-            xf[r] = pack2(fx, fx);
-            yf[r] = pack2(fy, fy);
-            tf[r] = pack2(ft, ft);
-            ioff[r] = (I * TI + tid) - J * TJ + r * VT;  // (global i) - (global j of sub-tile start)
-        }
-        if (TJ == VT || tid < TJ) {
-            const double4 p = gj[tid];
-            S.s_jxy[tid] = make_double2(p.x, p.y);
-            S.s_jtv[tid] = make_double2(p.z, p.w);
-            S.s_jf[tid] = __double2float_rn(__dsub_rn(p.x, F.cx));
-            S.s_jf[TJ + tid] = __double2float_rn(__dsub_rn(p.y, F.cy));
-            S.s_jf[2 * TJ + tid] = __double2float_rn(__dsub_rn(p.z, F.ct));
-        }
-        if (tid == 0) s_next = (long long)gridDim.x + (long long)atomicAdd(&P.stats[0], 1ull);
-        __syncthreads();
-
-        // 0: diagonal item; 1: time test needed; 2: the whole item is inside the time window
-        // (every t of a tile lies between the coarse-bucket edges of its first and last element;
-        // rounding is monotone)
-        int variant = 1;
-        if (J < I * JPI + JPI)
-            variant = 0;
-        else if (P.items) {
-            // largest lag the two boxes allow: rn(thi_J - tlo_I) and rn(thi_I - tlo_J)
-            double ilo = INFINITY, ihi = -INFINITY;
+                for (int s = 0; s < JPI; ++s)
+                    bulk_g2s(sbase + O_I + s * REC_D_BYTES, P.recs + (size_t)(I * JPI + s) * REC_BYTES,
+                             REC_D_BYTES, bar_i);
 #pragma unroll
-            for (int q = 0; q < JPI; ++q) {
-                ilo = fmin(ilo, P.bb[(size_t)(I * JPI + q) * 6 + 4]);
-                ihi = fmax(ihi, P.bb[(size_t)(I * JPI + q) * 6 + 5]);
+                for (int s = 0; s < NSTAGE; ++s) {
+                    if (s < L) {
+                        mbar_expect_tx(bar_j + 8 * s, REC_BYTES);
+                        bulk_g2s(sbase + O_J + s * REC_BYTES, P.recs + (size_t)item_J(s) * REC_BYTES,
+                                 REC_BYTES, bar_j + 8 * s);
+                    }
+                }
             }
-            const double jlo = P.bb[(size_t)J * 6 + 4], jhi = P.bb[(size_t)J * 6 + 5];
-            if (__dsub_rn(jhi, ilo) <= P.tmax && __dsub_rn(ihi, jlo) <= P.tmax) variant = 2;
-        } else if (P.sorted &&
-                 __dsub_rn(coarse_hi(S.s_jtv[TJ - 1].x), coarse_lo(S.s_itv[0].x)) <= P.tmax &&
-                 __dsub_rn(coarse_hi(S.s_itv[TI - 1].x), coarse_lo(S.s_jtv[0].x)) <= P.tmax)
-            variant = 2;
-
-        unsigned head = 0, tail = 0, npass = 0;
-        for (int jb = 0; jb < TJ; jb += VG) {
-            if (tail - head > (unsigned)(QW - (VG / JV) * 32))
-                drain<MODE>(S, P, sbase, wq_addr, warp_base, lane, lt, head, tail, npass, false);
-            if (variant == 2)
-                sweep<false, false>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
-            else if (variant == 1)
-                sweep<false, true>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
-            else
-                sweep<true, true>(S, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
-        }
-        drain<MODE>(S, P, sbase, wq_addr, warp_base, lane, lt, head, tail, npass, true);
-        npass_total += npass;
-
-        k = s_next;  // written before this item's second barrier
-        ++items_total;
-        if (++items_done == FLUSH_ITEMS) {
-            __syncthreads();
-            for (int b = tid; b < P.n_bins; b += VT) {
-                my_cnt[b] += S.s_cnt[b];
-                S.s_cnt[b] = 0u;
+            first_run = false;
+            // the thread's own i-points as centred floats (duplicated into both halves), straight
+            // from the records' float rows while the bulk copies are in flight
+            const int warp_base = tid & ~31;
+            f32x2 xf[VR], yf[VR], tf[VR];
+#pragma unroll
+            for (int r = 0; r < VR; ++r) {
+                const int ii = r * VT + tid;
+                const float *gf = reinterpret_cast<const float *>(
+                    P.recs + (size_t)(I * JPI + ii / TJ) * REC_BYTES + REC_F) + (ii % TJ);
+                const float fx = __ldg(gf), fy = __ldg(gf + TJ), ft = __ldg(gf + 2 * TJ);
+                xf[r] = pack2(fx, fx);
+                yf[r] = pack2(fy, fy);
+                tf[r] = pack2(ft, ft);
             }
-            items_done = 0;
+            mbar_wait(bar_i, ph_i);
+            ph_i ^= 1u;
+
+            for (int c = 0; c < L; ++c) {
+                const int st = c % NSTAGE;
+                const int J = item_J(c);
+                const unsigned jbase = O_J + (unsigned)st * REC_BYTES;
+                int ioff[VR];
+#pragma unroll
+                for (int r = 0; r < VR; ++r)
+                    ioff[r] = (I * TI + tid) - J * TJ + r * VT;  // (global i) - (global j of sub-tile start)
+                // 0: diagonal item; 1: time test needed; 2: the whole item is inside the time window
+                // (every t of a tile lies between the coarse-bucket edges of its first and last
+                // element; rounding is monotone)
+                int variant = 1;
+                if (J < I * JPI + JPI)
+                    variant = 0;
+                else if (P.items) {
+                    // largest lag the two boxes allow: rn(thi_J - tlo_I) and rn(thi_I - tlo_J)
+                    double ilo = INFINITY, ihi = -INFINITY;
+#pragma unroll
+                    for (int s = 0; s < JPI; ++s) {
+                        ilo = fmin(ilo, P.bb[(size_t)(I * JPI + s) * 6 + 4]);
+                        ihi = fmax(ihi, P.bb[(size_t)(I * JPI + s) * 6 + 5]);
+                    }
+                    const double jlo = P.bb[(size_t)J * 6 + 4], jhi = P.bb[(size_t)J * 6 + 5];
+                    if (__dsub_rn(jhi, ilo) <= P.tmax && __dsub_rn(ihi, jlo) <= P.tmax) variant = 2;
+                }
+#pragma unroll
+                for (int s = 0; s < NSTAGE; ++s)
+                    if (s == st) {
+                        mbar_wait(bar_j + 8 * s, ph_j[s]);
+                        ph_j[s] ^= 1u;
+                    }
+                if (variant == 1 && !P.items && P.sorted) {
+                    const double jt0 = lds_d(sbase + jbase + REC_TV), jt1 = lds_d(sbase + jbase + REC_TV + 16u * (TJ - 1));
+                    const double it0 = lds_d(sbase + O_I + REC_TV);
+                    const double it1 = lds_d(sbase + O_I + (JPI - 1) * REC_D_BYTES + REC_TV + 16u * (TJ - 1));
+                    if (__dsub_rn(coarse_hi(jt1), coarse_lo(it0)) <= P.tmax &&
+                        __dsub_rn(coarse_hi(it1), coarse_lo(jt0)) <= P.tmax)
+                        variant = 2;
+                }
+                const float *s_jf = reinterpret_cast<const float *>(smem_raw + jbase + REC_F);
+
+                unsigned head = 0, tail = 0, npass = 0;
+                for (int jb = 0; jb < TJ; jb += VG) {
+                    if (tail - head > (unsigned)(QW - (VG / JV) * 32))
+                        drain<MODE, FX>(S, P, sbase, jbase, wq_addr, warp_base, lane, lt, head, tail, npass, false);
+                    if (variant == 2)
+                        sweep<false, false>(s_jf, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
+                    else if (variant == 1)
+                        sweep<false, true>(s_jf, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
+                    else
+                        sweep<true, true>(s_jf, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
+                }
+                drain<MODE, FX>(S, P, sbase, jbase, wq_addr, warp_base, lane, lt, head, tail, npass, true);
+                npass_total += npass;
+                ++items_total;
+
+                // This warp is done with stage st.  The LAST warp to get here refills the stage with
+                // the next-but-one item of the run: nobody waits for anybody inside a run.
+                __syncwarp();
+                if (lane == 0) {
+                    // (this warp's reads of the stage have been consumed: its drain is finished.  No
+                    // __threadfence_block() here: a fence in the kernel turns every fire-and-forget
+                    // REDG of the histogram into an ATOMG that the warp then waits for.)
+                    if (atomicAdd(&s_done[st], 1u) == VT / 32 - 1) {
+                        s_done[st] = 0u;
+                        if (c + NSTAGE < L) {
+                            mbar_expect_tx(bar_j + 8 * st, REC_BYTES);
+                            bulk_g2s(sbase + jbase, P.recs + (size_t)item_J(c + NSTAGE) * REC_BYTES, REC_BYTES,
+                                     bar_j + 8 * st);
+                        }
+                    }
+                }
+            }
+            items_done += (unsigned)L;
+            w += L;
         }
+        kq = *s_next;  // written by thread 0 after the barrier of this chunk's first run
     }
     __syncthreads();
     for (int b = tid; b < P.n_bins; b += VT) {
         my_cnt[b] += S.s_cnt[b];
+        if (FX) {
+            my_limb[b] = S.s_lim[b];
+            my_limb[P.n_bins + b] = S.s_lim[P.n_bins + b];
+            my_limb[2 * P.n_bins + b] = S.s_lim[2 * P.n_bins + b];
+        }
     }
     // stats: pairs inside the window (warp reduce, one atomic per warp)
     for (int off = 16; off > 0; off >>= 1)
@@ -811,23 +1044,80 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
     if (tid == 0 && items_total) atomicAdd(&P.stats[3], (unsigned long long)items_total);
 }
 
+// Exact signed 128-bit integer -> float64 with ONE round-to-nearest-even.
+__device__ __forceinline__ double i128_to_double(__int128 v)
+{
+    const bool neg = v < 0;
+    unsigned __int128 m = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    const unsigned long long hi = (unsigned long long)(m >> 64), lo = (unsigned long long)m;
+    double d;
+    if (hi == 0ull) {
+        d = __ull2double_rn(lo);
+    } else {
+        const int s = 64 - __clzll((long long)hi);              // 1 .. 64: keep the top 64 bits
+        unsigned long long top = (unsigned long long)(m >> s);
+        const unsigned __int128 rest = m & ((((unsigned __int128)1) << s) - 1);
+        if (rest != 0) top |= 1ull;                            // sticky bit (64 - 53 guard bits above it)
+        d = ldexp(__ull2double_rn(top), s);
+    }
+    return neg ? -d : d;
+}
 
-// Fixed-order reduction over the per-block partials + the reference's peeled first pair.
+// Reduction over the per-block partials + the reference's peeled first pair.
+//   FX = true: exact 128-bit integer sums of the limb counters, ONE rounding to float64;
+//   FX = false: FP64 partial sums added in a fixed order (interleaved slices + a binary tree).
+template <bool FX>
 __global__ void __launch_bounds__(1024) reduce_kernel(Params P, int nblocks, const double *x, const double *y,
                               const double *t, const double *v, int64_t n, double smax,
                               double ws, double wt, int peel, int counts_f64, unsigned long long *counts,
                               double *sums)
 {
-    // 1024 threads = 32 bins x 32 slices of the block list: slice s adds the partials of blocks
-    // k = s, s+32, ... in increasing k (coalesced over the bins, all loads of a thread in flight
-    // together), then the 32 slices are combined in a fixed binary tree -- the same order for any
-    // launch, so the result is deterministic.
+    // 1024 threads = 32 bins x 32 slices of the block list: slice s adds the limb counters of
+    // blocks k = s, s+32, ... as 128-bit integers (coalesced over the bins), then the 32 slices
+    // are added.  Integer sums: the result does not depend on the grouping.
     constexpr int NSL = 32;
-    __shared__ double s_acc[NSL][32];
-    __shared__ unsigned long long s_cnt8[NSL][32];
+    __shared__ unsigned long long s_lo[NSL][32], s_hi[NSL][32], s_cnt8[NSL][32];
+    __shared__ unsigned s_poison[NSL][32];
     const int bl = threadIdx.x & 31, ks = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + bl;
-    {
+    double s;
+    unsigned long long c = 0;
+    if (FX) {
+        unsigned __int128 a = 0;
+        unsigned long long cc = 0;
+        unsigned poison = 0;
+        if (b < P.n_bins) {
+            for (int k = ks; k < nblocks; k += NSL) {
+                const unsigned *l = P.partial_limb + (size_t)k * 4 * P.n_bins + b;
+                const unsigned c0 = l[0], c1 = l[P.n_bins], c2 = l[2 * P.n_bins], wr = l[3 * P.n_bins];
+                a += (unsigned __int128)c0 + ((unsigned __int128)c1 << LIMB_BITS) +
+                     ((unsigned __int128)c2 << (2 * LIMB_BITS)) +
+                     ((unsigned __int128)(wr & ~POISON) << (2 * LIMB_BITS + 32));
+                poison |= wr & POISON;
+                cc += P.partial_cnt[(size_t)k * P.n_bins + b];
+            }
+        }
+        s_lo[ks][bl] = (unsigned long long)a;
+        s_hi[ks][bl] = (unsigned long long)(a >> 64);
+        s_cnt8[ks][bl] = cc;
+        s_poison[ks][bl] = poison;
+        __syncthreads();
+        if (ks != 0 || b >= P.n_bins) return;
+        unsigned __int128 tot = 0;
+        poison = 0;
+#pragma unroll 4
+        for (int q = 0; q < NSL; ++q) {
+            tot += ((unsigned __int128)s_hi[q][bl] << 64) | (unsigned __int128)s_lo[q][bl];
+            c += s_cnt8[q][bl];
+            poison |= s_poison[q][bl];
+        }
+        const FilterConst F = *P.filter;
+        // every term carried the bias (covariogram: terms of either sign); remove it exactly
+        const __int128 exact = (__int128)tot - (__int128)F.fx_bias * (__int128)c;
+        s = i128_to_double(exact) * F.fx_inv;
+        if (poison) s = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+        double *s_acc = reinterpret_cast<double *>(&s_lo[0][0]);      // [NSL][32]
         double a = 0.0;
         unsigned long long cc = 0;
         if (b < P.n_bins) {
@@ -837,23 +1127,22 @@ __global__ void __launch_bounds__(1024) reduce_kernel(Params P, int nblocks, con
                 cc += P.partial_cnt[(size_t)k * P.n_bins + b];
             }
         }
-        s_acc[ks][bl] = a;
+        s_acc[ks * 32 + bl] = a;
         s_cnt8[ks][bl] = cc;
+        __syncthreads();
+        if (ks != 0 || b >= P.n_bins) return;
+        double acc[NSL];
+#pragma unroll
+        for (int q = 0; q < NSL; ++q) {
+            acc[q] = s_acc[q * 32 + bl];
+            c += s_cnt8[q][bl];
+        }
+#pragma unroll
+        for (int w = 1; w < NSL; w <<= 1)
+#pragma unroll
+            for (int q = 0; q < NSL; q += 2 * w) acc[q] = acc[q] + acc[q + w];
+        s = acc[0];
     }
-    __syncthreads();
-    if (ks != 0 || b >= P.n_bins) return;
-    double acc[NSL];
-    unsigned long long c = 0;
-#pragma unroll
-    for (int q = 0; q < NSL; ++q) {
-        acc[q] = s_acc[q][bl];
-        c += s_cnt8[q][bl];
-    }
-#pragma unroll
-    for (int w = 1; w < NSL; w <<= 1)
-#pragma unroll
-        for (int q = 0; q < NSL; q += 2 * w) acc[q] = acc[q] + acc[q + w];
-    double s = acc[0];
     if (peel && n >= 2) {
         // rows 0 and 1 of the caller's arrays: the pair kernel binned them with the
         // reciprocal multiply; the reference bins this one pair with a true division.
@@ -898,6 +1187,47 @@ __global__ void __launch_bounds__(1024) reduce_kernel(Params P, int nblocks, con
     sums[b] = s;
 }
 
+// Fixed-order FP64 reduction of per-block partial sums (the sampled-pair branch, whose draws
+// are random anyway).
+__global__ void __launch_bounds__(1024) reduce_f64_kernel(const double *partial_sum,
+                                                          const unsigned long long *partial_cnt, int n_bins,
+                                                          int nblocks, unsigned long long *counts, double *sums)
+{
+    constexpr int NSL = 32;
+    __shared__ double s_acc[NSL][32];
+    __shared__ unsigned long long s_cnt8[NSL][32];
+    const int bl = threadIdx.x & 31, ks = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + bl;
+    {
+        double a = 0.0;
+        unsigned long long cc = 0;
+        if (b < n_bins) {
+#pragma unroll 8
+            for (int k = ks; k < nblocks; k += NSL) {
+                a += partial_sum[(size_t)k * n_bins + b];
+                cc += partial_cnt[(size_t)k * n_bins + b];
+            }
+        }
+        s_acc[ks][bl] = a;
+        s_cnt8[ks][bl] = cc;
+    }
+    __syncthreads();
+    if (ks != 0 || b >= n_bins) return;
+    double acc[NSL];
+    unsigned long long c = 0;
+#pragma unroll
+    for (int q = 0; q < NSL; ++q) {
+        acc[q] = s_acc[q][bl];
+        c += s_cnt8[q][bl];
+    }
+#pragma unroll
+    for (int w = 1; w < NSL; w <<= 1)
+#pragma unroll
+        for (int q = 0; q < NSL; q += 2 * w) acc[q] = acc[q] + acc[q + w];
+    counts[b] = c;
+    sums[b] = acc[0];
+}
+
 
 // ---- sampled-pair branch (el_max / n_samples, stif/utils.py:94-101) -------------------
 // n_samples draws of an ordered pair (i, j), each index uniform in [0, n), i == j skipped
@@ -934,9 +1264,9 @@ struct SampledParams {
     double smax, tmax;
 };
 
-__global__ void __launch_bounds__(VT) sampled_kernel(Params P, SampledParams Q)
+__global__ void __launch_bounds__(VT) sampled_kernel(Params P, SampledParams Q, double *partial_sum)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_sum = reinterpret_cast<double *>(smem_raw);
     unsigned *s_cnt = reinterpret_cast<unsigned *>(s_sum + P.n_bins);
     const int tid = threadIdx.x;
@@ -945,7 +1275,7 @@ __global__ void __launch_bounds__(VT) sampled_kernel(Params P, SampledParams Q)
         s_cnt[b] = 0u;
     }
     unsigned long long *my_cnt = P.partial_cnt + (size_t)blockIdx.x * P.n_bins;
-    double *my_sum = P.partial_sum + (size_t)blockIdx.x * P.n_bins;
+    double *my_sum = partial_sum + (size_t)blockIdx.x * P.n_bins;
     for (int b = tid; b < P.n_bins; b += VT) my_cnt[b] = 0ull;
     __syncthreads();
     const unsigned long long stride = (unsigned long long)gridDim.x * VT;
@@ -1086,9 +1416,9 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     const int n_bins = ns * nt;
     const bool cull = !(flags & STIF_VARIO_NO_CULL);
 
-    // [0..3] counters, [4..9] bounding box (gather_kernel), then the FilterConst
-    STIF_TRY(c->v_stats.reserve(10 * sizeof(unsigned long long) + sizeof(FilterConst)));
-    STIF_CUDA(cudaMemsetAsync(c->v_stats.p, 0, 10 * sizeof(unsigned long long), st));
+    // [0..3] counters, [4..11] bounding box of (x, y, t, v) (bbox_kernel), then the FilterConst
+    STIF_TRY(c->v_stats.reserve(12 * sizeof(unsigned long long) + sizeof(FilterConst)));
+    STIF_CUDA(cudaMemsetAsync(c->v_stats.p, 0, 12 * sizeof(unsigned long long), st));
     STIF_CUDA(cudaEventRecord(c->ev[0], st));
     c->n_phase = 3;
 
@@ -1110,7 +1440,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
                    ((flags & STIF_VARIO_SPACE_SORT) || n >= 160 * 1024);
     if (nJ > 65535 || items_max > (1ll << 27)) spatial = false;
     unsigned long long *ext = c->v_stats.as<unsigned long long>() + 4;
-    FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 6);
+    FilterConst *filter = reinterpret_cast<FilterConst *>(ext + 8);
 
     // 1. sort indices by time (or by time slab and space cell)
     STIF_TRY(c->v_idx.reserve(sizeof(unsigned) * n));
@@ -1124,7 +1454,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         STIF_TRY(c->v_keys.reserve(sizeof(double) * n));
         STIF_TRY(c->v_keys_out.reserve(sizeof(double) * n));
         const double slab_w = fabs(tmax) * (getenv("STIF_VARIO_SLAB") ? atof(getenv("STIF_VARIO_SLAB")) : 0.5);
-        bbox_kernel<<<c->sm_count * 4, tb, 0, st>>>(x, y, t, n, ext);
+        bbox_kernel<<<c->sm_count * 4, tb, 0, st>>>(x, y, t, nullptr, n, ext);
         spacetime_keys_kernel<<<nb_n, tb, 0, st>>>(x, y, t, n, ext, slab_w, c->v_keys.as<unsigned>(),
                                                    c->v_idx.as<unsigned>());
         size_t tmp_bytes = 0;
@@ -1157,15 +1487,17 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         iota_kernel<<<nb_n, tb, 0, st>>>(n, c->v_idx.as<unsigned>());
         order = c->v_idx.as<unsigned>();
     }
-    // 2. gather into sorted, padded AoS
-    STIF_TRY(c->v_pts.reserve(sizeof(double4) * n_pad));
+    // 2. bounding box -> pre-filter / fixed-point constants; gather into sorted, padded records
+    STIF_TRY(c->v_pts.reserve((size_t)REC_BYTES * (size_t)nJ));
     if (c->v_wait_upload) {   // host entry point: x, y, v arrive on the copy stream under the sort
         STIF_CUDA(cudaStreamWaitEvent(st, c->v_upload_ev, 0));
         c->v_wait_upload = false;
     }
-    gather_kernel<<<(unsigned)((n_pad + tb - 1) / tb), tb, 0, st>>>(x, y, t, v, order, n, n_pad,
-                                                                    c->v_pts.as<double4>(), ext);
-    filter_setup_kernel<<<1, 1, 0, st>>>(ext, smax, tmax, filter);
+    if (spatial) bbox_kernel<<<c->sm_count * 4, tb, 0, st>>>(nullptr, nullptr, nullptr, v, n, ext);
+    else bbox_kernel<<<c->sm_count * 4, tb, 0, st>>>(x, y, t, v, n, ext);
+    filter_setup_kernel<<<1, 1, 0, st>>>(ext, smax, tmax, mode, mean, filter);
+    unsigned char *recs = c->v_pts.as<unsigned char>();
+    gather_kernel<<<(unsigned)((n_pad + tb - 1) / tb), tb, 0, st>>>(x, y, t, v, order, n, n_pad, recs, filter);
     // 3. work list
     STIF_TRY(c->v_tileinfo.reserve(sizeof(int) * (3 * (size_t)nI + 1)));
     int *count = c->v_tileinfo.as<int>();
@@ -1179,13 +1511,12 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         STIF_TRY(c->v_items.reserve(sizeof(unsigned) * (size_t)items_max));
         bb = c->v_bb.as<double>();
         items = c->v_items.as<unsigned>();
-        tile_bbox_kernel<<<(nJ + 3) / 4, 128, 0, st>>>(c->v_pts.as<double4>(), nJ, bb);
+        tile_bbox_kernel<<<(nJ + 3) / 4, 128, 0, st>>>(recs, nJ, bb);
         items_kernel<false><<<(nI + 3) / 4, 128, 0, st>>>(bb, nI, nJ, tcut, tmax, count, nullptr, nullptr);
         scan_kernel<<<1, 1024, 0, st>>>(count, nI, prefix);
         items_kernel<true><<<(nI + 3) / 4, 128, 0, st>>>(bb, nI, nJ, tcut, tmax, nullptr, prefix, items);
     } else {
-        tile_range_kernel<<<(nI + 127) / 128, 128, 0, st>>>(c->v_pts.as<double4>(), n, nI, nJ, tmax,
-                                                            cull ? 1 : 0, count, jbeg);
+        tile_range_kernel<<<(nI + 127) / 128, 128, 0, st>>>(recs, n, nI, nJ, tmax, cull ? 1 : 0, count, jbeg);
         scan_kernel<<<1, 1024, 0, st>>>(count, nI, prefix);
     }
     STIF_CUDA(cudaGetLastError());
@@ -1193,7 +1524,7 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
 
     // 4. pair kernel
     Params P;
-    P.pts = c->v_pts.as<double4>();
+    P.recs = recs;
     P.item_prefix = prefix;
     P.item_jbeg = jbeg;
     P.nI = nI;
@@ -1229,10 +1560,11 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         P.thr = c->v_thr.as<double>();
     }
 
-    void (*kern)(Params) = mode == 0 ? pair_kernel<0> : pair_kernel<1>;
-    const size_t smem = sizeof(double4) * (TI + TJ) + sizeof(float4) * TJ +
-                        sizeof(unsigned) * QW * (VT / 32) + sizeof(unsigned) * (size_t)n_bins +
-                        sizeof(double) * ((size_t)ns + 2);
+    const bool fx = (flags & STIF_VARIO_DETERMINISTIC) != 0;
+    void (*kern)(Params) = fx ? (mode == 0 ? pair_kernel<0, true> : pair_kernel<1, true>)
+                              : (mode == 0 ? pair_kernel<0, false> : pair_kernel<1, false>);
+    const size_t smem = O_THR + sizeof(double) * ((size_t)ns + 2) +
+                        (fx ? 4 : 1) * sizeof(unsigned) * (size_t)n_bins;
     STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     int occ = 0;
@@ -1242,19 +1574,24 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
         return STIF_ECUDA;
     }
     const int grid = c->sm_count * occ;
-    STIF_TRY(c->v_partial.reserve((sizeof(double) + sizeof(unsigned long long)) * (size_t)grid *
-                                  n_bins));
-    P.partial_sum = c->v_partial.as<double>();
-    P.partial_cnt = reinterpret_cast<unsigned long long *>(P.partial_sum + (size_t)grid * n_bins);
+    STIF_TRY(c->v_partial.reserve((4 * sizeof(unsigned) + sizeof(unsigned long long)) * (size_t)grid * n_bins));
+    P.partial_cnt = c->v_partial.as<unsigned long long>();
+    P.partial_limb = reinterpret_cast<unsigned *>(P.partial_cnt + (size_t)grid * n_bins);
+    P.partial_sum = reinterpret_cast<double *>(P.partial_limb);     // the two modes share the space
     kern<<<grid, VT, smem, st>>>(P);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[2], st));
 
     // 5. reduce (+ peel fix-up on partition 0)
     const int peel = ((flags & STIF_VARIO_PEEL) && part == 0) ? 1 : 0;
-    reduce_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
-        P, grid, x, y, t, v, n, smax, ws, wt, peel, (flags & STIF_VARIO_COUNTS_F64) ? 1 : 0,
-        reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
+    if (fx)
+        reduce_kernel<true><<<(n_bins + 31) / 32, 1024, 0, st>>>(
+            P, grid, x, y, t, v, n, smax, ws, wt, peel, (flags & STIF_VARIO_COUNTS_F64) ? 1 : 0,
+            reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
+    else
+        reduce_kernel<false><<<(n_bins + 31) / 32, 1024, 0, st>>>(
+            P, grid, x, y, t, v, n, smax, ws, wt, peel, (flags & STIF_VARIO_COUNTS_F64) ? 1 : 0,
+            reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[3], st));
 
@@ -1395,14 +1732,13 @@ extern "C" int stif_variogram_sampled_dev(stif_ctx *c, const double *x, const do
     const unsigned long long want = (n_samples + VT - 1) / VT;
     if ((unsigned long long)grid > want) grid = (int)want;
     STIF_TRY(c->v_partial.reserve((sizeof(double) + sizeof(unsigned long long)) * (size_t)grid * n_bins));
-    P.partial_sum = c->v_partial.as<double>();
-    P.partial_cnt = reinterpret_cast<unsigned long long *>(P.partial_sum + (size_t)grid * n_bins);
-    sampled_kernel<<<grid, VT, smem, st>>>(P, Q);
+    double *partial_sum = c->v_partial.as<double>();
+    P.partial_cnt = reinterpret_cast<unsigned long long *>(partial_sum + (size_t)grid * n_bins);
+    sampled_kernel<<<grid, VT, smem, st>>>(P, Q, partial_sum);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[2], st));
-    reduce_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
-        P, grid, x, y, t, v, n, smax, ws, wt, 0, 0, reinterpret_cast<unsigned long long *>(counts_dev),
-        sums_dev);
+    reduce_f64_kernel<<<(n_bins + 31) / 32, 1024, 0, st>>>(
+        partial_sum, P.partial_cnt, n_bins, grid, reinterpret_cast<unsigned long long *>(counts_dev), sums_dev);
     STIF_CUDA(cudaGetLastError());
     STIF_CUDA(cudaEventRecord(c->ev[3], st));
     return STIF_OK;

@@ -70,10 +70,27 @@ def test_c2_whole_workload_against_oracle_golden(ctx, c2):
     assert_sums_close(sums, g["sums"])
     rel = np.abs(sums - g["sums"]) / np.abs(g["sums"])
     record_quantiles("variogram_c2_sums_vs_oracle", rel=rel.ravel())
-    # run-to-run reproducibility of the FP64 sums (the counts are integers)
+    # Default mode: the FP64 sums are accumulated with L2 atomics, whose order depends on the
+    # scheduling: repeatable to rounding only (bound asserted), the counts are integers.
     c_b, s_b = vario(ctx, x, y, t, v)
     assert np.array_equal(c_b, counts)
-    assert np.array_equal(s_b, sums), "variogram sums are not bitwise reproducible from run to run"
+    assert_sums_close(s_b, sums, rtol=1e-13)
+    # STIF_VARIO_DETERMINISTIC: fixed-point integer sums -- bit-identical from run to run, for any
+    # work list (culled / un-culled / space-time sorted visit the pairs in different orders on
+    # different blocks) and still within 1e-12 of the oracle
+    det = _native.VARIO_PEEL | _native.VARIO_DETERMINISTIC
+    runs = [vario(ctx, x, y, t, v, flags=det) for _ in range(3)]
+    runs.append(vario(ctx, x, y, t, v, flags=det | _native.VARIO_SPACE_SORT))
+    runs.append(vario(ctx, x, y, t, v, flags=det | _native.VARIO_NO_CULL))
+    for c_d, s_d in runs:
+        assert np.array_equal(c_d.astype(np.int64), g["counts"])
+        assert np.array_equal(s_d, runs[0][1]), "deterministic mode: sums differ between runs / work lists"
+    assert_sums_close(runs[0][1], g["sums"])
+    # the observation order does not matter either (every term is the same integer)
+    p = np.random.default_rng(7).permutation(len(x))
+    c_p, s_p = vario(ctx, x[p], y[p], t[p], v[p], flags=_native.VARIO_DETERMINISTIC)
+    c_q, s_q = vario(ctx, x, y, t, v, flags=_native.VARIO_DETERMINISTIC)
+    assert np.array_equal(c_p, c_q) and np.array_equal(s_p, s_q)
 
 
 def test_c2_culled_equals_unculled(ctx, c2):
@@ -293,9 +310,14 @@ def test_c5_indicator_kriging_k100(ctx):
     mscale = np.sum(np.abs(o["w"].astype(np.float64)) * np.abs(z[o["idx"].astype(np.int64)]), axis=1)
     vscale = np.sum(np.abs(o["w"].astype(np.float64) * o["gamma"]), axis=1)
     assert np.all(np.abs(m[:ns] - o["mean"])[rows] <= 1e-9 * mscale[rows])
-    assert np.all(np.abs(s[:ns] ** 2 - o["std"] ** 2)[rows] <= 4e-9 * vscale[rows])
+    # product_sum is not a valid variogram: sum(w gamma) is negative for part of the targets and
+    # the reference's np.sqrt returns NaN there (predictor.py:905) -- same targets on both sides
+    assert np.array_equal(np.isnan(s[:ns])[rows], np.isnan(o["std"])[rows])
+    fin = rows & ~np.isnan(o["std"])
+    assert fin.sum() > 0.5 * ns
+    assert np.all(np.abs(s[:ns] ** 2 - o["std"] ** 2)[fin] <= 4e-9 * vscale[fin])
     rel_m = (np.abs(m[:ns] - o["mean"]) / np.abs(o["mean"]))[rows]
-    rel_v = (np.abs(s[:ns] ** 2 - o["std"] ** 2) / np.abs(o["std"] ** 2))[rows]
+    rel_v = (np.abs(s[:ns] ** 2 - o["std"] ** 2) / np.abs(o["std"] ** 2))[fin]
     q = record_quantiles("c5_f64_vs_oracle", mean_rel=rel_m, var_rel=rel_v,
                          mean_over_scale=(np.abs(m[:ns] - o["mean"]) / mscale)[rows])
     assert q["mean_rel"]["p99"] <= 1e-9 * float(np.quantile((mscale / np.abs(o["mean"]))[rows], 0.99))

@@ -271,3 +271,37 @@ def test_space_sort_nan_inf(ctx):
     x[:] = np.nan
     c = _both_sort_modes(ctx, x, y, t, v, 20.0, 15.0, 10, 8)
     assert c.sum() == 0
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_deterministic_mode(ctx, mode):
+    """STIF_VARIO_DETERMINISTIC: every term enters an integer histogram as a 62-bit fixed-point
+    number (quantum q = 2^-60 .. 2^-59 of the largest possible term R), so the sums are
+    bit-identical between runs and work lists; a bin's sum is within count * q / 2 of the exact
+    sum of its terms -- i.e. 1e-12 relative for any bin whose mean term exceeds 1e-6 R, and an
+    ABSOLUTE 2^-60 R otherwise (sparse bins of nearly equal values keep the default mode's
+    relative accuracy only in the default mode)."""
+    space, t, v = synth(6000, seed=77)
+    v = v * 3.0 + (5.0 if mode == 1 else 0.0)
+    x, y = _native.split_space(space)
+    mean = float(np.mean(v)) if mode == 1 else 0.0
+    h, c = ov.raw(space, t, v, 30.0, 30, 30, 30, mode=mode)
+    outs = []
+    for flags in (_native.VARIO_PEEL | _native.VARIO_DETERMINISTIC,
+                  _native.VARIO_PEEL | _native.VARIO_DETERMINISTIC,
+                  _native.VARIO_PEEL | _native.VARIO_DETERMINISTIC | _native.VARIO_NO_CULL,
+                  _native.VARIO_PEEL | _native.VARIO_DETERMINISTIC | _native.VARIO_SPACE_SORT):
+        outs.append(ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30, mode=mode, mean=mean, flags=flags))
+    for counts, sums in outs:
+        assert np.array_equal(counts.astype(np.float64), c)
+        assert np.array_equal(sums, outs[0][1])                  # bit-identical
+    R = (v.max() - v.min()) ** 2 if mode == 0 else np.max(np.abs(v - mean)) ** 2
+    q = R * 2.0 ** -59
+    bound = RTOL_SUMS * (np.abs(h) if mode == 0 else c * np.var(v)) + c * q
+    assert np.all(np.abs(outs[0][1] - h) <= bound)
+    # non-finite values poison their bins (NaN), like an FP64 sum would, and only those
+    v2 = v.copy()
+    v2[17] = np.nan
+    _, s_nan = ctx.variogram_host(x, y, t, v2, 30.0, 30, 30, 30, mode=0, flags=_native.VARIO_DETERMINISTIC)
+    h2, _ = ov.raw(space, t, v2, 30.0, 30, 30, 30, mode=0, flags=0)
+    assert np.array_equal(np.isnan(s_nan), np.isnan(h2))

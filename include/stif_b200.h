@@ -17,8 +17,9 @@
  *     in, run, copy out and synchronise.
  *   - observations are structure-of-arrays float64 (x, y, t, value).  int64 times and
  *     bool values are converted by the caller; the conversion is exact below 2^53.
- *   - a context is bound to one CUDA device (one process per GPU) and is not
- *     thread-safe.
+ *   - a context is bound to one CUDA device and is not thread-safe; different contexts may be
+ *     used from different host threads concurrently (one process per GPU under torchrun, or one
+ *     thread per GPU in a single process: stif_b200/multi.py).
  */
 #ifndef STIF_B200_H
 #define STIF_B200_H
@@ -43,7 +44,13 @@ typedef struct stif_ctx stif_ctx;
 
 /* ---- context ---------------------------------------------------------------- */
 
-/* Create a context on CUDA device `device` (-1 = current device). */
+/* Number of CUDA devices visible to the process (0 if there is none / no driver). */
+int stif_device_count(void);
+/* Create a context on CUDA device `device` (-1 = current device).  SURVEY 8(b) proposed one
+ * context over a device list, stif_ctx_create(devices, ndev); the C ABI keeps ONE device per
+ * context (its calls enqueue on one stream and return), and a process that wants every GPU of
+ * the box creates one context per device and drives them from one host thread each --
+ * stif_b200/multi.py (MultiContext) does exactly that behind Predictor, no torchrun needed. */
 int stif_ctx_create(int device, stif_ctx **out);
 int stif_ctx_destroy(stif_ctx *ctx);
 const char *stif_last_error(void);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "stif_ctx_destroy": (ctypes.c_int, [_vp]),
     "stif_last_error": (ctypes.c_char_p, []),
     "stif_version": (ctypes.c_int, []),
+    "stif_device_count": (ctypes.c_int, []),
     "stif_sm_count": (ctypes.c_int, [_vp]),
     "stif_variogram_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_double,
                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -373,13 +374,32 @@ class Context:
         return rate.value, ms.value
 
 
+def device_count():
+    return int(load_library().stif_device_count())
+
+
 _default_ctx = None
 
 
 def default_context():
-    """Process-wide context on the current CUDA device (LOCAL_RANK if set)."""
+    """Process-wide context.
+
+    * under torchrun / with STIF_B200_DEVICE set: ONE GPU (LOCAL_RANK / the given index) -- the
+      ranks split the work between them (stif_b200/parallel.py);
+    * otherwise: EVERY visible GPU of the box from this one process (MultiContext: one context and
+      one host thread per device; CUDA_VISIBLE_DEVICES or STIF_B200_DEVICES="0,2,5" narrow the
+      set).  With one visible GPU this is a plain Context."""
     global _default_ctx
     if _default_ctx is None:
-        dev = int(os.environ.get("STIF_B200_DEVICE", os.environ.get("LOCAL_RANK", "-1")))
-        _default_ctx = Context(dev)
+        one = os.environ.get("STIF_B200_DEVICE", os.environ.get("LOCAL_RANK"))
+        if one is not None or "WORLD_SIZE" in os.environ:
+            _default_ctx = Context(int(one if one is not None else -1))
+        else:
+            env = os.environ.get("STIF_B200_DEVICES")
+            devices = [int(d) for d in env.split(",")] if env else list(range(max(device_count(), 1)))
+            if len(devices) > 1:
+                from .multi import MultiContext
+                _default_ctx = MultiContext(devices)
+            else:
+                _default_ctx = Context(devices[0])
     return _default_ctx

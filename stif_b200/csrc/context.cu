@@ -41,7 +41,17 @@ extern "C" {
 
 const char *stif_last_error(void) { return stif::g_err; }
 
-int stif_version(void) { return 100; }
+int stif_version(void) { return 200; }
+
+int stif_device_count(void)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return ndev;
+}
 
 int stif_ctx_create(int device, stif_ctx **out)
 {

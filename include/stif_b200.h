@@ -111,6 +111,17 @@ int stif_variogram_host(stif_ctx *ctx, const double *x, const double *y, const d
                         double mean, int flags, int part, int nparts,
                         uint64_t *counts_host, double *sums_host);
 
+/* The same over the BOUND observation set (stif_kriging_set_obs / stif_kriging_set_residuals:
+ * coordinates and residuals already on the device), optionally restricted to idx_host[n_idx]
+ * (host int64 indices into the bound set, numpy-style negatives allowed; NULL = all of it, n_idx
+ * ignored).  What Predictor.calc_cross_validation needs per fold (stif/predictor.py:293-296,
+ * calc_empirical_variogram(train)): the coordinates are uploaded once per Predictor, a fold that
+ * refits the covariate model replaces the residuals only, and a subset travels as 8 B per
+ * selected observation.  STIF_VARIO_PEEL refers to rows idx[0], idx[1]. */
+int stif_variogram_bound(stif_ctx *ctx, const int64_t *idx_host, int64_t n_idx, double space_dist_max,
+                         double time_dist_max, int n_space_bins, int n_time_bins, int mode, double mean,
+                         int flags, int part, int nparts, uint64_t *counts_host, double *sums_host);
+
 /* Sampled-pair branch of _pair_index_generator (stif/utils.py:94-101), reached when the
  * caller passes el_max: n_samples draws of an ordered pair (i, j) with replacement, each
  * index uniform in [0, n); draws with i == j are skipped but still count.  The reference's

@@ -52,6 +52,9 @@ SIGNATURES = {
                                            ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            _vp, _vp]),
+    "stif_variogram_bound": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "stif_variogram_sampled_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64,
                                                   ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_double,
@@ -183,6 +186,21 @@ class Context:
             self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(v), n, float(space_dist_max),
             float(time_dist_max), int(n_space_bins), int(n_time_bins), int(mode), float(mean),
             int(flags), int(part), int(nparts), _ptr(counts), _ptr(sums)), "stif_variogram_host")
+        shape = (int(n_space_bins), int(n_time_bins))
+        return counts.reshape(shape), sums.reshape(shape)
+
+    def variogram_bound(self, idx, space_dist_max, time_dist_max, n_space_bins, n_time_bins, mode=0, mean=0.0,
+                        flags=VARIO_PEEL, part=0, nparts=1):
+        """Variogram of the bound observation set (kriging_set_obs), restricted to `idx` (int64
+        array) or all of it (idx=None): nothing but the index list travels to the device."""
+        ii = None if idx is None else np.ascontiguousarray(idx, dtype=np.int64).reshape(-1)
+        nb = int(n_space_bins) * int(n_time_bins)
+        counts = np.zeros(max(nb, 0), dtype=np.uint64)
+        sums = np.zeros(max(nb, 0), dtype=np.float64)
+        _check(self._lib.stif_variogram_bound(
+            self._h, _ptr(ii), 0 if ii is None else len(ii), float(space_dist_max), float(time_dist_max),
+            int(n_space_bins), int(n_time_bins), int(mode), float(mean), int(flags), int(part), int(nparts),
+            _ptr(counts), _ptr(sums)), "stif_variogram_bound")
         shape = (int(n_space_bins), int(n_time_bins))
         return counts.reshape(shape), sums.reshape(shape)
 

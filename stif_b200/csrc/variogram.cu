@@ -1675,6 +1675,94 @@ extern "C" int stif_variogram_host(stif_ctx *c, const double *x, const double *y
     return STIF_OK;
 }
 
+namespace stif {
+namespace vario {
+__global__ void select_obs_kernel(const double *ox, const double *oy, const double *ot, const double *ov,
+                                  const long long *idx, int64_t n_idx, int64_t n_obs, double *x, double *y,
+                                  double *t, double *v, int *bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_idx) return;
+    long long k = idx[i];
+    if (k < 0) k += n_obs;                       // numpy-style negative indices
+    if (k < 0 || k >= n_obs) {
+        *bad = 1;
+        k = 0;
+    }
+    x[i] = ox[k];
+    y[i] = oy[k];
+    t[i] = ot[k];
+    v[i] = ov[k];
+}
+}  // namespace vario
+}  // namespace stif
+
+// Variogram / covariogram of the BOUND observation set (stif_kriging_set_obs: coordinates and
+// residuals already on the device), optionally restricted to an index list.  This is what the
+// cross-validation driver needs per fold (stif/predictor.py:293-296 calc_empirical_variogram(train)):
+// the coordinates never travel again, a fold that refits the covariate model replaces only the
+// residuals (stif_kriging_set_residuals), and a subset costs 8 B per selected observation (its
+// index) instead of 32 B.
+extern "C" int stif_variogram_bound(stif_ctx *c, const int64_t *idx_host, int64_t n_idx, double smax,
+                                    double tmax, int ns, int nt, int mode, double mean, int flags, int part,
+                                    int nparts, uint64_t *counts_host, double *sums_host)
+{
+    if (!c) {
+        set_error("stif_variogram_bound: ctx is NULL");
+        return STIF_EINVAL;
+    }
+    if (c->n_obs <= 0 || !c->k_obs.p) {
+        set_error("stif_variogram_bound: no observations bound (stif_kriging_set_obs)");
+        return STIF_ESTATE;
+    }
+    if (ns <= 0 || nt <= 0 || (int64_t)ns * nt > MAX_BINS || n_idx < 0 || !counts_host || !sums_host) {
+        set_error("stif_variogram_bound: bad arguments (n_idx=%lld, bins %d x %d)", (long long)n_idx, ns, nt);
+        return STIF_EINVAL;
+    }
+    STIF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t n_obs = c->n_obs;
+    const double *ox = c->k_obs.as<double>(), *oy = ox + n_obs, *ot = oy + n_obs, *ov = ot + n_obs;
+    const size_t nb = (size_t)ns * nt;
+    const int64_t n = idx_host ? n_idx : n_obs;
+    const size_t arr = (sizeof(double) * (size_t)n + 255) / 256 * 256;
+    // staging: [counts | sums | bad flag] then, for a subset, x y t v and the index list
+    STIF_TRY(c->v_stage.reserve(nb * 16 + 256 + (idx_host ? 5 * arr : 0)));
+    char *base = c->v_stage.as<char>();
+    uint64_t *dc = (uint64_t *)base;
+    double *ds = (double *)(base + nb * 8);
+    int *dbad = (int *)(base + nb * 16);
+    const double *x = ox, *y = oy, *t = ot, *v = ov;
+    if (idx_host) {
+        char *p = base + nb * 16 + 256;
+        double *sx = (double *)p, *sy = (double *)(p + arr), *stt = (double *)(p + 2 * arr), *sv = (double *)(p + 3 * arr);
+        long long *didx = (long long *)(p + 4 * arr);
+        STIF_CUDA(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+        if (n > 0) {
+            STIF_CUDA(cudaMemcpyAsync(didx, idx_host, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, st));
+            select_obs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ox, oy, ot, ov, didx, n, n_obs, sx, sy, stt,
+                                                                          sv, dbad);
+            STIF_CUDA(cudaGetLastError());
+        }
+        x = sx; y = sy; t = stt; v = sv;
+    }
+    const int rc = stif_variogram_dev(c, x, y, t, v, n, smax, tmax, ns, nt, mode, mean, flags, part, nparts, dc, ds, st);
+    if (rc != STIF_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    int bad = 0;
+    STIF_CUDA(cudaMemcpyAsync(counts_host, dc, nb * 8, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaMemcpyAsync(sums_host, ds, nb * 8, cudaMemcpyDeviceToHost, st));
+    if (idx_host) STIF_CUDA(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
+    if (bad) {
+        set_error("stif_variogram_bound: index out of range for %lld bound observations", (long long)n_obs);
+        return STIF_EINVAL;
+    }
+    return STIF_OK;
+}
+
 extern "C" int stif_variogram_sampled_dev(stif_ctx *c, const double *x, const double *y,
                                           const double *t, const double *v, int64_t n, double smax,
                                           double tmax, int ns, int nt, int mode, double mean,

@@ -82,6 +82,24 @@ class MultiContext:
             sums += s
         return counts, sums
 
+    def variogram_bound(self, idx, space_dist_max, time_dist_max, n_space_bins, n_time_bins, mode=0, mean=0.0,
+                        flags=_native.VARIO_PEEL, part=0, nparts=1, n_obs=None):
+        n_sel = (n_obs or 0) if idx is None else len(idx)
+        ctxs = self.contexts if (n_sel >= VARIOGRAM_MIN_OBS and nparts == 1) else self.contexts[:1]
+        self._last_variogram = ctxs
+        n = len(ctxs)
+        if n == 1:
+            return ctxs[0].variogram_bound(idx, space_dist_max, time_dist_max, n_space_bins, n_time_bins, mode=mode,
+                                           mean=mean, flags=flags, part=part, nparts=nparts)
+        outs = self._each(lambda i, c: c.variogram_bound(idx, space_dist_max, time_dist_max, n_space_bins,
+                                                         n_time_bins, mode=mode, mean=mean, flags=flags, part=i,
+                                                         nparts=n), ctxs)
+        counts, sums = outs[0][0].copy(), outs[0][1].copy()
+        for c, s in outs[1:]:
+            counts += c
+            sums += s
+        return counts, sums
+
     def variogram_sampled_host(self, x, y, t, v, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
                                n_samples, mode=0, mean=0.0, seed=None, seed_offset=0):
         n_samples = int(n_samples)

@@ -214,12 +214,55 @@ class Predictor:
                              "residuals")
         return space, time, self._residuals[idxs]
 
+    def _device_variogram(self, idxs, space_dist_max, time_dist_max, n_space_bins, n_time_bins, mode):
+        """All-pairs variogram / covariogram of the training observations `idxs` from the
+        DEVICE-RESIDENT observation set: coordinates are uploaded once per Predictor, residuals
+        when they change (cross-validation refits the covariate model per fold), and a subset
+        travels as its index list only (stif_variogram_bound).  Same arithmetic and result as
+        utils.get_variogram / get_covariogram on the sliced arrays."""
+        self._prepare_geostatistics()
+        if self._residuals is None and self._cov_model is not None:
+            raise ValueError("Covariate model is set, but was not fitted yet. Please fit the "
+                             "covariate model first, so the variogram can be calculated on the "
+                             "residuals")
+        self._upload_observations()
+        n = len(self._data.time_coords)
+        whole = isinstance(idxs, slice) and idxs == slice(None)
+        idx = None if whole else np.arange(n, dtype=np.int64)[idxs]
+        resid = np.asarray(self._residuals, dtype=np.float64)
+        vals = resid if whole else resid[idx]
+        mean = float(np.mean(vals)) if (mode == 1 and len(vals)) else 0.0
+        ctx = self.context
+        rank, ws = parallel.world()
+        kw = dict(mode=mode, mean=mean)
+        if ws > 1:
+            counts, sums = ctx.variogram_bound(idx, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
+                                               part=rank, nparts=ws, **kw)
+            counts, sums = parallel.allreduce_histograms(counts, sums)
+        elif hasattr(ctx, "contexts"):          # MultiContext: every visible GPU takes a partition
+            counts, sums = ctx.variogram_bound(idx, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
+                                               n_obs=n, **kw)
+        else:
+            counts, sums = ctx.variogram_bound(idx, space_dist_max, time_dist_max, n_space_bins, n_time_bins, **kw)
+        norm = counts.astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if mode == 0:
+                out = (sums * 0.5) / norm                       # stif/utils.py:178-188
+            else:
+                out = (sums / norm) / (float(np.var(vals)) if len(vals) else np.nan)   # :267-272
+        out[norm == 0] = np.nan
+        return out, norm, space_dist_max / n_space_bins, time_dist_max / n_time_bins
+
     def calc_empirical_variogram(self, idxs=slice(None), space_dist_max=3, time_dist_max=10,
                                  n_space_bins=10, n_time_bins=10, el_max=None):
-        space, time, residuals = self._variogram_inputs(idxs)
-        variogram, samples_per_bin, width_space, width_time = get_variogram(
-            space, time, residuals, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
-            el_max, ctx=self.context)
+        if el_max is None:
+            variogram, samples_per_bin, width_space, width_time = self._device_variogram(
+                idxs, space_dist_max, time_dist_max, n_space_bins, n_time_bins, 0)
+        else:
+            space, time, residuals = self._variogram_inputs(idxs)
+            variogram, samples_per_bin, width_space, width_time = get_variogram(
+                space, time, residuals, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
+                el_max, ctx=self.context)
         self._variogram = variogram
         self._variogram_bins_space = _bin_centres(n_space_bins, width_space)
         self._variogram_bins_time = _bin_centres(n_time_bins, width_time)
@@ -227,10 +270,14 @@ class Predictor:
 
     def calc_empirical_covariogram(self, idxs=slice(None), space_dist_max=3, time_dist_max=10,
                                    n_space_bins=10, n_time_bins=10, el_max=None):
-        space, time, residuals = self._variogram_inputs(idxs)
-        covariogram, samples_per_bin, width_space, width_time = get_covariogram(
-            space, time, residuals, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
-            el_max, ctx=self.context)
+        if el_max is None:
+            covariogram, samples_per_bin, width_space, width_time = self._device_variogram(
+                idxs, space_dist_max, time_dist_max, n_space_bins, n_time_bins, 1)
+        else:
+            space, time, residuals = self._variogram_inputs(idxs)
+            covariogram, samples_per_bin, width_space, width_time = get_covariogram(
+                space, time, residuals, space_dist_max, time_dist_max, n_space_bins, n_time_bins,
+                el_max, ctx=self.context)
         self._covariogram = covariogram
         self._covariogram_bins_space = _bin_centres(n_space_bins, width_space)
         self._covariogram_bins_time = _bin_centres(n_time_bins, width_time)

@@ -318,3 +318,32 @@ def test_data_get_kriging_idxs_matches_reference_filter(pm10, ctx):
     assert np.array_equal(got, want) and len(want) > 1000
     none = d2.get_kriging_idxs(tsp[:5] + 1e6, tt[:5], 7.5, 11.0, None, context=ctx)
     assert none.shape == (0, 2)
+
+
+def test_device_resident_variogram_of_a_subset(pm10, ctx):
+    """calc_empirical_variogram(idxs=train) runs on the device-resident observation
+    set + an index list (stif_variogram_bound) -- same result as the reference-shaped call on the
+    sliced host arrays, for index arrays, slices, negative indices and the covariogram; a refit of
+    the covariate model in between only replaces the residuals."""
+    data = Data(pm10, space_cols=["x", "y"], time_col="time", predictand_col="PM10",
+                covariate_cols=["x", "y", "time"])
+    p = Predictor(data, LinearRegression(), context=ctx)
+    n = len(pm10)
+    sp, tm = data.space_coords, data.time_coords
+    rng = np.random.default_rng(4)
+    for train, fit_rows in ((np.arange(0, 15000), slice(0, 15000)),
+                            (np.sort(rng.choice(n, 9000, replace=False)), slice(None)),
+                            (slice(2000, 12000), slice(2000, 12000)),
+                            (np.array([-1, -2, 5, 7, 11, 13] + list(range(100, 4000))), slice(None))):
+        p.fit_covariate_model(fit_rows)
+        p.calc_empirical_variogram(train, space_dist_max=6e5, time_dist_max=7, n_space_bins=10, n_time_bins=7)
+        resid = p.get_residuals()
+        vg, norm, _, _ = get_variogram(sp[train], tm[train], resid[train], 6e5, 7, 10, 7, None, ctx=ctx)
+        assert np.array_equal(p._variogram_samples_per_bin, norm)
+        assert np.allclose(p._variogram, vg, rtol=1e-12, atol=0, equal_nan=True)
+        p.calc_empirical_covariogram(train, space_dist_max=5e5, time_dist_max=10, n_space_bins=8, n_time_bins=5)
+        cg, cnorm, _, _ = get_covariogram(sp[train], tm[train], resid[train], 5e5, 10, 8, 5, None, ctx=ctx)
+        assert np.array_equal(p._covariogram_samples_per_bin, cnorm)
+        assert np.allclose(p._covariogram, cg, rtol=1e-9, atol=1e-12, equal_nan=True)
+    with pytest.raises(ValueError):
+        ctx.variogram_bound(np.array([0, n + 5]), 6e5, 7, 10, 7)

@@ -128,15 +128,26 @@ def library_digest():
         return None
 
 
-def ncu_counters(kernel_key):
+def ncu_counters(kernel_key, units):
     """Counters of one launch from a committed ncu capture (profiles/r02_kernel_counters.json,
-    written by tools/ncu_counters.py).  Returned with `build` = digest of the sources the capture
-    was taken on, so a reader sees whether it matches the library that ran (`library_digest`)."""
+    written by tools/ncu_counters.py), scaled linearly from the units of work of the captured
+    launch (pairs / targets) to `units` of this run's launch.  Returned with `build` = digest of
+    the sources the capture was taken on, so a reader sees whether it matches the library that
+    ran (`library_digest`)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_kernel_counters.json")) as f:
-            return json.load(f).get(kernel_key)
+            ent = json.load(f).get(kernel_key)
     except Exception:
         return None
+    if not ent:
+        return None
+    scale = units / float(ent.get("units_in_capture") or units)
+    out = dict(ent)
+    for key in ("warp_instr", "lsu_wavefronts", "shared_wavefronts", "dram_bytes", "dram_read", "dram_write"):
+        if key in out:
+            out[key] = out[key] * scale
+    out["scaled_by"] = scale
+    return out
 
 
 class ClockSampler:
@@ -323,7 +334,7 @@ def bench_variogram(env, workload, steps, warmup):
     lane_instr_per_pair = FP64_PER_PAIR + FP64_PER_BINNED * f_binned
     pair_ms_avg = env.max_over_ranks(pair_ms) / steps
     achieved = pairs * lane_instr_per_pair / world / (pair_ms_avg * 1e-3)   # per GPU
-    cnt = ncu_counters(f"pair_kernel_{workload}") if world == 1 else None
+    cnt = ncu_counters(f"pair_kernel_{workload}", pairs) if world == 1 else None
     roofline = {
         "bound": "fp64_issue", "kernel": "stif::vario::pair_kernel",
         "achieved": achieved, "peak": env.dfma_rate, "unit": "FP64 lane-instr/s per GPU",
@@ -458,7 +469,7 @@ def bench_kriging(env, cfg, steps, warmup, n_targets=0):
     peak_tf = 2 * env.dfma_rate / 1e12
     chol = bool(ss["cholesky_enabled"])
     kname = "stif::krig::solve_chol_kernel" if chol else "stif::krig::solve_blk_kernel (pivoted LU)"
-    cnt = ncu_counters(("solve_chol_" if chol else "solve_lu_") + cfg["name"]) if world == 1 else None
+    cnt = ncu_counters(("solve_chol_" if chol else "solve_lu_") + cfg["name"], n_t) if world == 1 else None
 
     (hx, _a), (hy, _b), (ht, _c) = pinned(tx), pinned(ty), pinned(tt)
     (hm, _d), (hs, _e) = pinned(np.zeros(n_t)), pinned(np.zeros(n_t))      # pinned result buffers
@@ -498,6 +509,7 @@ def bench_kriging(env, cfg, steps, warmup, n_targets=0):
                      "traffic_unit": "bytes per launch (ncu capture of this workload); algorithmic = 40 B "
                                      f"per target = {40 * n_t}",
                      "traffic_source": (cnt or {}).get("source"),
+                     "traffic_capture_build": (cnt or {}).get("build"), "library_build": library_digest(),
                      "peak_source": "2 x measured DFMA lane-instr/s (stif_bench_dfma)"},
         # neighbour search: candidates examined per second and the L2/HBM read rate
         # that implies (bytes per candidate record x candidates; the observation set is L2-resident)

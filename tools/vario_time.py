@@ -14,7 +14,7 @@ for n in sizes:
     t = rng.integers(0, 365, n).astype(np.float64); v = rng.normal(size=n)
     ker, prep, hashes = [], [], set()
     for rep in range(int(os.environ.get("REPS", 5))):
-        c, s = ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30)
+        c, s = ctx.variogram_host(x, y, t, v, 30.0, 30, 30, 30, flags=int(os.environ.get("FLAGS", 1)))
         ph = ctx.last_phase_ms()
         prep.append(ph[0]); ker.append(ph[1])
         hashes.add(hashlib.sha256(s.tobytes()).hexdigest()[:12])

@@ -202,6 +202,11 @@ def test_many_bins(ctx, ns, nt):
     space, t, v = synth(3000, seed=41, int_time=False)
     counts, _ = check(ctx, space, t, v, 35.0, 40.0, ns, nt)
     assert counts.sum() > 0
+    # the deterministic mode keeps four histograms per block in shared memory (131 KB at 8192 bins)
+    x, y = _native.split_space(space)
+    c_d, s_d = ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=_native.VARIO_PEEL | _native.VARIO_DETERMINISTIC)
+    c_e, s_e = ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=_native.VARIO_PEEL | _native.VARIO_DETERMINISTIC)
+    assert np.array_equal(c_d, counts) and np.array_equal(s_d, s_e)
 
 
 @pytest.mark.parametrize("smax", [1e-310, 5e-324, 1e308])

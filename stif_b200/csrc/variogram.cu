@@ -1565,6 +1565,16 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
                               : (mode == 0 ? pair_kernel<0, false> : pair_kernel<1, false>);
     const size_t smem = O_THR + sizeof(double) * ((size_t)ns + 2) +
                         (fx ? 4 : 1) * sizeof(unsigned) * (size_t)n_bins;
+    {
+        int smem_max = 0;
+        STIF_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        if (smem > (size_t)smem_max) {
+            set_error("stif_variogram: %d x %d bins need %zu B of shared memory per block (limit %d)%s", ns, nt,
+                      smem, smem_max, fx ? "; STIF_VARIO_DETERMINISTIC keeps four histograms per block -- use "
+                      "fewer bins or the default mode" : "");
+            return STIF_EINVAL;
+        }
+    }
     STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     int occ = 0;

@@ -204,8 +204,13 @@ def test_many_bins(ctx, ns, nt):
     assert counts.sum() > 0
     # the deterministic mode keeps four histograms per block in shared memory (131 KB at 8192 bins)
     x, y = _native.split_space(space)
-    c_d, s_d = ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=_native.VARIO_PEEL | _native.VARIO_DETERMINISTIC)
-    c_e, s_e = ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=_native.VARIO_PEEL | _native.VARIO_DETERMINISTIC)
+    det = _native.VARIO_PEEL | _native.VARIO_DETERMINISTIC
+    if 36 * 1024 + 8 * (ns + 2) + 16 * ns * nt > 227 * 1024:       # does not fit one block: a clear error
+        with pytest.raises(ValueError, match="STIF_VARIO_DETERMINISTIC"):
+            ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=det)
+        return
+    c_d, s_d = ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=det)
+    c_e, s_e = ctx.variogram_host(x, y, t, v, 35.0, 40.0, ns, nt, flags=det)
     assert np.array_equal(c_d, counts) and np.array_equal(s_d, s_e)
 
 

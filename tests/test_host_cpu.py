@@ -111,6 +111,19 @@ def _gloo_worker(rank, world, port, q):
         b, e = parallel.shard_bounds(n, rank, world)
         h, c = ov.raw(space, t, v, 3.0, 10, 6, 5, i_begin=b, i_end=e)
         counts, sums = parallel.allreduce_histograms(c.astype(np.uint64), h)
+        # the same through the public multi-rank entry point (non-NCCL branch: the host call per rank
+        # with part / nparts, then the ONE fused float64 all-reduce); the context is a stand-in whose
+        # "kernel" is the oracle on this rank's row block
+        class _Ctx:
+            def variogram_host(self, x, y, t_, v_, smax, tmax, ns, nt, mode=0, mean=0.0, flags=1, part=0, nparts=1):
+                assert (part, nparts) == (rank, world)
+                bb, ee = parallel.shard_bounds(len(x), part, nparts)
+                hh, cc = ov.raw(np.column_stack([x, y]), t_, v_, smax, tmax, ns, nt, i_begin=bb, i_end=ee)
+                return cc.astype(np.uint64), hh
+        counts2, sums2 = parallel.variogram_all_ranks(_Ctx(), space[:, 0].copy(), space[:, 1].copy(),
+                                                      t.astype(np.float64), v, 3.0, 10, 6, 5, 0, 0.0)
+        assert np.array_equal(counts2, counts) and np.array_equal(sums2, sums)
+        assert counts2.dtype == np.uint64 and counts2.shape == (6, 5)
         # kriging: shard targets, gather
         vals = np.arange(101, dtype=np.float64)
         idx = np.arange(101 * 3, dtype=np.uint32).reshape(101, 3)

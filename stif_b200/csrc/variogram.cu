@@ -636,13 +636,11 @@ __device__ __forceinline__ void add_fixed(const Smem &S, int bin, double val)
 //   FX = true (STIF_VARIO_DETERMINISTIC): as a fixed-point integer into shared-memory limb
 //     counters (add_fixed): bit-reproducible, ~25 more instructions per binned pair.
 template <int MODE, bool FX>
-__device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigned sbase, unsigned jbase,
-                                         int j, int ii, bool have)
+__device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigned ia, unsigned ja, bool have)
 {
+    // ia / ja: shared-memory byte addresses of the {x,y} halves of the i-point and the j-point
     bool inside = false;
     if (have) {
-        const unsigned ia = sbase + O_I + (unsigned)(ii / TJ) * REC_D_BYTES + 16u * (unsigned)(ii % TJ);
-        const unsigned ja = sbase + jbase + 16u * (unsigned)j;
         const double2 ixy = lds_d2(ia + REC_XY), itv = lds_d2(ia + REC_TV);
         const double2 jxy = lds_d2(ja + REC_XY), jtv = lds_d2(ja + REC_TV);
         const double dx = __dsub_rn(ixy.x, jxy.x);
@@ -693,34 +691,38 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
     return inside;
 }
 
-// Queue entry = (j / JV) | owner lane << 7 | m << 12, m = the 8-bit set of pending pairs between
-// the owner's VR i-points (rows r of the i-tile) and JV consecutive j-points: bit VR h + r.
+// Queue entry (32 bits): bits 0-7 = m, the set of pending pairs between the owner's 2 i-points (rows
+// r of the i-tile) and 4 consecutive j-points (bit 2 h + r); bits 12-16 = owner lane; bits 18-23 =
+// j / 4.  The fields sit where the drain needs them: the lowest pending pair is ffs(e) - 1, clearing it
+// is e & (e - 1), (e >> 8) & 0x1f0 is the owner's byte offset in a 16-byte row of the i-tile and
+// (e >> 12) & 0xfc0 the byte offset of the j group -- 10 instructions per batch less than the first
+// layout (j / 4 | lane << 7 | m << 12), which the drain had to take apart and scale.
 // A batch of 32 entries bins the lowest pending pair of each entry with all lanes active;
 // entries with pairs left are re-queued at the tail (ballot compaction),
 // so every batch but an item's last is full whatever the hit density.  The queue is circular:
 // a batch frees 32 slots before it appends at most 32.
+static_assert(NB == 8 && VR == 2 && TJ == VT && TJ <= 256, "queue entry layout assumes 2 i-points x 4 j-points, TJ = VT <= 256");
 template <int MODE, bool FX>
-__device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned sbase, unsigned jbase,
-                                      unsigned wq_addr, int warp_base, int lane, unsigned lt,
+__device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned ibase, unsigned jaddr,
+                                      unsigned wq_addr, int lane, unsigned lt,
                                       unsigned &head, unsigned &tail, unsigned &npass, bool flush)
 {
+    // ibase: address of row 0, slot warp_base of the i-tile; jaddr: address of the j-sub-tile
     while (tail - head >= 32u || (flush && tail != head)) {
         __syncwarp();
         const unsigned nv = min(tail - head, 32u);
         const bool have = (unsigned)lane < nv;
         unsigned e;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + (((head + lane) & (QW - 1)) << 2)) : "memory");
-        const unsigned m = e >> 12;
-        const unsigned b = (unsigned)__ffs((int)m) - 1u;  // lowest pending pair: row b % VR, j offset b / VR
-        npass += bin_pair<MODE, FX>(S, P, sbase, jbase, ((e & 0x7fu) << LJV) | (b >> LVR),
-                                (b & (VR - 1)) * VT + warp_base + ((e >> 7) & 31u), have) ? 1u : 0u;
-        const unsigned m2 = m & (m - 1u);
-        const bool left = have && m2 != 0u;
+        const unsigned b = (unsigned)__ffs((int)e) - 1u;  // lowest pending pair: row b & 1, j offset b >> 1
+        const unsigned ia = ibase + ((e >> 8) & 0x1f0u) + ((b & 1u) * (unsigned)REC_D_BYTES);
+        const unsigned ja = jaddr + ((e >> 12) & 0xfc0u) + ((b & 6u) << 3);
+        npass += bin_pair<MODE, FX>(S, P, ia, ja, have) ? 1u : 0u;
+        const unsigned e2 = e & (e - 1u);
+        const bool left = have && (e2 & 0xffu) != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, left);
         __syncwarp();
-        if (left)
-            st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2),
-                          (e & 0xfffu) | (m2 << 12));
+        if (left) st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2), e2);
         head += nv;
         tail += __popc(bal);
     }
@@ -812,7 +814,7 @@ __device__ __forceinline__ void sweep(const float *s_jf, const f32x2 (&xf)[VR], 
         const unsigned bal = __ballot_sync(0xffffffffu, any);
         if (any)
             st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2),
-                          tag | (m << 12) | (unsigned)(j >> LJV));
+                          tag | m | ((unsigned)j << 16));     // j is a multiple of 4: (j / 4) << 18
         tail += __popc(bal);
     }
 }
@@ -858,7 +860,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const unsigned wq_addr = sbase + O_Q + (unsigned)(tid >> 5) * QW * 4;
-    const unsigned lt = (1u << lane) - 1u, tag = (unsigned)lane << 7;
+    const unsigned lt = (1u << lane) - 1u, tag = (unsigned)lane << 12;
     unsigned ph_i = 0, ph_j[NSTAGE];
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) ph_j[s] = 0;
@@ -935,7 +937,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
             first_run = false;
             // the thread's own i-points as centred floats (duplicated into both halves), straight
             // from the records' float rows while the bulk copies are in flight
-            const int warp_base = tid & ~31;
+            const unsigned ibase = sbase + O_I + (unsigned)(tid & ~31) * 16u;
             f32x2 xf[VR], yf[VR], tf[VR];
 #pragma unroll
             for (int r = 0; r < VR; ++r) {
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
                 unsigned head = 0, tail = 0, npass = 0;
                 for (int jb = 0; jb < TJ; jb += VG) {
                     if (tail - head > (unsigned)(QW - (VG / JV) * 32))
-                        drain<MODE, FX>(S, P, sbase, jbase, wq_addr, warp_base, lane, lt, head, tail, npass, false);
+                        drain<MODE, FX>(S, P, ibase, sbase + jbase, wq_addr, lane, lt, head, tail, npass, false);
                     if (variant == 2)
                         sweep<false, false>(s_jf, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
                     else if (variant == 1)
@@ -1002,7 +1004,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
                     else
                         sweep<true, true>(s_jf, xf, yf, tf, ioff, F.thi, F.tmaxf, jb, wq_addr, lt, tag, tail);
                 }
-                drain<MODE, FX>(S, P, sbase, jbase, wq_addr, warp_base, lane, lt, head, tail, npass, true);
+                drain<MODE, FX>(S, P, ibase, sbase + jbase, wq_addr, lane, lt, head, tail, npass, true);
                 npass_total += npass;
                 ++items_total;
 

@@ -135,6 +135,8 @@ struct Params {
     int use_thr;          // 0: evaluate sqrt/mul/trunc per binned pair (degenerate widths)
     float inv_ws_f;       // float copy of inv_ws for the first guess
     float guard;          // distance from an integer below which the float guess is re-checked
+    float guard_hi;       // 1 - guard
+    float ns_f;           // (float)n_space_bins
     int sorted;           // observations are time-sorted (culling on)
     const FilterConst *filter;
     // space-time sort mode: explicit item list (I << 16 | J) and the sub-tiles' bounding boxes
@@ -533,6 +535,7 @@ __global__ void items_kernel(const double *bb, int nI, int nJ, double tcut, doub
 }
 
 struct Smem {
+    unsigned cnt_addr;       // shared-memory address of s_cnt
     double *g_sum;           // [n_bins] GLOBAL: this block's partial FP64 sums (default mode)
     unsigned *s_cnt;         // [n_bins] pair counts of this block
     unsigned *s_lim;         // [3][n_bins] limbs of the fixed-point sums (deterministic mode)
@@ -661,8 +664,8 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
             float f = __double2float_rn(d2), sq;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
             const float vf = __fmul_rn(sq, P.inv_ws_f), fl = floorf(vf), fr = __fsub_rn(vf, fl);
-            int bs = __float2int_rz(fminf(vf, (float)P.n_space_bins));
-            if (!(fr > P.guard && fr < 1.0f - P.guard && fl < (float)P.n_space_bins)) {
+            int bs = __float2int_rz(fminf(vf, P.ns_f));
+            if (!(fr > P.guard && fr < P.guard_hi && fl < P.ns_f)) {
                 if (P.use_thr) {
                     const unsigned thr = (unsigned)__cvta_generic_to_shared(S.s_thr);
                     bs = bs < 0 ? 0 : bs;
@@ -684,7 +687,7 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
                 const int bin = bs * P.n_time_bins + bt;
                 if (FX) add_fixed(S, bin, val);
                 else atomicAdd(&S.g_sum[bin], val);
-                atomicAdd(&S.s_cnt[bin], 1u);
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(S.cnt_addr + 4u * (unsigned)bin) : "memory");
             }
         }
     }
@@ -708,12 +711,14 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned i
                                       unsigned &head, unsigned &tail, unsigned &npass, bool flush)
 {
     // ibase: address of row 0, slot warp_base of the i-tile; jaddr: address of the j-sub-tile
+    unsigned rd = ((head + (unsigned)lane) & (QW - 1)) << 2;      // this lane's read offset in the ring
     while (tail - head >= 32u || (flush && tail != head)) {
         __syncwarp();
         const unsigned nv = min(tail - head, 32u);
-        const bool have = (unsigned)lane < nv;
+        const bool have = (rd - (head << 2) & (QW * 4 - 1)) < (nv << 2);   // lane < nv, without the lane id
         unsigned e;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + (((head + lane) & (QW - 1)) << 2)) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + rd) : "memory");
+        rd = (rd + (nv << 2)) & (QW * 4 - 1);
         const unsigned b = (unsigned)__ffs((int)e) - 1u;  // lowest pending pair: row b & 1, j offset b >> 1
         const unsigned ia = ibase + ((e >> 8) & 0x1f0u) + ((b & 1u) * (unsigned)REC_D_BYTES);
         const unsigned ja = jaddr + ((e >> 12) & 0xfc0u) + ((b & 6u) << 3);
@@ -829,8 +834,9 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
     S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
     S.s_lim = S.s_cnt + P.n_bins;
     S.n_bins = P.n_bins;
+    S.cnt_addr = (unsigned)__cvta_generic_to_shared(S.s_cnt);
     unsigned *s_done = reinterpret_cast<unsigned *>(smem_raw + O_BAR + 32);
-    long long *s_next = reinterpret_cast<long long *>(smem_raw + O_BAR + 48);
+    int *s_next = reinterpret_cast<int *>(smem_raw + O_BAR + 48);
     const unsigned bar_i = sbase + O_BAR, bar_j = sbase + O_BAR + 8;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -865,25 +871,31 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) ph_j[s] = 0;
 
-    const long long M = P.item_prefix[P.nI];  // total items
+    const int M = P.item_prefix[P.nI];  // total items (< 2^27 in the space-time mode, int in the other)
     // Items are claimed in chunks of CH consecutive list entries (the list is ordered by i-tile,
     // so a chunk is usually one run over the same i-tile).  CH is the same for every block and
-    // leaves each block >= 12 chunks, so the tail stays short.  This partition owns the chunks q
+    // leaves each block >= 12 chunks, so the tail stays short; with the default CHUNK_MAX = 1 it is
+    // a compile-time 1 and the run / stage loops below fold away.  This partition owns the chunks q
     // with q % nparts == part; a block starts with chunk blockIdx.x of its partition and then
     // takes the next unclaimed one (stats[0] counts the claims beyond the first round): items
-    // differ in cost.  Which block bins which item no longer matters to the result at all: the
-    // counts and the fixed-point sums are integers.
-    long long per = M / ((long long)gridDim.x * P.nparts * 12);
-    const int CH = per < 1 ? 1 : (per > CHUNK_MAX ? CHUNK_MAX : (int)per);
-    const long long NQ = (M + CH - 1) / CH;
+    // differ in cost.  Which block bins which item only changes the order of the FP64 sums (not at
+    // all the counts, and nothing in the deterministic mode).
+    // (32-bit indices on purpose: the kernel is compiled for 64 registers, and every 64-bit loop
+    // variable here was paid for by re-deriving addresses inside the drain.)
+    int CH = 1;
+    if (CHUNK_MAX > 1) {
+        const long long per = (long long)M / ((long long)gridDim.x * P.nparts * 12);
+        CH = per < 1 ? 1 : (per > CHUNK_MAX ? CHUNK_MAX : (int)per);
+    }
+    const int NQ = (M + CH - 1) / CH;
     unsigned long long npass_total = 0;
     unsigned items_done = 0, items_total = 0;
     __syncthreads();
-    for (long long kq = blockIdx.x;;) {
-        const long long q = kq * P.nparts + P.part;
-        if (q >= NQ) break;
-        long long w = q * CH;
-        const long long wend = (w + CH < M) ? w + CH : M;
+    for (int kq = blockIdx.x;;) {
+        const long long q64 = (long long)kq * P.nparts + P.part;
+        if (q64 >= NQ) break;
+        int w = (int)q64 * CH;
+        const int wend = (w + CH < M) ? w + CH : M;
         bool first_run = true;
         while (w < wend) {
             // ---- one run: items w .. w + L - 1 share the i-tile I ----
@@ -901,8 +913,8 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
                 }
                 I = lo;
                 J0 = P.item_jbeg[I] + (int)(w - P.item_prefix[I]);
-                const long long iend = P.item_prefix[I + 1];
-                L = (int)((iend < wend ? iend : wend) - w);
+                const int iend = P.item_prefix[I + 1];
+                L = (iend < wend ? iend : wend) - w;
             }
             auto item_J = [&](int c) -> int {
                 return P.items ? (int)(P.items[w + c] & 0xffffu) : J0 + c;
@@ -918,7 +930,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
                 __syncthreads();
             }
             if (tid == 0) {
-                if (first_run) *s_next = (long long)gridDim.x + (long long)atomicAdd(&P.stats[0], 1ull);
+                if (first_run) *s_next = (int)gridDim.x + (int)atomicAdd(&P.stats[0], 1ull);
                 // the i-tile: the FP64 parts of its JPI records; the first NSTAGE j-sub-tiles
                 mbar_expect_tx(bar_i, JPI * REC_D_BYTES);
 #pragma unroll
@@ -1551,6 +1563,8 @@ extern "C" int stif_variogram_dev(stif_ctx *c, const double *x, const double *y,
     P.filter = filter;
     P.use_thr = (P.inv_ws > 0.0 && isfinite(P.inv_ws) && isfinite((double)P.inv_ws_f)) ? 1 : 0;
     if (!P.use_thr) P.guard = 2.0f;  // no pair trusts the float guess
+    P.guard_hi = 1.0f - P.guard;
+    P.ns_f = (float)ns;
     {
         // context-owned host copy: stays valid until the next call, so no synchronisation
         std::vector<double> &thr = c->v_thr_host;

@@ -555,6 +555,15 @@ constexpr unsigned O_THR = O_BAR + 64;                    // s_thr, then s_cnt, 
 // O_BAR + 0: full barrier of the i-tile; + 8 (1 + s): full barrier of j stage s;
 // + 32 + 4 s: warps done with stage s; + 48: next chunk (long long)
 
+// Keep a value in a register: the result of an `asm volatile` cannot be re-derived, so the compiler
+// does not rematerialise it (from %tid / %cluster_ctaid / kernel parameters) inside the hot loops.
+__device__ __forceinline__ unsigned pin_u32(unsigned v)
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 __device__ __forceinline__ void st_shared_u32(unsigned addr, unsigned v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -712,14 +721,32 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned i
 {
     // ibase: address of row 0, slot warp_base of the i-tile; jaddr: address of the j-sub-tile
     unsigned rd = ((head + (unsigned)lane) & (QW - 1)) << 2;      // this lane's read offset in the ring
-    while (tail - head >= 32u || (flush && tail != head)) {
+    // full batches: every lane has an entry, no predicate on the way
+    while (tail - head >= 32u) {
         __syncwarp();
-        const unsigned nv = min(tail - head, 32u);
-        const bool have = (rd - (head << 2) & (QW * 4 - 1)) < (nv << 2);   // lane < nv, without the lane id
         unsigned e;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + rd) : "memory");
-        rd = (rd + (nv << 2)) & (QW * 4 - 1);
+        rd = (rd + 128u) & (QW * 4 - 1);
         const unsigned b = (unsigned)__ffs((int)e) - 1u;  // lowest pending pair: row b & 1, j offset b >> 1
+        const unsigned ia = ibase + ((e >> 8) & 0x1f0u) + ((b & 1u) * (unsigned)REC_D_BYTES);
+        const unsigned ja = jaddr + ((e >> 12) & 0xfc0u) + ((b & 6u) << 3);
+        npass += bin_pair<MODE, FX>(S, P, ia, ja, true) ? 1u : 0u;
+        const unsigned e2 = e & (e - 1u);
+        const bool left = (e2 & 0xffu) != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, left);
+        __syncwarp();
+        if (left) st_shared_u32(wq_addr + (((tail + __popc(bal & lt)) & (QW - 1)) << 2), e2);
+        head += 32u;
+        tail += __popc(bal);
+    }
+    // the item's last, partial batches
+    while (flush && tail != head) {
+        __syncwarp();
+        const unsigned nv = min(tail - head, 32u);
+        const bool have = (unsigned)lane < nv;
+        unsigned e;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(wq_addr + (((head + lane) & (QW - 1)) << 2)) : "memory");
+        const unsigned b = (unsigned)__ffs((int)e) - 1u;
         const unsigned ia = ibase + ((e >> 8) & 0x1f0u) + ((b & 1u) * (unsigned)REC_D_BYTES);
         const unsigned ja = jaddr + ((e >> 12) & 0xfc0u) + ((b & 6u) << 3);
         npass += bin_pair<MODE, FX>(S, P, ia, ja, have) ? 1u : 0u;
@@ -834,7 +861,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
     S.s_cnt = reinterpret_cast<unsigned *>(S.s_thr + P.n_space_bins + 2);
     S.s_lim = S.s_cnt + P.n_bins;
     S.n_bins = P.n_bins;
-    S.cnt_addr = (unsigned)__cvta_generic_to_shared(S.s_cnt);
+    S.cnt_addr = pin_u32((unsigned)__cvta_generic_to_shared(S.s_cnt));
     unsigned *s_done = reinterpret_cast<unsigned *>(smem_raw + O_BAR + 32);
     int *s_next = reinterpret_cast<int *>(smem_raw + O_BAR + 48);
     const unsigned bar_i = sbase + O_BAR, bar_j = sbase + O_BAR + 8;
@@ -949,7 +976,7 @@ __global__ void __launch_bounds__(VT, MINB) pair_kernel(Params P)
             first_run = false;
             // the thread's own i-points as centred floats (duplicated into both halves), straight
             // from the records' float rows while the bulk copies are in flight
-            const unsigned ibase = sbase + O_I + (unsigned)(tid & ~31) * 16u;
+            const unsigned ibase = pin_u32(sbase + O_I + (unsigned)(tid & ~31) * 16u);
             f32x2 xf[VR], yf[VR], tf[VR];
 #pragma unroll
             for (int r = 0; r < VR; ++r) {

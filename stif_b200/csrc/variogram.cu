@@ -648,7 +648,8 @@ __device__ __forceinline__ void add_fixed(const Smem &S, int bin, double val)
 //   FX = true (STIF_VARIO_DETERMINISTIC): as a fixed-point integer into shared-memory limb
 //     counters (add_fixed): bit-reproducible, ~25 more instructions per binned pair.
 template <int MODE, bool FX>
-__device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigned ia, unsigned ja, bool have)
+__device__ __forceinline__ void bin_pair(const Smem &S, const Params &P, unsigned ia, unsigned ja, bool have,
+                                         unsigned &npass)
 {
     // ia / ja: shared-memory byte addresses of the {x,y} halves of the i-point and the j-point
     bool inside = false;
@@ -661,6 +662,7 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
         const double lag_t = fabs(__dsub_rn(itv.x, jtv.x));
         inside = (d2 <= P.tcut) && (lag_t <= P.tmax);  // utils.py:160-165
         if (inside) {
+            ++npass;                                   // statistics: pairs inside the window
             // both bin indices are bounded by the cut-offs that let the pair in (lag <= max =
             // n_bins * width), so 32-bit conversions are exact.
             // trunc(sqrt_rn(d2)*inv_ws) is monotone in d2: the bin is looked up in the exact d2
@@ -700,7 +702,6 @@ __device__ __forceinline__ bool bin_pair(const Smem &S, const Params &P, unsigne
             }
         }
     }
-    return inside;
 }
 
 // Queue entry (32 bits): bits 0-7 = m, the set of pending pairs between the owner's 2 i-points (rows
@@ -730,7 +731,7 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned i
         const unsigned b = (unsigned)__ffs((int)e) - 1u;  // lowest pending pair: row b & 1, j offset b >> 1
         const unsigned ia = ibase + ((e >> 8) & 0x1f0u) + ((b & 1u) * (unsigned)REC_D_BYTES);
         const unsigned ja = jaddr + ((e >> 12) & 0xfc0u) + ((b & 6u) << 3);
-        npass += bin_pair<MODE, FX>(S, P, ia, ja, true) ? 1u : 0u;
+        bin_pair<MODE, FX>(S, P, ia, ja, true, npass);
         const unsigned e2 = e & (e - 1u);
         const bool left = (e2 & 0xffu) != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, left);
@@ -749,7 +750,7 @@ __device__ __forceinline__ void drain(const Smem &S, const Params &P, unsigned i
         const unsigned b = (unsigned)__ffs((int)e) - 1u;
         const unsigned ia = ibase + ((e >> 8) & 0x1f0u) + ((b & 1u) * (unsigned)REC_D_BYTES);
         const unsigned ja = jaddr + ((e >> 12) & 0xfc0u) + ((b & 6u) << 3);
-        npass += bin_pair<MODE, FX>(S, P, ia, ja, have) ? 1u : 0u;
+        bin_pair<MODE, FX>(S, P, ia, ja, have, npass);
         const unsigned e2 = e & (e - 1u);
         const bool left = have && (e2 & 0xffu) != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, left);

@@ -66,7 +66,10 @@ constexpr int QW = STIF_VARIO_QW;  // entries (uint32) of a warp's circular queu
 constexpr int NB = STIF_VARIO_NB;  // pair tests per lane and vote = bits of a queue entry's mask
 constexpr int JV = NB / VR;    // j-points per queue entry
 constexpr int LVR = VR == 4 ? 2 : 1, LJV = (NB == 16 ? 4 : 3) - LVR;
-constexpr int MINB = VR == 4 ? 3 : 4;  // resident CTAs per SM the kernel is compiled for
+#ifndef STIF_VARIO_MINB
+#define STIF_VARIO_MINB 4
+#endif
+constexpr int MINB = STIF_VARIO_MINB;  // resident CTAs per SM the kernel is compiled for (64 registers)
 constexpr int VG = JV > 4 ? JV : 4;  // j-points between queue checks
 constexpr int MAX_BINS = 8192; // histogram limit (16 B of shared memory per bin)
 constexpr unsigned FLUSH_ITEMS = 8192;  // 2^13 items x TI*TJ (<= 2^18) pairs < 2^32: u32 counts are safe

@@ -415,11 +415,11 @@ def bench_variogram(env, workload, steps, warmup):
                              "counts_bit_exact": counts_ok, "sums_max_rel_err": sums_rel},
         },
         "clocks": clocks, "e2e": e2e,
-        # own kernels per step, time-sorted mode: pack_keys, gather, filter_setup, tile_range, scan,
-        # pair, reduce; space-time sort mode (from 163 840 observations): bbox, spacetime_keys,
-        # gather, filter_setup, tile_bbox, items (count), scan, items (fill), pair, reduce
-        # (the CUB radix-sort passes in between are library launches and not counted)
-        "gpu_launches": (10 if spatial else 7) * steps,
+        # own kernels per step, time-sorted mode: pack_keys, bbox, filter_setup, gather, tile_range,
+        # scan, pair, reduce; space-time sort mode (from 163 840 observations): bbox (x, y, t),
+        # spacetime_keys, bbox (v), filter_setup, gather, tile_bbox, items (count), scan, items (fill),
+        # pair, reduce (the CUB radix-sort passes in between are library launches and not counted)
+        "gpu_launches": (11 if spatial else 8) * steps,
         "roofline": roofline, "wall_s_bracket": wall_bracket,
     }
     del dx, dy, dt_, dv
@@ -498,7 +498,9 @@ def bench_kriging(env, cfg, steps, warmup, n_targets=0):
         "e2e": {"value": n_t * world / e2e_s, "unit": "predictions/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t,
                 "path": "stif_kriging_predict_host (pinned host arrays), per rank"},
-        "gpu_launches": 6 * steps,     # target_keys, search, solve (Cholesky and/or LU), min-norm, stats
+        # target_keys, search, [Cholesky solve,] pivoted LU (the whole set, or the Cholesky fail list),
+        # minimum-norm re-solve of flagged targets, stats
+        "gpu_launches": (6 if chol else 5) * steps,
         "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s per GPU", "frac": achieved / peak_tf,
                      "flops_per_prediction": f_solve,

@@ -198,6 +198,15 @@ int stif_kriging_set_model(stif_ctx *ctx, int st_model, int space_model, int tim
 int stif_variogram_model_eval(stif_ctx *ctx, const double *h, const double *t, int64_t n,
                               double *gamma_out);
 
+/* calc_kriging_weights (stif/predictor.py:566-593) as a stand-alone call -- the callable the
+ * reference installs as Predictor._kriging_weights_function: ordinary-kriging weights (float64) of ONE
+ * neighbour set from its coordinates xs, ys, ts [k] and gamma-vector [k] under the current model.
+ * Solved like np.linalg.lstsq (SVD of the bordered matrix [Gamma 1; 1' 0], minimum-norm solution if it
+ * is rank-deficient).  Host pointers, k <= 128.  Not a hot path: get_kriging_prediction assembles and
+ * solves its systems inside stif_kriging_predict_*. */
+int stif_kriging_weights_host(stif_ctx *ctx, const double *xs, const double *ys, const double *ts,
+                              const double *gamma_vec, int k, double *w_out);
+
 /* Objective of the variogram-model fit (stif/variogram_models.py:221-308: prediction_grid +
  * weighted_mean_square_error, called by scipy's Nelder-Mead from Predictor.fit_variogram_model,
  * stif/predictor.py:738-753).  The optimiser stays on the host; only the objective moves.

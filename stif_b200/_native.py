@@ -71,6 +71,7 @@ SIGNATURES = {
     "stif_kriging_set_residuals": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int]),
     "stif_kriging_set_model": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, _vp, ctypes.c_int]),
+    "stif_kriging_weights_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "stif_variogram_model_eval": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
     "stif_fit_set_grid": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
     "stif_fit_wmse": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
@@ -284,6 +285,18 @@ class Context:
         _check(self._lib.stif_kriging_set_model(
             self._h, ST_MODELS[st_model], MARGINAL_MODELS[space_model], MARGINAL_MODELS[time_model],
             MARGINAL_MODELS[metric_model], _ptr(p), len(p)), "stif_kriging_set_model")
+
+    def kriging_weights(self, xs, ys, ts, gamma_vec):
+        """Ordinary-kriging weights (float64) of one neighbour set: calc_kriging_weights of the
+        reference (stif/predictor.py:566-593), solved like np.linalg.lstsq on the device."""
+        xs, ys, ts, g = _f64(xs).ravel(), _f64(ys).ravel(), _f64(ts).ravel(), _f64(gamma_vec).ravel()
+        k = len(g)
+        if not (len(xs) == k and len(ys) == k and len(ts) == k):
+            raise ValueError("coordinates and kriging vector must have the same length")
+        w = np.empty(k, dtype=np.float64)
+        _check(self._lib.stif_kriging_weights_host(self._h, _ptr(xs), _ptr(ys), _ptr(ts), _ptr(g), k, _ptr(w)),
+               "stif_kriging_weights")
+        return w
 
     def variogram_model_eval(self, h, t):
         h_b, t_b = np.broadcast_arrays(np.asarray(h, dtype=np.float64), np.asarray(t, dtype=np.float64))

@@ -1232,7 +1232,8 @@ __global__ void __launch_bounds__(WPT * 32) solve_blk_kernel(SolveParams P, int 
 // A rare path (statistics out[3] counts it): clarity over speed.
 constexpr int MN_THREADS = 128;
 
-__global__ void __launch_bounds__(MN_THREADS) solve_minnorm_kernel(SolveParams P, double *vscratch)
+__global__ void __launch_bounds__(MN_THREADS) solve_minnorm_kernel(SolveParams P, double *vscratch,
+                                                                   double *w64_out /* nullable: float64 weights */)
 {
     extern __shared__ __align__(16) double smem_d[];
     constexpr int NW = MN_THREADS / 32;
@@ -1361,6 +1362,8 @@ __global__ void __launch_bounds__(MN_THREADS) solve_minnorm_kernel(SolveParams P
             sol[r] = acc;
         }
         __syncthreads();
+        if (w64_out)
+            for (int r = tid; r < m; r += MN_THREADS) w64_out[(size_t)tg * k + r] = sol[r];
         if (warp == 0)
             solve_epilogue(P, sol, g0, ids, rs, sc64, sc32, sc32 + nmax, m, tg, lane);
     }
@@ -2099,7 +2102,8 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             STIF_TRY(c->k_scratch[S_MINNORM].reserve(sizeof(double) * (size_t)mn_grid * nmax * nmax));
             STIF_CUDA(cudaFuncSetAttribute(solve_minnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)mn_smem));
-            solve_minnorm_kernel<<<mn_grid, MN_THREADS, mn_smem, st>>>(QP, c->k_scratch[S_MINNORM].as<double>());
+            solve_minnorm_kernel<<<mn_grid, MN_THREADS, mn_smem, st>>>(QP, c->k_scratch[S_MINNORM].as<double>(),
+                                                                       nullptr);
             STIF_CUDA(cudaGetLastError());
         }
         stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,
@@ -2226,6 +2230,75 @@ extern "C" int stif_kriging_predict_host(stif_ctx *c, const double *tx, const do
     STIF_TRY(stats_to_host(c, st));
     STIF_CUDA(cudaStreamSynchronize(st));
     return nonfinite_check(c);
+}
+
+// calc_kriging_weights (stif/predictor.py:566-593) as a stand-alone call: the ordinary-kriging
+// weights of ONE neighbour set, given its coordinates and gamma-vector -- the callable the reference
+// installs as Predictor._kriging_weights_function.  Solved like np.linalg.lstsq (SVD of the bordered
+// matrix, minimum norm if rank-deficient) by the Jacobi kernel, in float64.  Host pointers.
+extern "C" int stif_kriging_weights_host(stif_ctx *c, const double *xs, const double *ys, const double *ts,
+                                         const double *gamma_vec, int k, double *w_out)
+{
+    STIF_TRY(check_ctx(c, "stif_kriging_weights"));
+    if (c->model.st_model < 0) {
+        set_error("Create variogram model function first.");      // predictor.py:559-560
+        return STIF_ESTATE;
+    }
+    if (k < 1 || k > KMAX || !xs || !ys || !ts || !gamma_vec || !w_out) {
+        set_error("stif_kriging_weights: bad arguments (k = %d, limit %d)", k, KMAX);
+        return STIF_EINVAL;
+    }
+    Model M;
+    STIF_TRY(build_model(c->model, M));
+    const int nmax = k + 1;
+    // one staging block: obs4[k] | gamma[k] | w64[k] | mean, std | V[nmax^2] | idx[k] | sel_n, list, count, singular
+    const size_t n_d = 4 * (size_t)k + k + k + 2 + (size_t)nmax * nmax;
+    STIF_TRY(c->k_scratch[S_EVAL].reserve(sizeof(double) * n_d + sizeof(unsigned) * ((size_t)k + 8)));
+    double *d = c->k_scratch[S_EVAL].as<double>();
+    double4 *obs4 = reinterpret_cast<double4 *>(d);
+    double *dg = d + 4 * (size_t)k, *dw = dg + k, *dms = dw + k, *dV = dms + 2;
+    unsigned *du = reinterpret_cast<unsigned *>(dV + (size_t)nmax * nmax);
+    std::vector<double> h(5 * (size_t)k);
+    std::vector<unsigned> hu((size_t)k + 8, 0u);
+    for (int e = 0; e < k; ++e) {
+        h[4 * e] = xs[e];
+        h[4 * e + 1] = ys[e];
+        h[4 * e + 2] = ts[e];
+        h[4 * e + 3] = 0.0;
+        h[4 * (size_t)k + e] = gamma_vec[e];
+        hu[e] = (unsigned)e;
+    }
+    hu[k] = (unsigned)k;        // sel_n[0] = k
+    hu[k + 1] = 0u;             // sing_list[0] = target 0
+    hu[k + 2] = 1u;             // sing_count
+    cudaStream_t st = c->stream;
+    STIF_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+    STIF_CUDA(cudaMemcpyAsync(du, hu.data(), sizeof(unsigned) * hu.size(), cudaMemcpyHostToDevice, st));
+    SolveParams QP;
+    memset(&QP, 0, sizeof(QP));
+    QP.oresid = dg;             // read (not used) by the float32-storage epilogue only
+    QP.c0 = 0;
+    QP.n = 1;
+    QP.k = k;
+    QP.flags = 0;
+    QP.M = M;
+    QP.sel_n = reinterpret_cast<const int *>(du + k);
+    QP.sel_idx = du;
+    QP.sel_gamma = dg;
+    QP.mean = dms;
+    QP.std = dms + 1;
+    QP.singular = du + k + 3;
+    QP.sing_list = du + k + 1;
+    QP.sing_count = du + k + 2;
+    QP.obs4 = obs4;
+    const size_t mn_smem = sizeof(double) * ((size_t)nmax * nmax + 10 * (size_t)nmax) +
+                           sizeof(float) * 2 * (size_t)nmax + sizeof(unsigned) * (size_t)nmax;
+    STIF_CUDA(cudaFuncSetAttribute(solve_minnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mn_smem));
+    solve_minnorm_kernel<<<1, MN_THREADS, mn_smem, st>>>(QP, dV, dw);
+    STIF_CUDA(cudaGetLastError());
+    STIF_CUDA(cudaMemcpyAsync(w_out, dw, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, st));
+    STIF_CUDA(cudaStreamSynchronize(st));
+    return STIF_OK;
 }
 
 extern "C" int stif_debug_numpy_row_sum(stif_ctx *c, const void *rows, int n_rows, int k, int is_f32,

@@ -142,6 +142,9 @@ class MultiContext:
     def variogram_model_eval(self, h, t):
         return self.contexts[0].variogram_model_eval(h, t)
 
+    def kriging_weights(self, xs, ys, ts, gamma_vec):
+        return self.contexts[0].kriging_weights(xs, ys, ts, gamma_vec)
+
     def fit_set_grid(self, bins_space, bins_time, empirical, weights):
         return self.contexts[0].fit_set_grid(bins_space, bins_time, empirical, weights)
 

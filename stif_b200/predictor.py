@@ -401,10 +401,15 @@ class Predictor:
         return parallel.kriging_all_ranks(run, len(tt))
 
     def _device_kriging_weights(self, kriging_vector, coords_spatial, coords_temporal):
-        """Reference signature of calc_kriging_weights (stif/predictor.py:567-593) is kept for
-        introspection only; the device solves the systems inside `_device_kriging`."""
-        raise NotImplementedError("kriging systems are assembled and solved on the device inside "
-                                  "_get_kriging_weights / get_kriging_prediction")
+        """calc_kriging_weights (stif/predictor.py:566-593): ordinary-kriging weights of ONE
+        neighbour set from its gamma-vector and coordinates, solved on the device like the
+        reference's np.linalg.lstsq (minimum norm if rank-deficient).  get_kriging_prediction does
+        not go through here: it assembles and solves its systems inside the fused device call."""
+        if getattr(self.context, "_model_owner", None) is not self:
+            self._push_model()
+        cs = np.asarray(coords_spatial, dtype=np.float64).reshape(-1, 2)
+        return self.context.kriging_weights(cs[:, 0], cs[:, 1], np.asarray(coords_temporal, dtype=np.float64),
+                                            kriging_vector)
 
     def _get_kriging_weights(self, space, time, min_kriging_points=10, max_kriging_points=100,
                              space_dist_max=None, time_dist_max=None, leave_out_idxs=None):

@@ -398,3 +398,27 @@ def test_bitwise_reproducible(ctx, models, params, k):
     b = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 30.0, 30.0, f32=False)
     for key in ("mean", "std", "w", "gamma", "idx", "n_used"):
         assert np.array_equal(a[key], b[key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("models,params", [(SUM_METRIC, P_SUM_METRIC), (PRODUCT_SUM, P_PRODUCT_SUM),
+                                           (("sum_metric", "gaussian", "spherical", "gaussian"), P_SUM_METRIC)])
+def test_stand_alone_kriging_weights(ctx, models, params):
+    """calc_kriging_weights (stif/predictor.py:566-593) as a call of its own -- the callable the
+    reference installs as _kriging_weights_function -- against the oracle's dgelsd solve."""
+    rng = np.random.default_rng(17)
+    ctx.kriging_set_model(*models, params)
+    for k in (1, 2, 7, 33, 100, 128):
+        xs, ys, ts = rng.uniform(0, 40, k), rng.uniform(0, 40, k), rng.uniform(0, 40, k)
+        g0 = ok.gamma(models, params, np.hypot(xs - 20.0, ys - 20.0), np.abs(ts - 41.0))
+        w = ctx.kriging_weights(xs, ys, ts, g0)
+        w_ref, rank = ok.weights(xs, ys, ts, g0, models, params)
+        assert rank == k + 1
+        assert abs(w.sum() - 1.0) < 1e-9
+        assert np.all(np.abs(w - w_ref) <= 1e-9 * np.abs(w_ref).max()), k
+    from stif_b200 import Data, Predictor
+    import pandas as pd
+    df = pd.DataFrame({"x": xs, "y": ys, "time": ts, "z": rng.normal(size=len(xs))})
+    p = Predictor(Data(df, space_cols=["x", "y"], time_col="time", predictand_col="z"), context=ctx)
+    p.set_variogram_model(params, *models)
+    w2 = p._kriging_weights_function(g0, np.column_stack([xs, ys]), ts)     # the reference's signature
+    assert np.array_equal(w2, w)

@@ -229,6 +229,11 @@ int stif_fit_wmse(stif_ctx *ctx, int st_model, int space_model, int time_model, 
                                    Cholesky fast path that valid variogram models take) */
 #define STIF_KRIG_TRY_CHOL 4    /* try the Cholesky fast path for any model (targets whose
                                    covariance matrix is not positive definite still go to the LU) */
+#define STIF_KRIG_TRY_LDL 8     /* solve every model's systems with the symmetric indefinite solver
+                                   (Bunch-Kaufman LDL' of the bordered system, one warp per target) that
+                                   models which are not valid variograms -- product, product_sum,
+                                   a negative total nugget -- take by default; targets with a tiny pivot
+                                   or a non-finite entry still go to the LU.  STIF_KRIG_FORCE_LU wins. */
 
 /* Predict n_targets points.  leave_out may be NULL; entry < 0 = none
  * (stif/data.py:204-205).  mean_out/std_out: n_targets doubles.  Optional outputs
@@ -258,9 +263,10 @@ int stif_kriging_predict_dev(stif_ctx *ctx, const double *tx, const double *ty,
  *          zero total nugget): they are solved by the minimum-norm path. */
 int stif_kriging_stats(stif_ctx *ctx, uint64_t out[4]);
 
-/* out[0] = targets of the last call that the covariance-form Cholesky kernel handed to the
- * pivoted LU (not positive definite / singular); out[1] = 1 if the Cholesky path was enabled
- * for the call's model, else 0. */
+/* out[0] = targets of the last call that the first-pass solver (the covariance-form Cholesky
+ * kernel, or the symmetric indefinite LDL' kernel) handed to the pivoted LU (not positive
+ * definite / tiny pivot / non-finite); out[1] = bit 0: the Cholesky path was enabled for the
+ * call's model, bit 1: the LDL' path was. */
 int stif_kriging_solver_stats(stif_ctx *ctx, uint64_t out[2]);
 
 /* Device time in ms of the phases of the last call, measured with CUDA events on the

@@ -27,6 +27,7 @@ VARIO_COUNTS_F64 = 16  # variogram_dev: counts written as float64 (one fused all
 KRIG_F32_STORAGE = 1
 KRIG_FORCE_LU = 2
 KRIG_TRY_CHOL = 4
+KRIG_TRY_LDL = 8
 
 ST_MODELS = {"sum": 0, "product": 1, "product_sum": 2, "metric": 3, "sum_metric": 4}
 MARGINAL_MODELS = {"spherical": 0, "gaussian": 1}
@@ -378,7 +379,8 @@ class Context:
     def kriging_solver_stats(self):
         out = (ctypes.c_uint64 * 2)()
         _check(self._lib.stif_kriging_solver_stats(self._h, out), "stif_kriging_solver_stats")
-        return {"cholesky_to_lu": int(out[0]), "cholesky_enabled": bool(out[1])}
+        return {"cholesky_to_lu": int(out[0]), "cholesky_enabled": bool(out[1] & 1),
+                "ldl_enabled": bool(out[1] & 2), "first_pass_to_lu": int(out[0])}
 
     def debug_numpy_row_sum(self, rows):
         """np.sum(rows, axis=1) by the DEVICE summation code of the float32-storage epilogue."""

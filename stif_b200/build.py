@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libstif_b200.so")
 SOURCES = ["context.cu", "variogram.cu", "kriging.cu"]
-HEADERS = ["common.cuh", "krig_chol.cuh", os.path.join("..", "..", "include", "stif_b200.h")]
+HEADERS = ["common.cuh", "krig_chol.cuh", "krig_ldl.cuh", os.path.join("..", "..", "include", "stif_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

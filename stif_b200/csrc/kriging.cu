@@ -1370,6 +1370,7 @@ __global__ void __launch_bounds__(MN_THREADS) solve_minnorm_kernel(SolveParams P
 }
 
 #include "krig_chol.cuh"
+#include "krig_ldl.cuh"
 
 // stats[0] += sum(exam_n), [1] += sum(cand_n), [2] += #(sel_n < 0), [3] += #(rank-deficient),
 // [4] += targets the covariance-form kernel handed to the pivoted LU, [5] += #(non-finite systems)
@@ -1922,7 +1923,16 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         STIF_CUDA(cudaMemcpy(c->k_pairtab.p, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     }
     CX.pairtab = c->k_pairtab.as<unsigned>();
-    c->k_chol_enabled = chol_var >= 0 ? 1 : 0;
+    // symmetric indefinite systems (models that are not valid variograms): Bunch-Kaufman LDL'
+    // (krig_ldl.cuh); STIF_KRIG_TRY_LDL sends every model through it, STIF_KRIG_FORCE_LU none
+    const bool use_ldl = !(flags & STIF_KRIG_FORCE_LU) && (chol_var < 0 || (flags & STIF_KRIG_TRY_LDL));
+    const bool use_chol = chol_var >= 0 && !use_ldl;
+    c->k_chol_enabled = (use_chol ? 1 : 0) | (use_ldl ? 2 : 0);
+    const int ldl_kp = (k + 1) & ~1;
+    int ldl_adbl = (k + 2) * (k + 3) / 2;
+    if (ldl_adbl < 5 * ldl_kp) ldl_adbl = 5 * ldl_kp;      // the epilogue's arrays alias the matrix
+    ldl_adbl = (ldl_adbl + 1) & ~1;
+    const size_t ldl_smem = sizeof(double) * ((size_t)ldl_adbl + 3 * (size_t)ldl_kp);
     const int chol_nt = (k + 2 + 7) / 8, chol_kp = (k + 1) & ~1;
     const size_t chol_smem = sizeof(double) * ((size_t)chol_nt * (chol_nt + 1) / 2 * 64 + 5 * (size_t)chol_kp) +
                              sizeof(unsigned) * (size_t)chol_kp;
@@ -2022,7 +2032,41 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
         QP.sing_list = fail_count + 1;
         QP.sing_count = QP.sing_list + chunk;
         STIF_CUDA(cudaMemsetAsync(QP.sing_count, 0, sizeof(unsigned), st));
-        if (chol_var >= 0) {
+        if (use_ldl) {
+            STIF_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(unsigned), st));
+            CX.fail_list = fail_list;
+            CX.fail_count = fail_count;
+            QP.count = nullptr;
+#define STIF_LDL_V(NG_, LUV_)                                                                      \
+    do {                                                                                           \
+        auto kern = solve_ldl_kernel<NG_, LUV_>;                                                   \
+        STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                       (int)ldl_smem));                                            \
+        int occ = 0;                                                                               \
+        STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, ldl_smem));        \
+        if (occ < 1) occ = 1;                                                                      \
+        int64_t gsz = (int64_t)occ * c->sm_count;                                                  \
+        if (gsz > nc) gsz = nc;                                                                    \
+        kern<<<(unsigned)gsz, 32, ldl_smem, st>>>(QP, CX, ldl_adbl);                               \
+    } while (0)
+#define STIF_LDL(NG_)                                                                              \
+    do {                                                                                           \
+        if (lu_var == LU_PRODUCT_SUM_SPH) STIF_LDL_V(NG_, LU_PRODUCT_SUM_SPH);                     \
+        else if (lu_var == LU_PRODUCT_SPH) STIF_LDL_V(NG_, LU_PRODUCT_SPH);                        \
+        else STIF_LDL_V(NG_, LU_GENERIC);                                                          \
+    } while (0)
+            // lane l owns rows l, l + 32, ... of the k + 2 rows
+            if (k <= 30) STIF_LDL(1);
+            else if (k <= 62) STIF_LDL(2);
+            else if (k <= 94) STIF_LDL(3);
+            else if (k <= 126) STIF_LDL(4);
+            else STIF_LDL(5);
+#undef STIF_LDL
+#undef STIF_LDL_V
+            STIF_CUDA(cudaGetLastError());
+            QP.order = fail_list;
+            QP.count = fail_count;
+        } else if (use_chol) {
             STIF_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(unsigned), st));
             CX.fail_list = fail_list;
             CX.fail_count = fail_count;
@@ -2107,7 +2151,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             STIF_CUDA(cudaGetLastError());
         }
         stats_kernel<<<c->sm_count, 256, 0, st>>>(exam_n, cand_n, sel_n, singular, nc,
-                                                 chol_var >= 0 ? fail_count : nullptr,
+                                                 (use_chol || use_ldl) ? fail_count : nullptr,
                                                  c->k_stats.as<unsigned long long>());
         STIF_CUDA(cudaGetLastError());
     }

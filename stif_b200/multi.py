@@ -190,7 +190,9 @@ class MultiContext:
         ctxs = self._last_kriging or self.contexts[:1]
         stats = [c.kriging_solver_stats() for c in ctxs]
         return {"cholesky_to_lu": sum(s["cholesky_to_lu"] for s in stats),
-                "cholesky_enabled": all(s["cholesky_enabled"] for s in stats)}
+                "cholesky_enabled": all(s["cholesky_enabled"] for s in stats),
+                "ldl_enabled": all(s["ldl_enabled"] for s in stats),
+                "first_pass_to_lu": sum(s["first_pass_to_lu"] for s in stats)}
 
     def last_phase_ms(self):
         ctxs = self._last_kriging or self._last_variogram or self.contexts[:1]

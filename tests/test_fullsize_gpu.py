@@ -280,7 +280,8 @@ def test_c4_translation_invariance(ctx):
 
 def test_c5_indicator_kriging_k100(ctx):
     """2M observations, presence/absence residuals, product_sum, k = 100: the model is not a
-    valid variogram, every system goes through the pivoted LU; sample vs the oracle."""
+    valid variogram, every system goes through the Bunch-Kaufman LDL' kernel; sample vs the oracle,
+    all targets vs the pivoted LU."""
     rng = np.random.default_rng(20261021)
     n_obs = 2_000_000
     x = rng.uniform(0, 1000, n_obs)
@@ -295,8 +296,19 @@ def test_c5_indicator_kriging_k100(ctx):
     ctx.kriging_set_model(*C5_MODEL, C5_PARAMS)
     m, s, w, g, idx, nu = ctx.kriging_predict_host(tx, ty, tt, 1, 100, 30.0, 30.0, flags=0, want_weights=True)
     ss, st = ctx.kriging_solver_stats(), ctx.kriging_stats()
-    assert not ss["cholesky_enabled"]
+    # not a valid variogram: the symmetric indefinite LDL' kernel solves every system itself
+    assert not ss["cholesky_enabled"] and ss["ldl_enabled"] and ss["first_pass_to_lu"] == 0
     assert 420 < st["candidates_in_window"] / n_t < 510               # C-bar ~ 465
+    # the pivoted LU on all 20 000 targets: the same matrix, general elimination
+    m_lu, s_lu, w_lu, _, idx_lu, _ = ctx.kriging_predict_host(tx, ty, tt, 1, 100, 30.0, 30.0,
+                                                              flags=_native.KRIG_FORCE_LU, want_weights=True)
+    assert not ctx.kriging_solver_stats()["ldl_enabled"]
+    assert np.array_equal(idx, idx_lu)
+    wsc = np.abs(w_lu).max(axis=1, keepdims=True)
+    assert np.all(np.abs(w - w_lu) <= 2.0 ** -22 * wsc)
+    msc = np.sum(np.abs(w_lu.astype(np.float64)) * np.abs(z[idx_lu.astype(np.int64)]), axis=1)
+    record_quantiles("c5_f64_ldl_vs_lu", mean_over_scale=np.abs(m - m_lu) / msc)
+    assert np.all(np.abs(m - m_lu) <= 1e-9 * msc)
     assert np.all(nu == 100)
     w64 = w.astype(np.float64)      # float32 outputs; product_sum weights are large and of both signs
     assert np.all(np.abs(w64.sum(axis=1) - 1.0) <= 1e-6 * np.abs(w64).sum(axis=1))

@@ -30,7 +30,8 @@ def synth(n_obs, n_tgt, seed=20261020, extent=300.0):
     return space, t, z, tsp, tt
 
 
-SOLVER_FLAGS = {"auto": 0, "lu": _native.KRIG_FORCE_LU, "chol": _native.KRIG_TRY_CHOL}
+SOLVER_FLAGS = {"auto": 0, "lu": _native.KRIG_FORCE_LU, "chol": _native.KRIG_TRY_CHOL,
+                "ldl": _native.KRIG_TRY_LDL}
 
 
 def gpu_predict(ctx, space, t, z, tsp, tt, models, params, min_pts, k, smax, tmax, leave=None, f32=True,
@@ -79,7 +80,7 @@ def compare(g, o, z, f32):
         assert np.all(dv <= RTOL * vscale[nonsing]), dv.max()
 
 
-@pytest.mark.parametrize("solver", ["auto", "lu", "chol"])
+@pytest.mark.parametrize("solver", ["auto", "lu", "chol", "ldl"])
 @pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("models,params,k", [
     (SUM_METRIC, P_SUM_METRIC, 50),
@@ -97,14 +98,18 @@ def test_models(ctx, models, params, k, f32, solver):
     ss = ctx.kriging_solver_stats()
     valid = models[0] in ("sum", "metric", "sum_metric")
     if solver == "lu":
-        assert not ss["cholesky_enabled"]
+        assert not ss["cholesky_enabled"] and not ss["ldl_enabled"]
+    elif solver == "ldl":
+        # every model through the symmetric indefinite solver; distinct points: nothing handed on
+        assert ss["ldl_enabled"] and not ss["cholesky_enabled"] and ss["first_pass_to_lu"] == 0
     elif solver == "chol" or valid:
-        assert ss["cholesky_enabled"]
+        assert ss["cholesky_enabled"] and not ss["ldl_enabled"]
         if models[0] in ("metric", "sum_metric"):
             # valid variogram, distinct points: positive definite, nothing handed to the LU
             assert ss["cholesky_to_lu"] == 0
     else:
-        assert not ss["cholesky_enabled"]       # product / product_sum: pivoted LU only
+        # product / product_sum: not a valid variogram -> Bunch-Kaufman LDL' of the bordered system
+        assert ss["ldl_enabled"] and not ss["cholesky_enabled"] and ss["first_pass_to_lu"] == 0
 
 
 def test_cholesky_hands_indefinite_systems_to_lu(ctx):
@@ -161,9 +166,55 @@ def test_cholesky_variants(ctx, models, params, k, radii):
 def test_lu_variants(ctx, models, params, k, radii):
     space, t, z, tsp, tt = synth(30000, 200, seed=33, extent=200.0)
     g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32=False)
-    assert not ctx.kriging_solver_stats()["cholesky_enabled"]
+    ss = ctx.kriging_solver_stats()
+    assert not ss["cholesky_enabled"] and ss["ldl_enabled"] and ss["first_pass_to_lu"] == 0
     o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32_storage=False)
     compare(g, o, z, False)
+    # and the same through the pivoted LU (same assembly expressions, general elimination)
+    g2 = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, radii[0], radii[1], f32=False, solver="lu")
+    assert not ctx.kriging_solver_stats()["ldl_enabled"]
+    compare(g2, o, z, False)
+    # the two solvers factor the same matrix: weights agree far below the float32 storage step
+    wscale = np.abs(g2["w"]).max(axis=1, keepdims=True) + 1e-30
+    assert np.all(np.abs(g["w"] - g2["w"]) <= 2.0 ** -22 * wscale)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 30, 31, 62, 63, 94, 95, 100, 126, 127, 128])
+def test_ldl_row_group_boundaries(ctx, k):
+    """The LDL' kernel is instantiated per number of 32-row groups of the k + 2 rows: both sides of
+    every boundary, for the indefinite model that takes it by default and for a valid one."""
+    space, t, z, tsp, tt = synth(40000, 96, seed=40 + k, extent=300.0)
+    for models, params in ((PRODUCT_SUM, P_PRODUCT_SUM), (SUM_METRIC, P_SUM_METRIC)):
+        g = gpu_predict(ctx, space, t, z, tsp, tt, models, params, 1, k, 45.0, 45.0, f32=False, solver="ldl")
+        ss = ctx.kriging_solver_stats()
+        assert ss["ldl_enabled"] and ss["first_pass_to_lu"] == 0
+        o = ok.predict(space, t, z, tsp, tt, models, params, 1, k, 45.0, 45.0, f32_storage=False)
+        if k >= 100:
+            assert (o["n_used"] == k).mean() > 0.5
+        compare(g, o, z, False)
+
+
+def test_ldl_hands_duplicates_to_lu_and_minnorm(ctx):
+    """Duplicate observations make the bordered system exactly singular: the LDL' kernel must see the
+    vanishing pivot, hand the target to the LU, which flags it for the minimum-norm kernel; the
+    results equal those of the LU-only path bit for bit (same second and third pass)."""
+    space, t, z, tsp, tt = synth(6000, 150, seed=77, extent=120.0)
+    space = np.concatenate([space, space[:3000]])
+    t = np.concatenate([t, t[:3000]])
+    z = np.concatenate([z, z[:3000]])
+    a = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 30.0, 30.0, f32=False)
+    ss, st = ctx.kriging_solver_stats(), ctx.kriging_stats()
+    assert ss["ldl_enabled"] and ss["first_pass_to_lu"] > 0 and st["targets_singular"] > 0
+    assert ss["first_pass_to_lu"] >= st["targets_singular"]
+    b = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, 24, 30.0, 30.0, f32=False,
+                    solver="lu")
+    st2 = ctx.kriging_stats()
+    assert st2["targets_singular"] == st["targets_singular"]
+    # targets the LDL' kernel kept: same matrix, another elimination order
+    wscale = np.abs(b["w"]).max(axis=1, keepdims=True) + 1e-30
+    assert np.all(np.abs(a["w"] - b["w"]) <= 2.0 ** -20 * wscale)
+    assert np.array_equal(a["idx"], b["idx"])
+    assert np.allclose(a["mean"], b["mean"], rtol=0, atol=1e-6 * np.abs(z).max())
 
 
 def test_k100_many_candidates(ctx):

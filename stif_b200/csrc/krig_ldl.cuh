@@ -1,5 +1,6 @@
-// krig_ldl.cuh -- symmetric indefinite kriging solve: Bunch-Kaufman LDL' of the reference's own
-// bordered system, one warp per target.  Included by kriging.cu (namespace stif::krig).
+// krig_ldl.cuh -- symmetric indefinite kriging solve: blocked Bunch-Kaufman LDL' of the reference's
+// own bordered system, one warp per target, trailing updates on the FP64 tensor cores.
+// Included by kriging.cu (namespace stif::krig).
 //
 // Replaces calc_kriging_weights (stif/predictor.py:566-593) for models that are NOT valid
 // variograms: product / product_sum (stif/variogram_models.py:126-127, :155-157) give an
@@ -15,11 +16,17 @@
 // Storage: rows 0..N-1 (N = m + 1: the m neighbours and the Lagrange row) and the right-hand
 // side as row N of the SAME packed lower triangle, row i at i (i + 1) / 2.  The elimination of a
 // pivot updates every row below it, so row N leaves the factorisation as z = D^-1 L^-1 P b and
-// only the back substitution  L' x' = z  remains.  Lane l owns rows l, l + 32, ...: the column
-// scans (pivot search), the multipliers and the rank-1 / rank-2 updates read and write a lane's
-// own rows (consecutive rows of the packed triangle fall into distinct banks: the triangular
-// numbers are a complete residue system modulo 16), the multipliers of the OTHER factor come
-// from the stored column by broadcast loads.
+// only the back substitution  L' x' = z  remains.  Lane l owns rows l, l + 32, ... (consecutive
+// rows of the packed triangle fall into distinct banks: the triangular numbers are a complete
+// residue system modulo 16).
+//
+// Blocking (the structure of LAPACK's dsytrf / dlasyf, without its workspace): inside a panel of
+// up to eight columns the matrix is touched by the symmetric interchanges only.  The column under
+// examination -- and row r of the Bunch-Kaufman test -- is brought up to date on the fly,
+//      a(i, j) - sum_q L(i, q) W(j, q),     W = L D  recomputed from D (registers),
+// with the lane's own rows' panel multipliers in registers; the multipliers L(:, j) are stored in
+// place.  After the panel the whole trailing matrix receives  - L W'  in 8x8 tiles of two
+// mma.sync.m8n8k4.f64 (DMMA) each, masked at the edges of the triangle.
 //
 // Any pivot below 1e-10 max|K| and any non-finite entry or solution sends the target to the
 // pivoted LU (fail list, exactly like the Cholesky kernel), which owns the rank decision.
@@ -83,59 +90,68 @@ __device__ __forceinline__ void ldl_assemble(double *A, const double2 *pxy, cons
     }
 }
 
-// Trailing update after the pivot block at columns j0 .. j0 + RANK - 1:
-//      a(i, c) -= w1_i l1_c (+ w2_i l2_c),   j0 + RANK <= c <= i < n,
-// w = the lane's own (unscaled) entries of the pivot columns, l = the stored multipliers of row c
-// (broadcast loads).  CU columns per iteration: all loads, then all FMAs, then all stores.
-template <int NG, int RANK, int CU>
-__device__ __forceinline__ void ldl_update(double *A, const int (&rb)[NG], const double (&w1)[NG],
-                                           const double (&w2)[NG], int j0, int n, int lane)
+// Trailing update after a panel at columns j0 .. j0 + pw - 1 (pw <= 8; j1 = j0 + pw):
+//      a(i, c) -= sum_q L(i, j0 + q) W(c, q),    j1 <= c <= i < n,    W = L D,
+// in 8x8 tiles of the absolute 8-grid: two DMMA per tile (A fragment = multipliers of the tile's
+// rows, B fragment = -W of the tile's columns, built from the multipliers and this lane's entries of
+// D), C fragment loaded / stored under the mask of the triangle and of the finished columns.  Rows
+// and columns outside the mask only pollute their own (masked) outputs.  Two tiles per iteration.
+__device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int j0, int pw, int j1, int n,
+                                             bool has22, int lane)
 {
-    int c = j0 + RANK;
-    int tcj = ldl_tri(c) + j0;                       // &l1 of row c
+    const int g = lane >> 2, t = lane & 3;
+    // this lane's entries of D for the panel columns t and 4 + t: diagonal, coupling with the next
+    // and with the previous column (a block never starts at the panel's last column)
+    const double d0 = dpan[t], d1 = dpan[4 + t];
+    const double u0 = dpan[8 + t], u1 = (t < 3) ? dpan[12 + t] : 0.0;
+    const double l0 = (t > 0) ? dpan[8 + t - 1] : 0.0, l1 = dpan[11 + t];
+    const bool k0 = t < pw, k1 = 4 + t < pw;
+    const int nT = (n + 7) >> 3;
+    const int cj = j0 + t;
 #pragma unroll 1
-    for (; c < n; c += CU) {
-        double l1[CU], l2[CU];
+    for (int J = j1 >> 3; J < nT; ++J) {
+        double b0 = 0.0, b1 = 0.0;
         {
-            int t = tcj;
-            const int t0 = tcj;
-#pragma unroll
-            for (int u = 0; u < CU; ++u) {
-                const int cc = c + u;
-                const int tt = cc < n ? t : t0;      // rows past the matrix are never used
-                l1[u] = A[tt];
-                if (RANK == 2) l2[u] = A[tt + 1];
-                t += cc + 1;                         // tri(cc + 1) = tri(cc) + cc + 1
+            const int c = min(8 * J + g, n - 1);
+            const int tc = ldl_tri(c) + cj;
+            if (k0) {
+                b0 = d0 * A[tc];
+                if (has22) {
+                    if (u0 != 0.0) b0 = __fma_rn(u0, A[tc + 1], b0);
+                    if (l0 != 0.0) b0 = __fma_rn(l0, A[tc - 1], b0);
+                }
             }
-            tcj = t;
+            if (k1) {
+                b1 = d1 * A[tc + 4];
+                if (has22) {
+                    if (u1 != 0.0) b1 = __fma_rn(u1, A[tc + 5], b1);
+                    if (l1 != 0.0) b1 = __fma_rn(l1, A[tc + 3], b1);
+                }
+            }
+            b0 = -b0;
+            b1 = -b1;
         }
-        const int gfirst = c >> 5;                   // groups above hold no row >= c
-        double a[NG][CU];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int i = lane + 32 * g;
-            if (g >= gfirst && i < n) {
-#pragma unroll
-                for (int u = 0; u < CU; ++u)
-                    if (i >= c + u) a[g][u] = A[rb[g] + c + u];
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-#pragma unroll
-            for (int u = 0; u < CU; ++u) {
-                a[g][u] = __fma_rn(-w1[g], l1[u], a[g][u]);
-                if (RANK == 2) a[g][u] = __fma_rn(-w2[g], l2[u], a[g][u]);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int i = lane + 32 * g;
-            if (g >= gfirst && i < n) {
-#pragma unroll
-                for (int u = 0; u < CU; ++u)
-                    if (i >= c + u) A[rb[g] + c + u] = a[g][u];
-            }
+        const int colA = 8 * J + 2 * t;
+        const bool cokA = colA >= j1, cokB = colA + 1 >= j1;
+#pragma unroll 1
+        for (int I = J; I < nT; I += 2) {
+            const int rowx = 8 * I + g, rowy = rowx + 8;
+            const int tx = ldl_tri(min(rowx, n - 1)), ty = ldl_tri(min(rowy, n - 1));
+            const bool rokx = rowx < n && rowx >= j1, roky = rowy < n && rowy >= j1 && I + 1 < nT;
+            const bool xA = rokx && cokA && colA <= rowx, xB = rokx && cokB && colA + 1 <= rowx;
+            const bool yA = roky && cokA && colA <= rowy, yB = roky && cokB && colA + 1 <= rowy;
+            const double ax0 = k0 ? A[tx + cj] : 0.0, ax1 = k1 ? A[tx + cj + 4] : 0.0;
+            const double ay0 = k0 ? A[ty + cj] : 0.0, ay1 = k1 ? A[ty + cj + 4] : 0.0;
+            double cx0 = xA ? A[tx + colA] : 0.0, cx1 = xB ? A[tx + colA + 1] : 0.0;
+            double cy0 = yA ? A[ty + colA] : 0.0, cy1 = yB ? A[ty + colA + 1] : 0.0;
+            dmma884(cx0, cx1, ax0, b0);
+            dmma884(cy0, cy1, ay0, b0);
+            dmma884(cx0, cx1, ax1, b1);
+            dmma884(cy0, cy1, ay1, b1);
+            if (xA) A[tx + colA] = cx0;
+            if (xB) A[tx + colA + 1] = cx1;
+            if (yA) A[ty + colA] = cy0;
+            if (yB) A[ty + colA + 1] = cy1;
         }
     }
 }
@@ -169,11 +185,49 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[NG], unsigne
     __syncwarp();
 }
 
+// D of the current panel lives in shared memory: dpan[0..7] = the diagonal, dpan[8..15]: dpan[8 + q] =
+// the coupling of a 2x2 block that starts at panel column q.
+// W(x, qq) = (L D)(x, qq) for one finished panel column qq < q (broadcast loads, same value in every lane).
+__device__ __forceinline__ double ldl_w1(const double *A, const double *dpan, int txj0, int qq, int q, bool has22)
+{
+    double w = dpan[qq] * A[txj0 + qq];
+    if (has22) {
+        if (qq + 1 < q) w = __fma_rn(dpan[8 + qq], A[txj0 + qq + 1], w);
+        if (qq > 0) w = __fma_rn(dpan[8 + qq - 1], A[txj0 + qq - 1], w);
+    }
+    return w;
+}
+
+// Column x >= j (the column under examination, row r of the Bunch-Kaufman test by symmetry, or the
+// second column of a 2x2 block) brought up to date over the q finished panel columns,
+//      a(c, x) - sum_qq L(c, qq) W(x, qq),
+// for the lane's rows `on` and for the diagonal entry.
+template <int NG>
+__device__ __forceinline__ void ldl_col_generic(const double *A, const double *dpan, const int (&rb)[NG], int j0,
+                                                int q, int x, bool has22, const bool (&on)[NG], int lane,
+                                                double (&val)[NG], double &diag)
+{
+    const int tx = ldl_tri(x);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const int c = lane + 32 * g;
+        val[g] = on[g] ? ((c < x) ? A[tx + c] : A[rb[g] + x]) : 0.0;
+    }
+    diag = A[tx + x];
+#pragma unroll 1
+    for (int qq = 0; qq < q; ++qq) {
+        const double w = ldl_w1(A, dpan, tx + j0, qq, q, has22);
+        diag = __fma_rn(-A[tx + j0 + qq], w, diag);
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+            if (on[g]) val[g] = __fma_rn(-A[rb[g] + j0 + qq], w, val[g]);
+    }
+}
+
 template <int NG, int LUV>
 __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams X, int adbl)
 {
     extern __shared__ __align__(16) double smem_d[];
-    constexpr int CU = 4;
     const int lane = threadIdx.x;
     const int k = P.k;
     const int kp = (k + 1) & ~1;
@@ -182,6 +236,7 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
     double *pt = reinterpret_cast<double *>(pxy + kp);
     unsigned char *perm = reinterpret_cast<unsigned char *>(pxy);     // pxy is dead after the assembly
     double *sol = pt;                                                 // and so is pt
+    double *dpan = pt + kp;                                           // D of the current panel: dd[8], off[8]
     // the epilogue's arrays alias the matrix, which is dead after the back substitution
     double *g0 = A, *rs = A + kp, *sc64 = A + 2 * kp;
     float *sc32a = reinterpret_cast<float *>(A + 3 * kp), *sc32b = sc32a + kp;
@@ -290,96 +345,109 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
         __syncwarp();
         fetch_ids();
 
-        // ---- Bunch-Kaufman: pivots among rows / columns 0 .. N-1 ----
-        int j = 0;
-        while (j < N && !fail) {
-            const int tj = ldl_tri(j);
-            double v[NG];
-            unsigned key = 0u;
+        // ---- blocked Bunch-Kaufman: pivots among rows / columns 0 .. N-1 ----
+        int j0 = 0;
+        while (j0 < N && !fail) {
+            if (lane < 16) dpan[lane] = 0.0;
+            __syncwarp();
+            bool has22 = false;
+            int q = 0, forced = 0, r = 0;       // q: finished columns of this panel
+            double lam = 0.0;
+            while (q < 8 && j0 + q < N) {
+                const int j = j0 + q, tj = ldl_tri(j);
+                bool act[NG];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int i = lane + 32 * g;
-                v[g] = 0.0;
-                if (i > j && i < n) {
-                    v[g] = A[rb[g] + j];
-                    if (i < N) key = max(key, (ldl_hi_abs(v[g]) & ~0xffu) | (unsigned)i);
-                }
-            }
-            double d = A[tj + j];
-            key = __reduce_max_sync(FULL, key);
-            const int r = (int)(key & 0xffu);
-            const double lam = ldl_from_hi(key & ~0xffu);      // max |a(i, j)|, i > j (truncated to 12 bits)
-            const double aj = fabs(d);
-            int kind = 0;                                      // 0: 1x1; 1: 1x1 after j <-> r; 2: 2x2 with r
-            if (!(aj >= LDL_ALPHA * lam)) {
-                if (r <= j) { fail = true; break; }            // NaN pivot
-                const int tr = ldl_tri(r);
-                unsigned sk = 0u;
+                for (int g = 0; g < NG; ++g) act[g] = lane + 32 * g > j && lane + 32 * g < n;
+                double v[NG], d;
+                ldl_col_generic<NG>(A, dpan, rb, j0, q, j, has22, act, lane, v, d);
+                int kind;                       // 0 / 1: 1x1 pivot; 2: 2x2 pivot with column j + 1
+                if (forced == 0) {
+                    unsigned key = 0u;
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const int c = lane + 32 * g;
-                    if (c >= j && c < N && c != r) {
-                        const double val = (c < r) ? A[tr + c] : A[rb[g] + r];
-                        sk = max(sk, ldl_hi_abs(val));
+                    for (int g = 0; g < NG; ++g) {
+                        const int i = lane + 32 * g;
+                        if (act[g] && i < N) key = max(key, (ldl_hi_abs(v[g]) & ~0xffu) | (unsigned)i);
                     }
-                }
-                const double arr = fabs(A[tr + r]);
-                sk = __reduce_max_sync(FULL, sk);
-                const double sig = ldl_from_hi(sk);            // max |a(r, c)|, c != r
-                if (aj * sig >= LDL_ALPHA * lam * lam) kind = 0;
-                else if (arr >= LDL_ALPHA * sig) kind = 1;
-                else kind = 2;
-            }
-            if (kind == 1) {
-                ldl_swap<NG>(A, rb, perm, j, r, n, lane);
-                d = A[tj + j];
+                    key = __reduce_max_sync(FULL, key);
+                    r = (int)(key & 0xffu);
+                    lam = ldl_from_hi(key & ~0xffu);       // max |a(i, j)|, i > j (truncated to 12 bits)
+                    const double aj = fabs(d);
+                    kind = 0;
+                    if (!(aj >= LDL_ALPHA * lam)) {
+                        if (r <= j) { fail = true; break; }            // NaN pivot
+                        // row r up to date; sigma = max |a(r, c)| over c != r (c = j: lam)
+                        bool on[NG];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const int i = lane + 32 * g;
-                    v[g] = (i > j && i < n) ? A[rb[g] + j] : 0.0;
-                }
-            } else if (kind == 2 && r != j + 1) {
-                ldl_swap<NG>(A, rb, perm, j + 1, r, n, lane);
-            }
-            if (kind < 2) {
-                if (!(fabs(d) > tol)) { fail = true; break; }
-                const double dinv = ldl_rcp(d);
+                        for (int g = 0; g < NG; ++g) on[g] = act[g] && lane + 32 * g < N && lane + 32 * g != r;
+                        double val[NG], arr;
+                        ldl_col_generic<NG>(A, dpan, rb, j0, q, r, has22, on, lane, val, arr);
+                        unsigned sk = key & ~0xffu;
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const int i = lane + 32 * g;
-                    if (i > j && i < n) A[rb[g] + j] = v[g] * dinv;
-                }
-                __syncwarp();
-                ldl_update<NG, 1, CU>(A, rb, v, v, j, n, lane);
-                __syncwarp();
-                j += 1;
-            } else {
-                if (!(lam > tol)) { fail = true; break; }
-                const int tj1 = tj + j + 1;
-                const double d11 = A[tj + j], d21 = A[tj1 + j], d22 = A[tj1 + j + 1];
-                // [l1 l2] = [w1 w2] D^-1, scaled by the off-diagonal like LAPACK's dsytf2
-                const double t = ldl_rcp(d21);
-                const double ak = d11 * t, akp1 = d22 * t;
-                const double den = t * ldl_rcp(__fma_rn(ak, akp1, -1.0));
-                double w1[NG], w2[NG];
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const int i = lane + 32 * g;
-                    w1[g] = 0.0;
-                    w2[g] = 0.0;
-                    if (i > j + 1 && i < n) {
-                        w1[g] = A[rb[g] + j];
-                        w2[g] = A[rb[g] + j + 1];
-                        A[rb[g] + j] = den * __fma_rn(akp1, w1[g], -w2[g]);
-                        A[rb[g] + j + 1] = den * __fma_rn(ak, w2[g], -w1[g]);
+                        for (int g = 0; g < NG; ++g)
+                            if (on[g]) sk = max(sk, ldl_hi_abs(val[g]));
+                        sk = __reduce_max_sync(FULL, sk);
+                        const double sig = ldl_from_hi(sk);
+                        if (aj * sig >= LDL_ALPHA * lam * lam) kind = 0;
+                        else if (fabs(arr) >= LDL_ALPHA * sig) kind = 1;
+                        else kind = 2;
                     }
+                    if (kind == 2 && q == 7) break;        // the 2x2 block would leave the panel: close it
+                    const int p = (kind == 1) ? j : j + 1;
+                    if (kind == 1 || (kind == 2 && r != p)) {
+                        ldl_swap<NG>(A, rb, perm, p, r, n, lane);
+                        forced = kind;
+                        continue;
+                    }
+                } else {
+                    kind = forced;
+                    forced = 0;
+                }
+                if (kind < 2) {
+                    if (!(fabs(d) > tol)) { fail = true; break; }
+                    const double dinv = ldl_rcp(d);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+                        if (act[g]) A[rb[g] + j] = v[g] * dinv;
+                    if (lane == 0) dpan[q] = d;
+                    q += 1;
+                } else {
+                    if (!(lam > tol)) { fail = true; break; }
+                    // column j + 1 up to date (over the same q finished columns)
+                    const int tj1 = tj + j + 1;
+                    bool on[NG];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) on[g] = act[g] && lane + 32 * g > j + 1;
+                    double v2[NG], d22, d21 = 0.0;
+                    ldl_col_generic<NG>(A, dpan, rb, j0, q, j + 1, has22, on, lane, v2, d22);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+                        if (((j + 1) >> 5) == g) d21 = __shfl_sync(FULL, v[g], (j + 1) & 31);
+                    // [l1 l2] = [w1 w2] D^-1, scaled by the off-diagonal like LAPACK's dsytf2
+                    const double t = ldl_rcp(d21);
+                    const double ak = d * t, akp1 = d22 * t;
+                    const double den = t * ldl_rcp(__fma_rn(ak, akp1, -1.0));
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        if (on[g]) {
+                            A[rb[g] + j] = den * __fma_rn(akp1, v[g], -v2[g]);
+                            A[rb[g] + j + 1] = den * __fma_rn(ak, v2[g], -v[g]);
+                        }
+                    }
+                    if (lane == 0) {
+                        A[tj1 + j] = 0.0;                  // L(j+1, j) = 0
+                        dpan[q] = d;
+                        dpan[8 + q] = d21;
+                        dpan[q + 1] = d22;
+                    }
+                    has22 = true;
+                    q += 2;
                 }
                 __syncwarp();
-                if (lane == 0) A[tj1 + j] = 0.0;               // L(j+1, j) = 0: D is not needed again
-                ldl_update<NG, 2, CU>(A, rb, w1, w2, j, n, lane);
-                __syncwarp();
-                j += 2;
             }
+            if (fail) break;
+            if (j0 + q < N) ldl_trailing(A, dpan, j0, q, j0 + q, n, has22, lane);
+            __syncwarp();
+            j0 += q;
         }
         fetch_obs();
 

@@ -1932,7 +1932,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     int ldl_adbl = (k + 2) * (k + 3) / 2;
     if (ldl_adbl < 5 * ldl_kp) ldl_adbl = 5 * ldl_kp;      // the epilogue's arrays alias the matrix
     ldl_adbl = (ldl_adbl + 1) & ~1;
-    const size_t ldl_smem = sizeof(double) * ((size_t)ldl_adbl + 3 * (size_t)ldl_kp);
+    const size_t ldl_smem = sizeof(double) * ((size_t)ldl_adbl + 3 * (size_t)ldl_kp + 16);
     const int chol_nt = (k + 2 + 7) / 8, chol_kp = (k + 1) & ~1;
     const size_t chol_smem = sizeof(double) * ((size_t)chol_nt * (chol_nt + 1) / 2 * 64 + 5 * (size_t)chol_kp) +
                              sizeof(unsigned) * (size_t)chol_kp;

@@ -187,40 +187,66 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[NG], unsigne
 
 // D of the current panel lives in shared memory: dpan[0..7] = the diagonal, dpan[8..15]: dpan[8 + q] =
 // the coupling of a 2x2 block that starts at panel column q.
-// W(x, qq) = (L D)(x, qq) for one finished panel column qq < q (broadcast loads, same value in every lane).
-__device__ __forceinline__ double ldl_w1(const double *A, const double *dpan, int txj0, int qq, int q, bool has22)
-{
-    double w = dpan[qq] * A[txj0 + qq];
-    if (has22) {
-        if (qq + 1 < q) w = __fma_rn(dpan[8 + qq], A[txj0 + qq + 1], w);
-        if (qq > 0) w = __fma_rn(dpan[8 + qq - 1], A[txj0 + qq - 1], w);
-    }
-    return w;
-}
-
+//
 // Column x >= j (the column under examination, row r of the Bunch-Kaufman test by symmetry, or the
 // second column of a 2x2 block) brought up to date over the q finished panel columns,
-//      a(c, x) - sum_qq L(c, qq) W(x, qq),
-// for the lane's rows `on` and for the diagonal entry.
+//      a(c, x) - sum_qq L(c, qq) W(x, qq),     W(x, qq) = (L D)(x, qq)  (broadcast loads),
+// for the lane's rows `on` and for the diagonal entry.  The loop over the (at most eight) finished
+// columns is unrolled with a uniform early exit, so every address is base + constant.
 template <int NG>
 __device__ __forceinline__ void ldl_col_generic(const double *A, const double *dpan, const int (&rb)[NG], int j0,
                                                 int q, int x, bool has22, const bool (&on)[NG], int lane,
                                                 double (&val)[NG], double &diag)
 {
     const int tx = ldl_tri(x);
+    const double *lx = A + tx + j0;          // row x's multipliers
+    const double *lp[NG];                    // the lane's own rows' multipliers
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         const int c = lane + 32 * g;
+        lp[g] = A + rb[g] + j0;
         val[g] = on[g] ? ((c < x) ? A[tx + c] : A[rb[g] + x]) : 0.0;
     }
-    diag = A[tx + x];
-#pragma unroll 1
-    for (int qq = 0; qq < q; ++qq) {
-        const double w = ldl_w1(A, dpan, tx + j0, qq, q, has22);
-        diag = __fma_rn(-A[tx + j0 + qq], w, diag);
+    double dg = A[tx + x];
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+        if (qq >= q) break;
+        const double lxq = lx[qq];
+        double w = dpan[qq] * lxq;
+        if (has22) {
+            if (qq + 1 < q) w = __fma_rn(dpan[8 + qq], lx[qq + 1], w);
+            if (qq > 0) w = __fma_rn(dpan[8 + qq - 1], lx[qq - 1], w);
+        }
+        dg = __fma_rn(-lxq, w, dg);
 #pragma unroll
         for (int g = 0; g < NG; ++g)
-            if (on[g]) val[g] = __fma_rn(-A[rb[g] + j0 + qq], w, val[g]);
+            if (on[g]) val[g] = __fma_rn(-lp[g][qq], w, val[g]);
+    }
+    diag = dg;
+}
+
+// Back substitution, rows of group GI (rows 32 GI .. 32 GI + 31) from the bottom up: x'_i is final once
+// the rows below it are done; lane l keeps z of columns l, l + 32, ...  Template recursion keeps every
+// register index a compile-time constant.
+template <int NG, int GI>
+__device__ __forceinline__ void ldl_backsub(const double *A, double (&zr)[NG], int N, int lane)
+{
+    if constexpr (GI >= 0) {
+        if (32 * GI < N) {
+            int i = min(32 * GI + 31, N - 1);
+            int ti = ldl_tri(i);
+#pragma unroll 1
+            for (; i >= 32 * GI && i >= 1; --i) {
+                const double xi = __shfl_sync(FULL, zr[GI], i & 31);
+#pragma unroll
+                for (int g = 0; g <= GI; ++g) {
+                    const int c = lane + 32 * g;
+                    if (c < i) zr[g] = __fma_rn(-A[ti + c], xi, zr[g]);
+                }
+                ti -= i;                                   // tri(i - 1) = tri(i) - i
+            }
+        }
+        ldl_backsub<NG, GI - 1>(A, zr, N, lane);
     }
 }
 
@@ -420,8 +446,10 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     double v2[NG], d22, d21 = 0.0;
                     ldl_col_generic<NG>(A, dpan, rb, j0, q, j + 1, has22, on, lane, v2, d22);
 #pragma unroll
-                    for (int g = 0; g < NG; ++g)
-                        if (((j + 1) >> 5) == g) d21 = __shfl_sync(FULL, v[g], (j + 1) & 31);
+                    for (int g = 0; g < NG; ++g) {         // every group shuffles: no run-time register index
+                        const double cand = __shfl_sync(FULL, v[g], (j + 1) & 31);
+                        if (((j + 1) >> 5) == g) d21 = cand;
+                    }
                     // [l1 l2] = [w1 w2] D^-1, scaled by the off-diagonal like LAPACK's dsytf2
                     const double t = ldl_rcp(d21);
                     const double ak = d * t, akp1 = d22 * t;
@@ -461,22 +489,7 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                 const int c = lane + 32 * g;
                 zr[g] = (c < N) ? A[tN + c] : 0.0;
             }
-#pragma unroll
-            for (int gi = NG - 1; gi >= 0; --gi) {
-                if (32 * gi >= N) continue;
-                int i = min(32 * gi + 31, N - 1);
-                int ti = ldl_tri(i);
-#pragma unroll 1
-                for (; i >= 32 * gi && i >= 1; --i) {
-                    const double xi = __shfl_sync(FULL, zr[gi], i & 31);
-#pragma unroll
-                    for (int g = 0; g <= gi; ++g) {
-                        const int c = lane + 32 * g;
-                        if (c < i) zr[g] = __fma_rn(-A[ti + c], xi, zr[g]);
-                    }
-                    ti -= i;                                   // tri(i - 1) = tri(i) - i
-                }
-            }
+            ldl_backsub<NG, NG - 1>(A, zr, N, lane);
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const int c = lane + 32 * g;

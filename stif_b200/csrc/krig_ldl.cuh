@@ -50,7 +50,7 @@ __device__ __forceinline__ double ldl_rcp(double x)
 // same expressions as the LU's assembly, so both solvers factor the same matrix.
 template <int LUV>
 __device__ __forceinline__ void ldl_assemble(double *A, const double2 *pxy, const double *pt, int m,
-                                             const SolveParams &P, int lane, double &amax, bool &bad)
+                                             const SolveParams &P, int lane, unsigned &amax_hi)
 {
     constexpr int U = 4;
     const int npairs = (m * (m - 1)) >> 1;
@@ -83,8 +83,7 @@ __device__ __forceinline__ void ldl_assemble(double *A, const double2 *pxy, cons
             if (e0 + 32 * u < npairs) {
                 const int a = w[u] & 0xff, b = (w[u] >> 8) & 0xff;
                 A[ldl_tri(a) + b] = g[u];
-                amax = fmax(amax, fabs(g[u]));                       // fmax ignores NaN
-                bad = bad || !(fabs(g[u]) < INFINITY);
+                amax_hi = max(amax_hi, ldl_hi_abs(g[u]));            // Inf / NaN: >= 0x7ff00000
             }
         }
     }
@@ -96,6 +95,48 @@ __device__ __forceinline__ void ldl_assemble(double *A, const double2 *pxy, cons
 // rows, B fragment = -W of the tile's columns, built from the multipliers and this lane's entries of
 // D), C fragment loaded / stored under the mask of the triangle and of the finished columns.  Rows
 // and columns outside the mask only pollute their own (masked) outputs.  Two tiles per iteration.
+// Two tiles (rows 8 I + g and 8 I + 8 + g, tile column J).  EDGE: the mask of the triangle, of the
+// finished columns and of the matrix end is applied; interior tile pairs need none of it.
+template <bool EDGE>
+__device__ __forceinline__ void ldl_tile_pair(double *A, int rowx, int tx, int cj, int colA, int j1, int n,
+                                              bool secondrow, bool k0, bool k1, double b0, double b1)
+{
+    const int rowy = rowx + 8;
+    const int ty = tx + 8 * rowx + 36;                   // tri(r + 8) = tri(r) + 8 r + 36
+    if (EDGE) {
+        const bool inx = rowx < n, iny = rowy < n && secondrow;
+        const bool rokx = inx && rowx >= j1, roky = iny && rowy >= j1;
+        const bool cokA = colA >= j1, cokB = colA + 1 >= j1;
+        const bool xA = rokx && cokA && colA <= rowx, xB = rokx && cokB && colA + 1 <= rowx;
+        const bool yA = roky && cokA && colA <= rowy, yB = roky && cokB && colA + 1 <= rowy;
+        const double ax0 = (k0 && inx) ? A[tx + cj] : 0.0, ax1 = (k1 && inx) ? A[tx + cj + 4] : 0.0;
+        const double ay0 = (k0 && iny) ? A[ty + cj] : 0.0, ay1 = (k1 && iny) ? A[ty + cj + 4] : 0.0;
+        double cx0 = xA ? A[tx + colA] : 0.0, cx1 = xB ? A[tx + colA + 1] : 0.0;
+        double cy0 = yA ? A[ty + colA] : 0.0, cy1 = yB ? A[ty + colA + 1] : 0.0;
+        dmma884(cx0, cx1, ax0, b0);
+        dmma884(cy0, cy1, ay0, b0);
+        dmma884(cx0, cx1, ax1, b1);
+        dmma884(cy0, cy1, ay1, b1);
+        if (xA) A[tx + colA] = cx0;
+        if (xB) A[tx + colA + 1] = cx1;
+        if (yA) A[ty + colA] = cy0;
+        if (yB) A[ty + colA + 1] = cy1;
+    } else {
+        const double ax0 = A[tx + cj], ax1 = k1 ? A[tx + cj + 4] : 0.0;
+        const double ay0 = A[ty + cj], ay1 = k1 ? A[ty + cj + 4] : 0.0;
+        double cx0 = A[tx + colA], cx1 = A[tx + colA + 1];
+        double cy0 = A[ty + colA], cy1 = A[ty + colA + 1];
+        dmma884(cx0, cx1, ax0, b0);
+        dmma884(cy0, cy1, ay0, b0);
+        dmma884(cx0, cx1, ax1, b1);
+        dmma884(cy0, cy1, ay1, b1);
+        A[tx + colA] = cx0;
+        A[tx + colA + 1] = cx1;
+        A[ty + colA] = cy0;
+        A[ty + colA + 1] = cy1;
+    }
+}
+
 __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int j0, int pw, int j1, int n,
                                              bool has22, int lane)
 {
@@ -108,8 +149,10 @@ __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int 
     const bool k0 = t < pw, k1 = 4 + t < pw;
     const int nT = (n + 7) >> 3;
     const int cj = j0 + t;
+    const int Jf = j1 >> 3;
+    const bool k0all = pw >= 4;                          // every lane's first k-column is a finished one
 #pragma unroll 1
-    for (int J = j1 >> 3; J < nT; ++J) {
+    for (int J = Jf; J < nT; ++J) {
         double b0 = 0.0, b1 = 0.0;
         {
             const int c = min(8 * J + g, n - 1);
@@ -132,26 +175,25 @@ __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int 
             b1 = -b1;
         }
         const int colA = 8 * J + 2 * t;
-        const bool cokA = colA >= j1, cokB = colA + 1 >= j1;
+        int rowx = 8 * J + g;
+        int tx = ldl_tri(rowx);
+        // the diagonal tile (and its lower neighbour) under the mask
+        ldl_tile_pair<true>(A, rowx, tx, cj, colA, j1, n, J + 1 < nT, k0, k1, b0, b1);
+        tx += 16 * rowx + 136;                           // tri(r + 16) = tri(r) + 16 r + 136
+        rowx += 16;
+        int I = J + 2;
+        if (J > Jf && k0all) {                           // interior: all columns >= j1, all rows below the diagonal
+            for (; 8 * I + 15 < n; I += 2) {
+                ldl_tile_pair<false>(A, rowx, tx, cj, colA, j1, n, true, true, k1, b0, b1);
+                tx += 16 * rowx + 136;
+                rowx += 16;
+            }
+        }
 #pragma unroll 1
-        for (int I = J; I < nT; I += 2) {
-            const int rowx = 8 * I + g, rowy = rowx + 8;
-            const int tx = ldl_tri(min(rowx, n - 1)), ty = ldl_tri(min(rowy, n - 1));
-            const bool rokx = rowx < n && rowx >= j1, roky = rowy < n && rowy >= j1 && I + 1 < nT;
-            const bool xA = rokx && cokA && colA <= rowx, xB = rokx && cokB && colA + 1 <= rowx;
-            const bool yA = roky && cokA && colA <= rowy, yB = roky && cokB && colA + 1 <= rowy;
-            const double ax0 = k0 ? A[tx + cj] : 0.0, ax1 = k1 ? A[tx + cj + 4] : 0.0;
-            const double ay0 = k0 ? A[ty + cj] : 0.0, ay1 = k1 ? A[ty + cj + 4] : 0.0;
-            double cx0 = xA ? A[tx + colA] : 0.0, cx1 = xB ? A[tx + colA + 1] : 0.0;
-            double cy0 = yA ? A[ty + colA] : 0.0, cy1 = yB ? A[ty + colA + 1] : 0.0;
-            dmma884(cx0, cx1, ax0, b0);
-            dmma884(cy0, cy1, ay0, b0);
-            dmma884(cx0, cx1, ax1, b1);
-            dmma884(cy0, cy1, ay1, b1);
-            if (xA) A[tx + colA] = cx0;
-            if (xB) A[tx + colA + 1] = cx1;
-            if (yA) A[ty + colA] = cy0;
-            if (yB) A[ty + colA + 1] = cy1;
+        for (; I < nT; I += 2) {
+            ldl_tile_pair<true>(A, rowx, tx, cj, colA, j1, n, I + 1 < nT, k0, k1, b0, b1);
+            tx += 16 * rowx + 136;
+            rowx += 16;
         }
     }
 }
@@ -193,7 +235,7 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[NG], unsigne
 //      a(c, x) - sum_qq L(c, qq) W(x, qq),     W(x, qq) = (L D)(x, qq)  (broadcast loads),
 // for the lane's rows `on` and for the diagonal entry.  The loop over the (at most eight) finished
 // columns is unrolled with a uniform early exit, so every address is base + constant.
-template <int NG>
+template <int NG, bool BELOW>                // BELOW: every row in `on` lies below x (no symmetric access)
 __device__ __forceinline__ void ldl_col_generic(const double *A, const double *dpan, const int (&rb)[NG], int j0,
                                                 int q, int x, bool has22, const bool (&on)[NG], int lane,
                                                 double (&val)[NG], double &diag)
@@ -205,7 +247,8 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
     for (int g = 0; g < NG; ++g) {
         const int c = lane + 32 * g;
         lp[g] = A + rb[g] + j0;
-        val[g] = on[g] ? ((c < x) ? A[tx + c] : A[rb[g] + x]) : 0.0;
+        const int o = (BELOW || c > x) ? rb[g] + x : tx + c;
+        val[g] = on[g] ? A[o] : 0.0;
     }
     double dg = A[tx + x];
 #pragma unroll
@@ -359,10 +402,12 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
             continue;
         }
         __syncwarp();
-        double amax = fmax(fabs(gdiag), 1.0);         // the border holds ones
-        if (m > 1) ldl_assemble<LUV>(A, pxy, pt, m, P, lane, amax, bad);
-        amax = __longlong_as_double((long long)warp_max_u64((unsigned long long)__double_as_longlong(amax)));
-        const double tol = 1e-10 * amax;
+        // largest |entry| (high word: 2^-20 resolution is plenty for a tolerance); the border holds ones
+        unsigned amax_hi = max(ldl_hi_abs(gdiag), 0x3ff00000u);
+        if (m > 1) ldl_assemble<LUV>(A, pxy, pt, m, P, lane, amax_hi);
+        amax_hi = __reduce_max_sync(FULL, amax_hi);
+        bad = bad || amax_hi >= 0x7ff00000u;          // NaN / Inf among the gamma entries
+        const double tol = 1e-10 * ldl_from_hi(amax_hi);
         bool fail = __any_sync(FULL, bad);
         __syncwarp();                                 // pxy is dead from here: perm lives there
 #pragma unroll
@@ -385,7 +430,7 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
 #pragma unroll
                 for (int g = 0; g < NG; ++g) act[g] = lane + 32 * g > j && lane + 32 * g < n;
                 double v[NG], d;
-                ldl_col_generic<NG>(A, dpan, rb, j0, q, j, has22, act, lane, v, d);
+                ldl_col_generic<NG, true>(A, dpan, rb, j0, q, j, has22, act, lane, v, d);
                 int kind;                       // 0 / 1: 1x1 pivot; 2: 2x2 pivot with column j + 1
                 if (forced == 0) {
                     unsigned key = 0u;
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
 #pragma unroll
                         for (int g = 0; g < NG; ++g) on[g] = act[g] && lane + 32 * g < N && lane + 32 * g != r;
                         double val[NG], arr;
-                        ldl_col_generic<NG>(A, dpan, rb, j0, q, r, has22, on, lane, val, arr);
+                        ldl_col_generic<NG, false>(A, dpan, rb, j0, q, r, has22, on, lane, val, arr);
                         unsigned sk = key & ~0xffu;
 #pragma unroll
                         for (int g = 0; g < NG; ++g)
@@ -444,7 +489,7 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
 #pragma unroll
                     for (int g = 0; g < NG; ++g) on[g] = act[g] && lane + 32 * g > j + 1;
                     double v2[NG], d22, d21 = 0.0;
-                    ldl_col_generic<NG>(A, dpan, rb, j0, q, j + 1, has22, on, lane, v2, d22);
+                    ldl_col_generic<NG, true>(A, dpan, rb, j0, q, j + 1, has22, on, lane, v2, d22);
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {         // every group shuffles: no run-time register index
                         const double cand = __shfl_sync(FULL, v[g], (j + 1) & 31);

@@ -48,17 +48,17 @@ __device__ __forceinline__ double ldl_rcp(double x)
 
 // gamma(D_s, D_t) of the neighbour pairs, strictly lower triangle (predictor.py:573-575); the
 // same expressions as the LU's assembly, so both solvers factor the same matrix.
-template <int LUV>
+template <int LUV, int NT>
 __device__ __forceinline__ void ldl_assemble(double *A, const double2 *pxy, const double *pt, int m,
-                                             const SolveParams &P, int lane, unsigned &amax_hi)
+                                             const SolveParams &P, int tid, unsigned &amax_hi)
 {
     constexpr int U = 4;
     const int npairs = (m * (m - 1)) >> 1;
 #pragma unroll 1
-    for (int e0 = lane; e0 < npairs; e0 += 32 * U) {
+    for (int e0 = tid; e0 < npairs; e0 += NT * U) {
         unsigned w[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) w[u] = (e0 + 32 * u < npairs) ? __ldg(P.pairtab + e0 + 32 * u) : 0x00000100u;
+        for (int u = 0; u < U; ++u) w[u] = (e0 + NT * u < npairs) ? __ldg(P.pairtab + e0 + NT * u) : 0x00000100u;
         double g[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -80,7 +80,7 @@ __device__ __forceinline__ void ldl_assemble(double *A, const double2 *pxy, cons
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (e0 + 32 * u < npairs) {
+            if (e0 + NT * u < npairs) {
                 const int a = w[u] & 0xff, b = (w[u] >> 8) & 0xff;
                 A[ldl_tri(a) + b] = g[u];
                 amax_hi = max(amax_hi, ldl_hi_abs(g[u]));            // Inf / NaN: >= 0x7ff00000
@@ -137,8 +137,9 @@ __device__ __forceinline__ void ldl_tile_pair(double *A, int rowx, int tx, int c
     }
 }
 
+template <int W>
 __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int j0, int pw, int j1, int n,
-                                             bool has22, int lane)
+                                             bool has22, int lane, int warp)
 {
     const int g = lane >> 2, t = lane & 3;
     // this lane's entries of D for the panel columns t and 4 + t: diagonal, coupling with the next
@@ -152,7 +153,7 @@ __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int 
     const int Jf = j1 >> 3;
     const bool k0all = pw >= 4;                          // every lane's first k-column is a finished one
 #pragma unroll 1
-    for (int J = Jf; J < nT; ++J) {
+    for (int J = Jf + warp; J < nT; J += W) {          // tile columns dealt to the warps
         double b0 = 0.0, b1 = 0.0;
         {
             const int c = min(8 * J + g, n - 1);
@@ -198,33 +199,57 @@ __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int 
     }
 }
 
+// Row ownership: W warps per target; thread (warp, lane) owns rows r0 + RS s, r0 = lane + 32 warp,
+// RS = 32 W, s = 0 .. GW-1 (rows >= n are idle).  W = 1: one warp, barriers are __syncwarp().
+template <int W>
+__device__ __forceinline__ void ldl_sync()
+{
+    if constexpr (W == 1) __syncwarp();
+    else __syncthreads();
+}
+
+// max over the whole target (all W warps); slots: 2 W words, double-buffered by `phase`
+template <int W>
+__device__ __forceinline__ unsigned ldl_allmax(unsigned v, unsigned *slots, int &phase, int warp, int lane)
+{
+    v = __reduce_max_sync(FULL, v);
+    if constexpr (W > 1) {
+        if (lane == 0) slots[phase * W + warp] = v;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < W; ++w) v = max(v, slots[phase * W + w]);
+        phase ^= 1;
+    }
+    return v;
+}
+
 // Symmetric interchange of rows / columns p < r of the packed lower triangle (all n rows: the
 // finished columns of L and the right-hand-side row move with them).  Entry (r, p) stays.
-template <int NG>
-__device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[NG], unsigned char *perm, int p, int r,
-                                         int n, int lane)
+template <int GW, int RS, int W>
+__device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[GW], unsigned char *perm, int p, int r,
+                                         int n, int r0, int tid)
 {
     const int tp = ldl_tri(p), tr = ldl_tri(r);
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        const int i = lane + 32 * g;
+    for (int s = 0; s < GW; ++s) {
+        const int i = r0 + RS * s;
         if (i < n && i != r) {
             int o1, o2;
             if (i < p) { o1 = tp + i; o2 = tr + i; }
             else if (i == p) { o1 = tp + p; o2 = tr + r; }
-            else if (i < r) { o1 = rb[g] + p; o2 = tr + i; }
-            else { o1 = rb[g] + p; o2 = rb[g] + r; }
+            else if (i < r) { o1 = rb[s] + p; o2 = tr + i; }
+            else { o1 = rb[s] + p; o2 = rb[s] + r; }
             const double t1 = A[o1], t2 = A[o2];
             A[o1] = t2;
             A[o2] = t1;
         }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         const unsigned char t = perm[p];
         perm[p] = perm[r];
         perm[r] = t;
     }
-    __syncwarp();
+    ldl_sync<W>();
 }
 
 // D of the current panel lives in shared memory: dpan[0..7] = the diagonal, dpan[8..15]: dpan[8 + q] =
@@ -233,22 +258,22 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[NG], unsigne
 // Column x >= j (the column under examination, row r of the Bunch-Kaufman test by symmetry, or the
 // second column of a 2x2 block) brought up to date over the q finished panel columns,
 //      a(c, x) - sum_qq L(c, qq) W(x, qq),     W(x, qq) = (L D)(x, qq)  (broadcast loads),
-// for the lane's rows `on` and for the diagonal entry.  The loop over the (at most eight) finished
+// for the thread's rows `on` and for the diagonal entry.  The loop over the (at most eight) finished
 // columns is unrolled with a uniform early exit, so every address is base + constant.
-template <int NG, bool BELOW>                // BELOW: every row in `on` lies below x (no symmetric access)
-__device__ __forceinline__ void ldl_col_generic(const double *A, const double *dpan, const int (&rb)[NG], int j0,
-                                                int q, int x, bool has22, const bool (&on)[NG], int lane,
-                                                double (&val)[NG], double &diag)
+template <int GW, int RS, bool BELOW>        // BELOW: every row in `on` lies below x (no symmetric access)
+__device__ __forceinline__ void ldl_col_generic(const double *A, const double *dpan, const int (&rb)[GW], int j0,
+                                                int q, int x, bool has22, const bool (&on)[GW], int r0,
+                                                double (&val)[GW], double &diag)
 {
     const int tx = ldl_tri(x);
     const double *lx = A + tx + j0;          // row x's multipliers
-    const double *lp[NG];                    // the lane's own rows' multipliers
+    const double *lp[GW];                    // the thread's own rows' multipliers
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        const int c = lane + 32 * g;
-        lp[g] = A + rb[g] + j0;
-        const int o = (BELOW || c > x) ? rb[g] + x : tx + c;
-        val[g] = on[g] ? A[o] : 0.0;
+    for (int s = 0; s < GW; ++s) {
+        const int c = r0 + RS * s;
+        lp[s] = A + rb[s] + j0;
+        const int o = (BELOW || c > x) ? rb[s] + x : tx + c;
+        val[s] = on[s] ? A[o] : 0.0;
     }
     double dg = A[tx + x];
 #pragma unroll
@@ -262,15 +287,15 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
         }
         dg = __fma_rn(-lxq, w, dg);
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
-            if (on[g]) val[g] = __fma_rn(-lp[g][qq], w, val[g]);
+        for (int s = 0; s < GW; ++s)
+            if (on[s]) val[s] = __fma_rn(-lp[s][qq], w, val[s]);
     }
     diag = dg;
 }
 
-// Back substitution, rows of group GI (rows 32 GI .. 32 GI + 31) from the bottom up: x'_i is final once
-// the rows below it are done; lane l keeps z of columns l, l + 32, ...  Template recursion keeps every
-// register index a compile-time constant.
+// Back substitution (warp 0), rows of group GI (rows 32 GI .. 32 GI + 31) from the bottom up: x'_i is
+// final once the rows below it are done; lane l keeps z of columns l, l + 32, ...  Template recursion
+// keeps every register index a compile-time constant.
 template <int NG, int GI>
 __device__ __forceinline__ void ldl_backsub(const double *A, double (&zr)[NG], int N, int lane)
 {
@@ -293,11 +318,16 @@ __device__ __forceinline__ void ldl_backsub(const double *A, double (&zr)[NG], i
     }
 }
 
-template <int NG, int LUV>
-__global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams X, int adbl)
+// NG: 32-row groups of the k + 2 rows; W: warps per target (row groups dealt round-robin).
+template <int NG, int W, int LUV>
+__global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholParams X, int adbl)
 {
     extern __shared__ __align__(16) double smem_d[];
-    const int lane = threadIdx.x;
+    constexpr int GW = (NG + W - 1) / W;      // row slots per thread
+    constexpr int RS = 32 * W;                // row stride between a thread's slots
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = tid;                       // = lane + 32 warp
     const int k = P.k;
     const int kp = (k + 1) & ~1;
     double *A = smem_d;                                               // packed lower triangle, adbl doubles
@@ -306,22 +336,26 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
     unsigned char *perm = reinterpret_cast<unsigned char *>(pxy);     // pxy is dead after the assembly
     double *sol = pt;                                                 // and so is pt
     double *dpan = pt + kp;                                           // D of the current panel: dd[8], off[8]
+    double *sxch = dpan + 16;                                         // one double handed between the warps
+    unsigned *slots = reinterpret_cast<unsigned *>(sxch + 1);         // [2][W] max exchange (<= 10 words)
     // the epilogue's arrays alias the matrix, which is dead after the back substitution
     double *g0 = A, *rs = A + kp, *sc64 = A + 2 * kp;
     float *sc32a = reinterpret_cast<float *>(A + 3 * kp), *sc32b = sc32a + kp;
     unsigned *ids = reinterpret_cast<unsigned *>(A + 4 * kp);
-    int rb[NG];
+    int rb[GW];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) rb[g] = ldl_tri(lane + 32 * g);
+    for (int s = 0; s < GW; ++s) rb[s] = ldl_tri(r0 + RS * s);
     const double gdiag = gamma_st(P.M, 0.0, 0.0);                     // diagonal = gamma(0, 0), no special case
+    int phase = 0;
 
-    // The next target's selection is fetched into registers while the current one is factorised.
-    unsigned tl = 0, ntl = 0, nid[NG];
+    // The next target's selection is fetched into registers while the current one is factorised
+    // (thread -> neighbours r0 + RS s, the same ownership as the rows).
+    unsigned tl = 0, ntl = 0, nid[GW];
     int m = 0, nm = 0;
-    double4 no[NG];
-    double ng[NG];
+    double4 no[GW];
+    double ng[GW];
 #pragma unroll
-    for (int i = 0; i < NG; ++i) {
+    for (int i = 0; i < GW; ++i) {
         nid[i] = 0u;
         no[i] = make_double4(0.0, 0.0, 0.0, 0.0);
         ng[i] = 0.0;
@@ -330,15 +364,15 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
     auto fetch_ids = [&]() {
         nm = has_next ? P.sel_n[ntl] : 0;
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-            const int e = lane + 32 * i;
+        for (int i = 0; i < GW; ++i) {
+            const int e = r0 + RS * i;
             if (has_next && e < k) nid[i] = P.sel_idx[(size_t)ntl * k + e];
         }
     };
     auto fetch_obs = [&]() {
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-            const int e = lane + 32 * i;
+        for (int i = 0; i < GW; ++i) {
+            const int e = r0 + RS * i;
             if (e < nm) {
                 no[i] = X.obs4[nid[i]];
                 ng[i] = P.sel_gamma[(size_t)ntl * k + e];
@@ -357,15 +391,15 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
         const int64_t tg = P.c0 + tl;
         const int N = m + 1, n = m + 2;
         const int tN = ldl_tri(N);
-        __syncwarp();
+        ldl_sync<W>();                                // the previous target's epilogue is done with the arrays
         // ---- neighbours (prefetched), diagonal, Lagrange row, right-hand-side row ----
-        unsigned cid[NG];
-        double cres[NG], cg[NG];
+        unsigned cid[GW];
+        double cres[GW], cg[GW];
         bool bad = !(fabs(gdiag) < INFINITY);
         if (m > 0) {
 #pragma unroll
-            for (int i = 0; i < NG; ++i) {
-                const int e = lane + 32 * i;
+            for (int i = 0; i < GW; ++i) {
+                const int e = r0 + RS * i;
                 cid[i] = nid[i];
                 cres[i] = no[i].w;
                 cg[i] = ng[i];
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     bad = bad || !(fabs(ng[i]) < INFINITY);
                 }
             }
-            if (lane == 0) {
+            if (tid == 0) {
                 A[ldl_tri(m) + m] = 0.0;              // predictor.py:580
                 A[tN + m] = 1.0;
                 A[tN + N] = 0.0;
@@ -389,57 +423,57 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
         if (m <= 0) {
             fetch_ids();
             fetch_obs();
-            if (lane == 0) {
+            if (tid == 0) {
                 P.mean[tg] = 0.0;
                 P.std[tg] = 0.0;
                 if (P.nused_out) P.nused_out[tg] = m < 0 ? -1 : 0;
             }
-            for (int e = lane; e < k; e += 32) {
+            for (int e = tid; e < k; e += NT) {
                 if (P.w_out) P.w_out[(size_t)tg * k + e] = 0.f;
                 if (P.g_out) P.g_out[(size_t)tg * k + e] = 0.f;
                 if (P.idx_out) P.idx_out[(size_t)tg * k + e] = 0u;
             }
             continue;
         }
-        __syncwarp();
-        // largest |entry| (high word: 2^-20 resolution is plenty for a tolerance); the border holds ones
+        ldl_sync<W>();
+        // largest |entry| (high word: 2^-20 resolution is plenty for a tolerance); the border holds ones;
+        // NaN / Inf among the entries show as a high word >= 0x7ff00000
         unsigned amax_hi = max(ldl_hi_abs(gdiag), 0x3ff00000u);
-        if (m > 1) ldl_assemble<LUV>(A, pxy, pt, m, P, lane, amax_hi);
-        amax_hi = __reduce_max_sync(FULL, amax_hi);
-        bad = bad || amax_hi >= 0x7ff00000u;          // NaN / Inf among the gamma entries
+        if (bad) amax_hi = 0x7ff00000u;
+        if (m > 1) ldl_assemble<LUV, NT>(A, pxy, pt, m, P, tid, amax_hi);
+        amax_hi = ldl_allmax<W>(amax_hi, slots, phase, warp, lane);
         const double tol = 1e-10 * ldl_from_hi(amax_hi);
-        bool fail = __any_sync(FULL, bad);
-        __syncwarp();                                 // pxy is dead from here: perm lives there
+        bool fail = amax_hi >= 0x7ff00000u;           // uniform over the target's warps
+        ldl_sync<W>();                                // pxy is dead from here: perm lives there
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
-            if (lane + 32 * g < N) perm[lane + 32 * g] = (unsigned char)(lane + 32 * g);
-        __syncwarp();
+        for (int s = 0; s < GW; ++s)
+            if (r0 + RS * s < N) perm[r0 + RS * s] = (unsigned char)(r0 + RS * s);
         fetch_ids();
 
-        // ---- blocked Bunch-Kaufman: pivots among rows / columns 0 .. N-1 ----
+        // ---- blocked Bunch-Kaufman: pivots among rows / columns 0 .. N-1 (uniform control flow) ----
         int j0 = 0;
         while (j0 < N && !fail) {
-            if (lane < 16) dpan[lane] = 0.0;
-            __syncwarp();
+            if (tid < 16) dpan[tid] = 0.0;
+            ldl_sync<W>();
             bool has22 = false;
             int q = 0, forced = 0, r = 0;       // q: finished columns of this panel
             double lam = 0.0;
             while (q < 8 && j0 + q < N) {
                 const int j = j0 + q, tj = ldl_tri(j);
-                bool act[NG];
+                bool act[GW];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) act[g] = lane + 32 * g > j && lane + 32 * g < n;
-                double v[NG], d;
-                ldl_col_generic<NG, true>(A, dpan, rb, j0, q, j, has22, act, lane, v, d);
+                for (int s = 0; s < GW; ++s) act[s] = r0 + RS * s > j && r0 + RS * s < n;
+                double v[GW], d;
+                ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j, has22, act, r0, v, d);
                 int kind;                       // 0 / 1: 1x1 pivot; 2: 2x2 pivot with column j + 1
                 if (forced == 0) {
                     unsigned key = 0u;
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        const int i = lane + 32 * g;
-                        if (act[g] && i < N) key = max(key, (ldl_hi_abs(v[g]) & ~0xffu) | (unsigned)i);
+                    for (int s = 0; s < GW; ++s) {
+                        const int i = r0 + RS * s;
+                        if (act[s] && i < N) key = max(key, (ldl_hi_abs(v[s]) & ~0xffu) | (unsigned)i);
                     }
-                    key = __reduce_max_sync(FULL, key);
+                    key = ldl_allmax<W>(key, slots, phase, warp, lane);
                     r = (int)(key & 0xffu);
                     lam = ldl_from_hi(key & ~0xffu);       // max |a(i, j)|, i > j (truncated to 12 bits)
                     const double aj = fabs(d);
@@ -447,16 +481,16 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     if (!(aj >= LDL_ALPHA * lam)) {
                         if (r <= j) { fail = true; break; }            // NaN pivot
                         // row r up to date; sigma = max |a(r, c)| over c != r (c = j: lam)
-                        bool on[NG];
+                        bool on[GW];
 #pragma unroll
-                        for (int g = 0; g < NG; ++g) on[g] = act[g] && lane + 32 * g < N && lane + 32 * g != r;
-                        double val[NG], arr;
-                        ldl_col_generic<NG, false>(A, dpan, rb, j0, q, r, has22, on, lane, val, arr);
+                        for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s < N && r0 + RS * s != r;
+                        double val[GW], arr;
+                        ldl_col_generic<GW, RS, false>(A, dpan, rb, j0, q, r, has22, on, r0, val, arr);
                         unsigned sk = key & ~0xffu;
 #pragma unroll
-                        for (int g = 0; g < NG; ++g)
-                            if (on[g]) sk = max(sk, ldl_hi_abs(val[g]));
-                        sk = __reduce_max_sync(FULL, sk);
+                        for (int s = 0; s < GW; ++s)
+                            if (on[s]) sk = max(sk, ldl_hi_abs(val[s]));
+                        sk = ldl_allmax<W>(sk, slots, phase, warp, lane);
                         const double sig = ldl_from_hi(sk);
                         if (aj * sig >= LDL_ALPHA * lam * lam) kind = 0;
                         else if (fabs(arr) >= LDL_ALPHA * sig) kind = 1;
@@ -465,7 +499,8 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     if (kind == 2 && q == 7) break;        // the 2x2 block would leave the panel: close it
                     const int p = (kind == 1) ? j : j + 1;
                     if (kind == 1 || (kind == 2 && r != p)) {
-                        ldl_swap<NG>(A, rb, perm, p, r, n, lane);
+                        ldl_sync<W>();                     // every warp has read rows p and r
+                        ldl_swap<GW, RS, W>(A, rb, perm, p, r, n, r0, tid);
                         forced = kind;
                         continue;
                     }
@@ -477,36 +512,45 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     if (!(fabs(d) > tol)) { fail = true; break; }
                     const double dinv = ldl_rcp(d);
 #pragma unroll
-                    for (int g = 0; g < NG; ++g)
-                        if (act[g]) A[rb[g] + j] = v[g] * dinv;
-                    if (lane == 0) dpan[q] = d;
+                    for (int s = 0; s < GW; ++s)
+                        if (act[s]) A[rb[s] + j] = v[s] * dinv;
+                    if (tid == 0) dpan[q] = d;
                     q += 1;
                 } else {
                     if (!(lam > tol)) { fail = true; break; }
                     // column j + 1 up to date (over the same q finished columns)
                     const int tj1 = tj + j + 1;
-                    bool on[NG];
+                    bool on[GW];
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) on[g] = act[g] && lane + 32 * g > j + 1;
-                    double v2[NG], d22, d21 = 0.0;
-                    ldl_col_generic<NG, true>(A, dpan, rb, j0, q, j + 1, has22, on, lane, v2, d22);
+                    for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s > j + 1;
+                    double v2[GW], d22, d21 = 0.0;
+                    ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j + 1, has22, on, r0, v2, d22);
+                    // d21 = the updated a(j + 1, j), held by the owner of row j + 1
+                    if constexpr (W == 1) {
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {         // every group shuffles: no run-time register index
-                        const double cand = __shfl_sync(FULL, v[g], (j + 1) & 31);
-                        if (((j + 1) >> 5) == g) d21 = cand;
+                        for (int s = 0; s < GW; ++s) {     // every slot shuffles: no run-time register index
+                            const double cand = __shfl_sync(FULL, v[s], (j + 1) & 31);
+                            if (((j + 1) >> 5) == s) d21 = cand;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < GW; ++s)
+                            if (r0 + RS * s == j + 1) sxch[0] = v[s];
+                        __syncthreads();
+                        d21 = sxch[0];
                     }
                     // [l1 l2] = [w1 w2] D^-1, scaled by the off-diagonal like LAPACK's dsytf2
                     const double t = ldl_rcp(d21);
                     const double ak = d * t, akp1 = d22 * t;
                     const double den = t * ldl_rcp(__fma_rn(ak, akp1, -1.0));
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        if (on[g]) {
-                            A[rb[g] + j] = den * __fma_rn(akp1, v[g], -v2[g]);
-                            A[rb[g] + j + 1] = den * __fma_rn(ak, v2[g], -v[g]);
+                    for (int s = 0; s < GW; ++s) {
+                        if (on[s]) {
+                            A[rb[s] + j] = den * __fma_rn(akp1, v[s], -v2[s]);
+                            A[rb[s] + j + 1] = den * __fma_rn(ak, v2[s], -v[s]);
                         }
                     }
-                    if (lane == 0) {
+                    if (tid == 0) {
                         A[tj1 + j] = 0.0;                  // L(j+1, j) = 0
                         dpan[q] = d;
                         dpan[8 + q] = d21;
@@ -515,20 +559,21 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     has22 = true;
                     q += 2;
                 }
-                __syncwarp();
+                ldl_sync<W>();
             }
             if (fail) break;
-            if (j0 + q < N) ldl_trailing(A, dpan, j0, q, j0 + q, n, has22, lane);
-            __syncwarp();
+            if (j0 + q < N) ldl_trailing<W>(A, dpan, j0, q, j0 + q, n, has22, lane, warp);
+            ldl_sync<W>();
             j0 += q;
         }
         fetch_obs();
 
-        // ---- back substitution L' x' = z (row N), row by row: x'_i is final once the rows below it
-        //      are done; lane l keeps z of columns l, l + 32, ... ----
-        double zr[NG];
-        bool finite = true;
-        if (!fail) {
+        // ---- back substitution L' x' = z (row N) by warp 0: lane l keeps z of columns l, l + 32, ... ----
+        ldl_sync<W>();
+        bool solved = !fail;
+        if (warp == 0 && !fail) {
+            double zr[NG];
+            bool finite = true;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const int c = lane + 32 * g;
@@ -544,23 +589,23 @@ __global__ void __launch_bounds__(32) solve_ldl_kernel(SolveParams P, CholParams
                     if (o < m) sol[o] = zr[g];                 // o == m: the Lagrange multiplier
                 }
             }
-            fail = !__all_sync(FULL, finite);
+            solved = __all_sync(FULL, finite);
         }
-        if (fail) {   // tiny pivot / non-finite: the pivoted LU takes this target (and decides its rank)
-            if (lane == 0) X.fail_list[atomicAdd(X.fail_count, 1u)] = tl;
-            continue;
-        }
-        __syncwarp();
+        ldl_sync<W>();                                // the matrix is dead: stage the epilogue's inputs there
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-            const int e = lane + 32 * i;
+        for (int i = 0; i < GW; ++i) {
+            const int e = r0 + RS * i;
             if (e < m) {
                 g0[e] = cg[i];
                 rs[e] = cres[i];
                 ids[e] = cid[i];
             }
         }
-        __syncwarp();
-        solve_epilogue(P, sol, g0, ids, rs, sc64, sc32a, sc32b, m, tg, lane);
+        ldl_sync<W>();
+        if (warp == 0) {
+            if (solved) solve_epilogue(P, sol, g0, ids, rs, sc64, sc32a, sc32b, m, tg, lane);
+            // tiny pivot / non-finite: the pivoted LU takes this target (and decides its rank)
+            else if (lane == 0) X.fail_list[atomicAdd(X.fail_count, 1u)] = tl;
+        }
     }
 }

@@ -1932,7 +1932,7 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     int ldl_adbl = (k + 2) * (k + 3) / 2;
     if (ldl_adbl < 5 * ldl_kp) ldl_adbl = 5 * ldl_kp;      // the epilogue's arrays alias the matrix
     ldl_adbl = (ldl_adbl + 1) & ~1;
-    const size_t ldl_smem = sizeof(double) * ((size_t)ldl_adbl + 3 * (size_t)ldl_kp + 16);
+    const size_t ldl_smem = sizeof(double) * ((size_t)ldl_adbl + 3 * (size_t)ldl_kp + 24);
     const int chol_nt = (k + 2 + 7) / 8, chol_kp = (k + 1) & ~1;
     const size_t chol_smem = sizeof(double) * ((size_t)chol_nt * (chol_nt + 1) / 2 * 64 + 5 * (size_t)chol_kp) +
                              sizeof(unsigned) * (size_t)chol_kp;
@@ -2037,30 +2037,31 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
             CX.fail_list = fail_list;
             CX.fail_count = fail_count;
             QP.count = nullptr;
-#define STIF_LDL_V(NG_, LUV_)                                                                      \
+#define STIF_LDL_V(NG_, W_, LUV_)                                                                  \
     do {                                                                                           \
-        auto kern = solve_ldl_kernel<NG_, LUV_>;                                                   \
+        auto kern = solve_ldl_kernel<NG_, W_, LUV_>;                                               \
         STIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        (int)ldl_smem));                                            \
         int occ = 0;                                                                               \
-        STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, ldl_smem));        \
+        STIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W_, ldl_smem));   \
         if (occ < 1) occ = 1;                                                                      \
         int64_t gsz = (int64_t)occ * c->sm_count;                                                  \
         if (gsz > nc) gsz = nc;                                                                    \
-        kern<<<(unsigned)gsz, 32, ldl_smem, st>>>(QP, CX, ldl_adbl);                               \
+        kern<<<(unsigned)gsz, 32 * W_, ldl_smem, st>>>(QP, CX, ldl_adbl);                          \
     } while (0)
-#define STIF_LDL(NG_)                                                                              \
+#define STIF_LDL(NG_, W_)                                                                          \
     do {                                                                                           \
-        if (lu_var == LU_PRODUCT_SUM_SPH) STIF_LDL_V(NG_, LU_PRODUCT_SUM_SPH);                     \
-        else if (lu_var == LU_PRODUCT_SPH) STIF_LDL_V(NG_, LU_PRODUCT_SPH);                        \
-        else STIF_LDL_V(NG_, LU_GENERIC);                                                          \
+        if (lu_var == LU_PRODUCT_SUM_SPH) STIF_LDL_V(NG_, W_, LU_PRODUCT_SUM_SPH);                 \
+        else if (lu_var == LU_PRODUCT_SPH) STIF_LDL_V(NG_, W_, LU_PRODUCT_SPH);                    \
+        else STIF_LDL_V(NG_, W_, LU_GENERIC);                                                      \
     } while (0)
-            // lane l owns rows l, l + 32, ... of the k + 2 rows
-            if (k <= 30) STIF_LDL(1);
-            else if (k <= 62) STIF_LDL(2);
-            else if (k <= 94) STIF_LDL(3);
-            else if (k <= 126) STIF_LDL(4);
-            else STIF_LDL(5);
+            // k + 2 rows in groups of 32; one warp per target while many targets fit an SM, one warp
+            // per row group when the matrix (42 KB at k = 100) leaves room for five targets only
+            if (k <= 30) STIF_LDL(1, 1);
+            else if (k <= 62) STIF_LDL(2, 1);
+            else if (k <= 94) STIF_LDL(3, 3);
+            else if (k <= 126) STIF_LDL(4, 4);
+            else STIF_LDL(5, 5);
 #undef STIF_LDL
 #undef STIF_LDL_V
             STIF_CUDA(cudaGetLastError());

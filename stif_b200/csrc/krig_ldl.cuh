@@ -253,7 +253,7 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[GW], unsigne
 }
 
 // D of the current panel lives in shared memory: dpan[0..7] = the diagonal, dpan[8..15]: dpan[8 + q] =
-// the coupling of a 2x2 block that starts at panel column q.
+// the coupling of a 2x2 block that starts at panel column q (bit q of the uniform mask m22).
 //
 // Column x >= j (the column under examination, row r of the Bunch-Kaufman test by symmetry, or the
 // second column of a 2x2 block) brought up to date over the q finished panel columns,
@@ -262,7 +262,7 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[GW], unsigne
 // columns is unrolled with a uniform early exit, so every address is base + constant.
 template <int GW, int RS, bool BELOW>        // BELOW: every row in `on` lies below x (no symmetric access)
 __device__ __forceinline__ void ldl_col_generic(const double *A, const double *dpan, const int (&rb)[GW], int j0,
-                                                int q, int x, bool has22, const bool (&on)[GW], int r0,
+                                                int q, int x, unsigned m22, const bool (&on)[GW], int r0,
                                                 double (&val)[GW], double &diag)
 {
     const int tx = ldl_tri(x);
@@ -281,10 +281,8 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
         if (qq >= q) break;
         const double lxq = lx[qq];
         double w = dpan[qq] * lxq;
-        if (has22) {
-            if (qq + 1 < q) w = __fma_rn(dpan[8 + qq], lx[qq + 1], w);
-            if (qq > 0) w = __fma_rn(dpan[8 + qq - 1], lx[qq - 1], w);
-        }
+        if (m22 & (1u << qq)) w = __fma_rn(dpan[8 + qq], lx[qq + 1], w);                     // first column of a block
+        if (qq > 0 && (m22 & (1u << (qq > 0 ? qq - 1 : 0)))) w = __fma_rn(dpan[8 + qq - 1], lx[qq - 1], w);   // second
         dg = __fma_rn(-lxq, w, dg);
 #pragma unroll
         for (int s = 0; s < GW; ++s)
@@ -455,7 +453,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
         while (j0 < N && !fail) {
             if (tid < 16) dpan[tid] = 0.0;
             ldl_sync<W>();
-            bool has22 = false;
+            unsigned m22 = 0u;                  // bit q: a 2x2 block starts at panel column q
             int q = 0, forced = 0, r = 0;       // q: finished columns of this panel
             double lam = 0.0;
             while (q < 8 && j0 + q < N) {
@@ -464,7 +462,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
 #pragma unroll
                 for (int s = 0; s < GW; ++s) act[s] = r0 + RS * s > j && r0 + RS * s < n;
                 double v[GW], d;
-                ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j, has22, act, r0, v, d);
+                ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j, m22, act, r0, v, d);
                 int kind;                       // 0 / 1: 1x1 pivot; 2: 2x2 pivot with column j + 1
                 if (forced == 0) {
                     unsigned key = 0u;
@@ -485,7 +483,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
 #pragma unroll
                         for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s < N && r0 + RS * s != r;
                         double val[GW], arr;
-                        ldl_col_generic<GW, RS, false>(A, dpan, rb, j0, q, r, has22, on, r0, val, arr);
+                        ldl_col_generic<GW, RS, false>(A, dpan, rb, j0, q, r, m22, on, r0, val, arr);
                         unsigned sk = key & ~0xffu;
 #pragma unroll
                         for (int s = 0; s < GW; ++s)
@@ -524,7 +522,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
 #pragma unroll
                     for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s > j + 1;
                     double v2[GW], d22, d21 = 0.0;
-                    ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j + 1, has22, on, r0, v2, d22);
+                    ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j + 1, m22, on, r0, v2, d22);
                     // d21 = the updated a(j + 1, j), held by the owner of row j + 1
                     if constexpr (W == 1) {
 #pragma unroll
@@ -556,13 +554,13 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
                         dpan[8 + q] = d21;
                         dpan[q + 1] = d22;
                     }
-                    has22 = true;
+                    m22 |= 1u << q;
                     q += 2;
                 }
                 ldl_sync<W>();
             }
             if (fail) break;
-            if (j0 + q < N) ldl_trailing<W>(A, dpan, j0, q, j0 + q, n, has22, lane, warp);
+            if (j0 + q < N) ldl_trailing<W>(A, dpan, j0, q, j0 + q, n, m22 != 0u, lane, warp);
             ldl_sync<W>();
             j0 += q;
         }

@@ -2057,11 +2057,15 @@ extern "C" int stif_kriging_predict_dev(stif_ctx *c, const double *tx, const dou
     } while (0)
             // k + 2 rows in groups of 32; one warp per target while many targets fit an SM, one warp
             // per row group when the matrix (42 KB at k = 100) leaves room for five targets only
-            if (k <= 30) STIF_LDL(1, 1);
-            else if (k <= 62) STIF_LDL(2, 1);
-            else if (k <= 94) STIF_LDL(3, 3);
-            else if (k <= 126) STIF_LDL(4, 4);
-            else STIF_LDL(5, 5);
+            {
+                const char *ew = getenv("STIF_LDL_WARPS");     // experiments: warps per target
+                const int wsel = ew ? atoi(ew) : 0;
+                if (k <= 30) STIF_LDL(1, 1);
+                else if (k <= 62) { if (wsel == 2) STIF_LDL(2, 2); else STIF_LDL(2, 1); }
+                else if (k <= 94) STIF_LDL(3, 3);
+                else if (k <= 126) { if (wsel == 2) STIF_LDL(4, 2); else if (wsel == 1) STIF_LDL(4, 1); else STIF_LDL(4, 4); }
+                else STIF_LDL(5, 5);
+            }
 #undef STIF_LDL
 #undef STIF_LDL_V
             STIF_CUDA(cudaGetLastError());

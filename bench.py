@@ -470,9 +470,12 @@ def bench_kriging(env, cfg, steps, warmup, n_targets=0):
     # the assemble + solve kernel alone: its own flops (the gamma-vector work is the search kernel's)
     achieved = n_t * f_solve / (solve_ms_avg * 1e-3) / 1e12
     peak_tf = 2 * env.dfma_rate / 1e12
-    chol = bool(ss["cholesky_enabled"])
-    kname = "stif::krig::solve_chol_kernel" if chol else "stif::krig::solve_blk_kernel (pivoted LU)"
-    cnt = ncu_counters(("solve_chol_" if chol else "solve_lu_") + cfg["name"], n_t) if world == 1 else None
+    chol, ldl = bool(ss["cholesky_enabled"]), bool(ss.get("ldl_enabled"))
+    kname = ("stif::krig::solve_chol_kernel" if chol else
+             "stif::krig::solve_ldl_kernel (blocked Bunch-Kaufman LDL')" if ldl else
+             "stif::krig::solve_blk_kernel (pivoted LU)")
+    cnt = ncu_counters(("solve_chol_" if chol else "solve_ldl_" if ldl else "solve_lu_") + cfg["name"],
+                       n_t) if world == 1 else None
 
     (hx, _a), (hy, _b), (ht, _c) = pinned(tx), pinned(ty), pinned(tt)
     (hm, _d), (hs, _e) = pinned(np.zeros(n_t)), pinned(np.zeros(n_t))      # pinned result buffers
@@ -492,20 +495,24 @@ def bench_kriging(env, cfg, steps, warmup, n_targets=0):
                    "candidates_per_target": cbar,
                    "candidates_examined_per_target": st["candidates_examined"] / n_t,
                    "targets_rank_deficient": st["targets_singular"],
-                   "solver": "covariance-form Cholesky" if chol else "pivoted LU of the bordered system",
+                   "solver": ("covariance-form Cholesky" if chol else
+                              "Bunch-Kaufman LDL' of the bordered system" if ldl else
+                              "pivoted LU of the bordered system"),
+                   "first_pass_to_lu": ss.get("first_pass_to_lu"),
                    "l2": "256 MB device write between steps"},
         "phases_ms": {"search": search_ms_avg, "solve": solve_ms_avg},
         "e2e": {"value": n_t * world / e2e_s, "unit": "predictions/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": 24 * n_t, "d2h_bytes_per_step": 16 * n_t,
                 "path": "stif_kriging_predict_host (pinned host arrays), per rank"},
-        # target_keys, search, [Cholesky solve,] pivoted LU (the whole set, or the Cholesky fail list),
+        # target_keys, search, [Cholesky / LDL' solve,] pivoted LU (the whole set, or the first pass's fail list),
         # minimum-norm re-solve of flagged targets, stats
-        "gpu_launches": (6 if chol else 5) * steps,
+        "gpu_launches": (6 if (chol or ldl) else 5) * steps,
         "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s per GPU", "frac": achieved / peak_tf,
                      "flops_per_prediction": f_solve,
                      "flops_note": "SURVEY 8(d) assemble + solve share: k(k-1)/2 F_gamma + (k+1)^3/3 + 2(k+1)^2 "
-                                   "+ 4k (FMA = 2, sqrt = 1; an LU gets no credit for its extra n^3/3); the "
+                                   "+ 4k (FMA = 2, sqrt = 1; an LU gets no credit for its extra n^3/3, a symmetric "
+                                   "factorisation executes n^3/6 of it); the "
                                    "gamma-vector share Cbar F_gamma belongs to the search kernel",
                      "kernel_ms": solve_ms_avg,
                      "frac_incl_search": (n_t * (f_search + f_solve) / (ms_per_step * 1e-3) / 1e12) / peak_tf,

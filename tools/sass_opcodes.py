@@ -6,7 +6,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "stif_b200", "libstif_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KERNELS = ["pair_kernelILi0ELb0", "pair_kernelILi0ELb1", "solve_chol_kernelILi2ELi2ELi0", "search_kernelILi1", "solve_blk_kernelILi4ELi2",
+KERNELS = ["pair_kernelILi0ELb0", "pair_kernelILi0ELb1", "solve_chol_kernelILi2ELi2ELi0", "search_kernelILi1", "solve_blk_kernelILi4ELi2", "solve_ldl_kernelILi4ELi4ELi2", "solve_ldl_kernelILi2ELi1ELi2",
            "solve_minnorm_kernel", "reduce_kernelILb1"]
 INTEREST = ("FADD2", "FMUL2", "FFMA2", "UBLKCP", "SYNCS", "DMMA", "REDG", "ATOMS", "ATOMG", "DFMA", "DADD", "DMUL", "DSETP", "MUFU",
             "LDS", "STS", "LDG", "STG", "SHFL", "VOTE", "REDUX", "BAR", "F2I", "I2F")

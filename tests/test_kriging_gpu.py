@@ -237,6 +237,35 @@ def test_min_points_and_empty(ctx):
     compare(g, o, z, True)
 
 
+@pytest.mark.parametrize("k", [12, 100])
+def test_ldl_ragged_and_empty_targets(ctx, k):
+    """The LDL' kernel (one warp per target at k = 12, four at k = 100) on targets without any
+    candidate, below min_kriging_points, and with anything between 10 and k neighbours."""
+    space, t, z, tsp, tt = synth(3000, 300, seed=3)
+    tt[:50] = -5.0            # before every observation: causal filter leaves nothing
+    tsp[50:60] = 1e6          # far outside the grid
+    g = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 10, k, 60.0, 60.0, f32=False)
+    ss = ctx.kriging_solver_stats()
+    assert ss["ldl_enabled"] and ss["first_pass_to_lu"] == 0
+    o = ok.predict(space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 10, k, 60.0, 60.0, f32_storage=False)
+    assert np.all(g["n_used"][:60] == -1) and np.all(g["mean"][:60] == 0) and np.all(g["std"][:60] == 0)
+    used = o["n_used"][o["n_used"] > 0]
+    assert used.min() < min(k, 30) and used.max() == min(k, used.max())   # ragged systems (and full ones at k = 12)
+    assert k > 12 or used.max() == k
+    compare(g, o, z, False)
+
+
+def test_ldl_fewer_observations_than_k(ctx):
+    space, t, z, tsp, tt = synth(12, 40, seed=8, extent=20.0)
+    tt[:] = 400.0
+    for k in (50, 100):
+        g = gpu_predict(ctx, space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, k, 1e3, 1e3, f32=False)
+        assert ctx.kriging_solver_stats()["ldl_enabled"]
+        o = ok.predict(space, t, z, tsp, tt, PRODUCT_SUM, P_PRODUCT_SUM, 1, k, 1e3, 1e3, f32_storage=False)
+        assert np.all(o["n_used"] == 12)
+        compare(g, o, z, False)
+
+
 def test_leave_out(ctx):
     space, t, z, _, _ = synth(5000, 1, seed=5)
     sel = np.arange(0, 5000, 10)
@@ -304,7 +333,7 @@ def test_errors(ctx):
     c2.close()
 
 
-@pytest.mark.parametrize("solver", ["auto", "lu"])
+@pytest.mark.parametrize("solver", ["auto", "lu", "ldl"])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 46, 47, 48, 55, 62, 63, 64, 65, 96, 127,
                                128])
 def test_every_kernel_variant(ctx, k, solver):

@@ -1,6 +1,6 @@
 // krig_ldl.cuh -- symmetric indefinite kriging solve: blocked Bunch-Kaufman LDL' of the reference's
-// own bordered system, one warp per target, trailing updates on the FP64 tensor cores.
-// Included by kriging.cu (namespace stif::krig).
+// own bordered system, trailing updates on the FP64 tensor cores; one warp per target up to
+// k = 62, one warp per 32-row group above.  Included by kriging.cu (namespace stif::krig).
 //
 // Replaces calc_kriging_weights (stif/predictor.py:566-593) for models that are NOT valid
 // variograms: product / product_sum (stif/variogram_models.py:126-127, :155-157) give an
@@ -9,24 +9,32 @@
 //      P K P' = L D L'      (D block diagonal with 1x1 and 2x2 blocks, partial pivoting after
 //                            Bunch and Kaufman: element growth bounded like the pivoted LU's)
 // needs half the flops and -- decisive here -- half the shared memory of the general LU: the
-// packed lower triangle of a k = 100 system is 42 KB, so five targets are resident per SM with
-// ONE warp each and the factorisation runs without a single CTA barrier (the multi-warp LU spent
-// 22 % of its stall samples at barriers and another 34 % waiting, at two CTAs per SM).
+// packed lower triangle of a k = 100 system is 42 KB against 92 KB, five targets are resident per
+// SM instead of two.
 //
 // Storage: rows 0..N-1 (N = m + 1: the m neighbours and the Lagrange row) and the right-hand
 // side as row N of the SAME packed lower triangle, row i at i (i + 1) / 2.  The elimination of a
 // pivot updates every row below it, so row N leaves the factorisation as z = D^-1 L^-1 P b and
-// only the back substitution  L' x' = z  remains.  Lane l owns rows l, l + 32, ... (consecutive
-// rows of the packed triangle fall into distinct banks: the triangular numbers are a complete
-// residue system modulo 16).
+// only the back substitution  L' x' = z  remains.  Thread (warp, lane) owns rows
+// lane + 32 (warp + W s) (consecutive rows of the packed triangle fall into distinct banks: the
+// triangular numbers are a complete residue system modulo 16).
 //
 // Blocking (the structure of LAPACK's dsytrf / dlasyf, without its workspace): inside a panel of
 // up to eight columns the matrix is touched by the symmetric interchanges only.  The column under
-// examination -- and row r of the Bunch-Kaufman test -- is brought up to date on the fly,
-//      a(i, j) - sum_q L(i, q) W(j, q),     W = L D  recomputed from D (registers),
-// with the lane's own rows' panel multipliers in registers; the multipliers L(:, j) are stored in
-// place.  After the panel the whole trailing matrix receives  - L W'  in 8x8 tiles of two
-// mma.sync.m8n8k4.f64 (DMMA) each, masked at the edges of the triangle.
+// examination -- and row r of the Bunch-Kaufman test, by symmetry -- is brought up to date on the
+// fly,
+//      a(i, j) - sum_q L(i, q) W(j, q),     W = L D  recomputed from D (16 doubles of shared memory),
+// and the multipliers L(:, j) are stored in place.  After the panel the whole trailing matrix
+// receives  - L W'  in 8x8 tiles of two mma.sync.m8n8k4.f64 (DMMA) each, masked at the edges of
+// the triangle.
+//
+// Warps per target: with one warp a target needs no CTA barrier at all, and up to k = 62 sixteen
+// such targets are resident per SM.  At k = 100 only five fit, too few to hide the latency of the
+// dependent panel steps, so every 32-row group gets its own warp (W = NG): the warps take identical
+// decisions from shared data (pivot keys meet in a double-buffered slot + one barrier), tile
+// columns of the trailing update are dealt round-robin, warp 0 does the back substitution and the
+// epilogue.  Results are bit-identical for every W (measured at C5, 125k targets: 25.9 ms with one
+// warp, 21.0 with two, 19.1 with four; the pivoted LU: 34.7).
 //
 // Any pivot below 1e-10 max|K| and any non-finite entry or solution sends the target to the
 // pivoted LU (fail list, exactly like the Cholesky kernel), which owns the rank decision.
@@ -152,8 +160,11 @@ __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int 
     const int cj = j0 + t;
     const int Jf = j1 >> 3;
     const bool k0all = pw >= 4;                          // every lane's first k-column is a finished one
+    // tile columns dealt to the warps, every other round in reverse order: column J holds nT - J tiles
 #pragma unroll 1
-    for (int J = Jf + warp; J < nT; J += W) {          // tile columns dealt to the warps
+    for (int it = 0;; ++it) {
+        const int J = Jf + it * W + ((it & 1) ? W - 1 - warp : warp);
+        if (J >= nT) break;
         double b0 = 0.0, b1 = 0.0;
         {
             const int c = min(8 * J + g, n - 1);

@@ -40,6 +40,10 @@
 // pivoted LU (fail list, exactly like the Cholesky kernel), which owns the rank decision.
 
 constexpr double LDL_ALPHA = 0.6403882032022076;     // (1 + sqrt 17) / 8
+#ifndef STIF_LDL_PW
+#define STIF_LDL_PW 8
+#endif
+constexpr int LDL_PW = STIF_LDL_PW;                  // panel width (<= 8: two DMMA k-steps of 4)
 
 __device__ __forceinline__ int ldl_tri(int i) { return (i * (i + 1)) >> 1; }
 __device__ __forceinline__ unsigned ldl_hi_abs(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
@@ -288,7 +292,7 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
     }
     double dg = A[tx + x];
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) {
+    for (int qq = 0; qq < LDL_PW; ++qq) {
         if (qq >= q) break;
         const double lxq = lx[qq];
         double w = dpan[qq] * lxq;
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
             unsigned m22 = 0u;                  // bit q: a 2x2 block starts at panel column q
             int q = 0, forced = 0, r = 0;       // q: finished columns of this panel
             double lam = 0.0;
-            while (q < 8 && j0 + q < N) {
+            while (q < LDL_PW && j0 + q < N) {
                 const int j = j0 + q, tj = ldl_tri(j);
                 bool act[GW];
 #pragma unroll
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
                         else if (fabs(arr) >= LDL_ALPHA * sig) kind = 1;
                         else kind = 2;
                     }
-                    if (kind == 2 && q == 7) break;        // the 2x2 block would leave the panel: close it
+                    if (kind == 2 && q == LDL_PW - 1) break;   // the 2x2 block would leave the panel: close it
                     const int p = (kind == 1) ? j : j + 1;
                     if (kind == 1 || (kind == 2 && r != p)) {
                         ldl_sync<W>();                     // every warp has read rows p and r

@@ -291,17 +291,37 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
         val[s] = on[s] ? A[o] : 0.0;
     }
     double dg = A[tx + x];
+    if (m22 == 0u) {                         // no 2x2 block among the finished columns: W = d L
 #pragma unroll
-    for (int qq = 0; qq < LDL_PW; ++qq) {
-        if (qq >= q) break;
-        const double lxq = lx[qq];
-        double w = dpan[qq] * lxq;
-        if (m22 & (1u << qq)) w = __fma_rn(dpan[8 + qq], lx[qq + 1], w);                     // first column of a block
-        if (qq > 0 && (m22 & (1u << (qq > 0 ? qq - 1 : 0)))) w = __fma_rn(dpan[8 + qq - 1], lx[qq - 1], w);   // second
-        dg = __fma_rn(-lxq, w, dg);
+        for (int qq = 0; qq < LDL_PW; ++qq) {
+            if (qq >= q) break;
+            const double lxq = lx[qq];
+            const double w = dpan[qq] * lxq;
+            dg = __fma_rn(-lxq, w, dg);
 #pragma unroll
-        for (int s = 0; s < GW; ++s)
-            if (on[s]) val[s] = __fma_rn(-lp[s][qq], w, val[s]);
+            for (int s = 0; s < GW; ++s)
+                if (on[s]) val[s] = __fma_rn(-lp[s][qq], w, val[s]);
+        }
+    } else {
+        // W(x, qq) = d L(x, qq) + off(qq) L(x, qq + 1) + off(qq - 1) L(x, qq - 1); off is zero wherever no
+        // block couples the two columns, and L(x, qq + 1) is a finite entry of row x even when that
+        // column is not finished yet (j0 + qq + 1 <= j <= x), so the products need no predicate
+        double lprev = 0.0, offprev = 0.0, lcur = lx[0];
+#pragma unroll
+        for (int qq = 0; qq < LDL_PW; ++qq) {
+            if (qq >= q) break;
+            const double lnext = lx[qq + 1], offq = dpan[8 + qq];
+            double w = dpan[qq] * lcur;
+            w = __fma_rn(offq, lnext, w);
+            w = __fma_rn(offprev, lprev, w);
+            dg = __fma_rn(-lcur, w, dg);
+#pragma unroll
+            for (int s = 0; s < GW; ++s)
+                if (on[s]) val[s] = __fma_rn(-lp[s][qq], w, val[s]);
+            lprev = lcur;
+            lcur = lnext;
+            offprev = offq;
+        }
     }
     diag = dg;
 }

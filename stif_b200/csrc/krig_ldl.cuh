@@ -156,9 +156,9 @@ __device__ __forceinline__ void ldl_trailing(double *A, const double *dpan, int 
     const int g = lane >> 2, t = lane & 3;
     // this lane's entries of D for the panel columns t and 4 + t: diagonal, coupling with the next
     // and with the previous column (a block never starts at the panel's last column)
-    const double d0 = dpan[t], d1 = dpan[4 + t];
-    const double u0 = dpan[8 + t], u1 = (t < 3) ? dpan[12 + t] : 0.0;
-    const double l0 = (t > 0) ? dpan[8 + t - 1] : 0.0, l1 = dpan[11 + t];
+    const double d0 = dpan[2 * t], d1 = dpan[2 * (4 + t)];
+    const double u0 = dpan[2 * t + 1], u1 = (t < 3) ? dpan[2 * (4 + t) + 1] : 0.0;
+    const double l0 = (t > 0) ? dpan[2 * (t - 1) + 1] : 0.0, l1 = dpan[2 * (3 + t) + 1];
     const bool k0 = t < pw, k1 = 4 + t < pw;
     const int nT = (n + 7) >> 3;
     const int cj = j0 + t;
@@ -267,8 +267,9 @@ __device__ __forceinline__ void ldl_swap(double *A, const int (&rb)[GW], unsigne
     ldl_sync<W>();
 }
 
-// D of the current panel lives in shared memory: dpan[0..7] = the diagonal, dpan[8..15]: dpan[8 + q] =
-// the coupling of a 2x2 block that starts at panel column q (bit q of the uniform mask m22).
+// D of the current panel lives in shared memory as pairs: dpan[2 q] = the diagonal entry of panel column
+// q, dpan[2 q + 1] = the coupling of a 2x2 block that starts at q (bit q of the uniform mask m22), so
+// one 16-byte broadcast load fetches both.
 //
 // Column x >= j (the column under examination, row r of the Bunch-Kaufman test by symmetry, or the
 // second column of a 2x2 block) brought up to date over the q finished panel columns,
@@ -296,7 +297,7 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
         for (int qq = 0; qq < LDL_PW; ++qq) {
             if (qq >= q) break;
             const double lxq = lx[qq];
-            const double w = dpan[qq] * lxq;
+            const double w = dpan[2 * qq] * lxq;
             dg = __fma_rn(-lxq, w, dg);
 #pragma unroll
             for (int s = 0; s < GW; ++s)
@@ -310,8 +311,9 @@ __device__ __forceinline__ void ldl_col_generic(const double *A, const double *d
 #pragma unroll
         for (int qq = 0; qq < LDL_PW; ++qq) {
             if (qq >= q) break;
-            const double lnext = lx[qq + 1], offq = dpan[8 + qq];
-            double w = dpan[qq] * lcur;
+            const double2 dq = *reinterpret_cast<const double2 *>(dpan + 2 * qq);     // {d, off}
+            const double lnext = lx[qq + 1], offq = dq.y;
+            double w = dq.x * lcur;
             w = __fma_rn(offq, lnext, w);
             w = __fma_rn(offprev, lprev, w);
             dg = __fma_rn(-lcur, w, dg);
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
     double *pt = reinterpret_cast<double *>(pxy + kp);
     unsigned char *perm = reinterpret_cast<unsigned char *>(pxy);     // pxy is dead after the assembly
     double *sol = pt;                                                 // and so is pt
-    double *dpan = pt + kp;                                           // D of the current panel: dd[8], off[8]
+    double *dpan = pt + kp;                                           // D of the current panel: 8 x {diagonal, coupling}, 16-byte aligned
     double *sxch = dpan + 16;                                         // one double handed between the warps
     unsigned *slots = reinterpret_cast<unsigned *>(sxch + 1);         // [2][W] max exchange (<= 10 words)
     // the epilogue's arrays alias the matrix, which is dead after the back substitution
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
 #pragma unroll
                     for (int s = 0; s < GW; ++s)
                         if (act[s]) A[rb[s] + j] = v[s] * dinv;
-                    if (tid == 0) dpan[q] = d;
+                    if (tid == 0) dpan[2 * q] = d;
                     q += 1;
                 } else {
                     if (!(lam > tol)) { fail = true; break; }
@@ -585,9 +587,9 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
                     }
                     if (tid == 0) {
                         A[tj1 + j] = 0.0;                  // L(j+1, j) = 0
-                        dpan[q] = d;
-                        dpan[8 + q] = d21;
-                        dpan[q + 1] = d22;
+                        dpan[2 * q] = d;
+                        dpan[2 * q + 1] = d21;
+                        dpan[2 * q + 2] = d22;
                     }
                     m22 |= 1u << q;
                     q += 2;

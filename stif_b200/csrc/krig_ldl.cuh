@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
     unsigned char *perm = reinterpret_cast<unsigned char *>(pxy);     // pxy is dead after the assembly
     double *sol = pt;                                                 // and so is pt
     double *dpan = pt + kp;                                           // D of the current panel: 8 x {diagonal, coupling}, 16-byte aligned
-    double *sxch = dpan + 16;                                         // one double handed between the warps
-    unsigned *slots = reinterpret_cast<unsigned *>(sxch + 1);         // [2][W] max exchange (<= 10 words)
+    double *sxch = dpan + 16;                                         // three doubles handed between rows' owners
+    unsigned *slots = reinterpret_cast<unsigned *>(sxch + 3);         // [2][W] max exchange (<= 10 words)
     // the epilogue's arrays alias the matrix, which is dead after the back substitution
     double *g0 = A, *rs = A + kp, *sc64 = A + 2 * kp;
     float *sc32a = reinterpret_cast<float *>(A + 3 * kp), *sc32b = sc32a + kp;
@@ -491,8 +491,7 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
             if (tid < 16) dpan[tid] = 0.0;
             ldl_sync<W>();
             unsigned m22 = 0u;                  // bit q: a 2x2 block starts at panel column q
-            int q = 0, forced = 0, r = 0;       // q: finished columns of this panel
-            double lam = 0.0;
+            int q = 0;                          // finished columns of this panel
             while (q < LDL_PW && j0 + q < N) {
                 const int j = j0 + q, tj = ldl_tri(j);
                 bool act[GW];
@@ -500,48 +499,47 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
                 for (int s = 0; s < GW; ++s) act[s] = r0 + RS * s > j && r0 + RS * s < n;
                 double v[GW], d;
                 ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j, m22, act, r0, v, d);
-                int kind;                       // 0 / 1: 1x1 pivot; 2: 2x2 pivot with column j + 1
-                if (forced == 0) {
-                    unsigned key = 0u;
+                unsigned key = 0u;
 #pragma unroll
-                    for (int s = 0; s < GW; ++s) {
-                        const int i = r0 + RS * s;
-                        if (act[s] && i < N) key = max(key, (ldl_hi_abs(v[s]) & ~0xffu) | (unsigned)i);
-                    }
-                    key = ldl_allmax<W>(key, slots, phase, warp, lane);
-                    r = (int)(key & 0xffu);
-                    lam = ldl_from_hi(key & ~0xffu);       // max |a(i, j)|, i > j (truncated to 12 bits)
-                    const double aj = fabs(d);
-                    kind = 0;
-                    if (!(aj >= LDL_ALPHA * lam)) {
-                        if (r <= j) { fail = true; break; }            // NaN pivot
-                        // row r up to date; sigma = max |a(r, c)| over c != r (c = j: lam)
-                        bool on[GW];
+                for (int s = 0; s < GW; ++s) {
+                    const int i = r0 + RS * s;
+                    if (act[s] && i < N) key = max(key, (ldl_hi_abs(v[s]) & ~0xffu) | (unsigned)i);
+                }
+                key = ldl_allmax<W>(key, slots, phase, warp, lane);
+                const int r = (int)(key & 0xffu);
+                const double lam = ldl_from_hi(key & ~0xffu);  // max |a(i, j)|, i > j (truncated to 12 bits)
+                const double aj = fabs(d);
+                int kind = 0;                   // 0 / 1: 1x1 pivot (1: after j <-> r); 2: 2x2 pivot (j, r)
+                double val[GW], arr = 0.0;      // column r up to date (row r of the test, by symmetry)
 #pragma unroll
-                        for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s < N && r0 + RS * s != r;
-                        double val[GW], arr;
-                        ldl_col_generic<GW, RS, false>(A, dpan, rb, j0, q, r, m22, on, r0, val, arr);
-                        unsigned sk = key & ~0xffu;
+                for (int s = 0; s < GW; ++s) val[s] = 0.0;
+                if (!(aj >= LDL_ALPHA * lam)) {
+                    if (r <= j) { fail = true; break; }            // NaN pivot
+                    // sigma = max |a(r, c)| over c != r (c = j: lam); the values are kept: after an
+                    // interchange column r IS the pivot column and needs no second evaluation
+                    bool on[GW];
 #pragma unroll
-                        for (int s = 0; s < GW; ++s)
-                            if (on[s]) sk = max(sk, ldl_hi_abs(val[s]));
-                        sk = ldl_allmax<W>(sk, slots, phase, warp, lane);
-                        const double sig = ldl_from_hi(sk);
-                        if (aj * sig >= LDL_ALPHA * lam * lam) kind = 0;
-                        else if (fabs(arr) >= LDL_ALPHA * sig) kind = 1;
-                        else kind = 2;
-                    }
-                    if (kind == 2 && q == LDL_PW - 1) break;   // the 2x2 block would leave the panel: close it
-                    const int p = (kind == 1) ? j : j + 1;
-                    if (kind == 1 || (kind == 2 && r != p)) {
-                        ldl_sync<W>();                     // every warp has read rows p and r
-                        ldl_swap<GW, RS, W>(A, rb, perm, p, r, n, r0, tid);
-                        forced = kind;
-                        continue;
-                    }
-                } else {
-                    kind = forced;
-                    forced = 0;
+                    for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s != r;
+                    ldl_col_generic<GW, RS, false>(A, dpan, rb, j0, q, r, m22, on, r0, val, arr);
+                    unsigned sk = key & ~0xffu;
+#pragma unroll
+                    for (int s = 0; s < GW; ++s)
+                        if (on[s] && r0 + RS * s < N) sk = max(sk, ldl_hi_abs(val[s]));
+                    sk = ldl_allmax<W>(sk, slots, phase, warp, lane);
+                    const double sig = ldl_from_hi(sk);
+                    if (aj * sig >= LDL_ALPHA * lam * lam) kind = 0;
+                    else if (fabs(arr) >= LDL_ALPHA * sig) kind = 1;
+                    else kind = 2;
+                }
+                if (kind == 2 && q == LDL_PW - 1) break;   // the 2x2 block would leave the panel: close it
+                if (kind == 1) {
+                    // rows / columns j <-> r: the new column j is the old column r (row r keeps a(r, j))
+                    ldl_sync<W>();                         // every warp has read rows j and r
+                    ldl_swap<GW, RS, W>(A, rb, perm, j, r, n, r0, tid);
+#pragma unroll
+                    for (int s = 0; s < GW; ++s)
+                        if (r0 + RS * s != r) v[s] = val[s];
+                    d = arr;
                 }
                 if (kind < 2) {
                     if (!(fabs(d) > tol)) { fail = true; break; }
@@ -553,36 +551,32 @@ __global__ void __launch_bounds__(32 * W) solve_ldl_kernel(SolveParams P, CholPa
                     q += 1;
                 } else {
                     if (!(lam > tol)) { fail = true; break; }
-                    // column j + 1 up to date (over the same q finished columns)
-                    const int tj1 = tj + j + 1;
-                    bool on[GW];
+                    // 2x2 pivot: rows / columns j + 1 <-> r, the second pivot column is the old column r.
+                    // Three entries change owner: a(j+1, j) and a(j+1, r) move to row r, a(r, j) becomes d21.
+                    const int pr = j + 1, tj1 = tj + j + 1;
 #pragma unroll
-                    for (int s = 0; s < GW; ++s) on[s] = act[s] && r0 + RS * s > j + 1;
-                    double v2[GW], d22, d21 = 0.0;
-                    ldl_col_generic<GW, RS, true>(A, dpan, rb, j0, q, j + 1, m22, on, r0, v2, d22);
-                    // d21 = the updated a(j + 1, j), held by the owner of row j + 1
-                    if constexpr (W == 1) {
-#pragma unroll
-                        for (int s = 0; s < GW; ++s) {     // every slot shuffles: no run-time register index
-                            const double cand = __shfl_sync(FULL, v[s], (j + 1) & 31);
-                            if (((j + 1) >> 5) == s) d21 = cand;
+                    for (int s = 0; s < GW; ++s) {
+                        const int i = r0 + RS * s;
+                        if (i == pr) {
+                            sxch[0] = v[s];
+                            sxch[1] = val[s];
                         }
-                    } else {
-#pragma unroll
-                        for (int s = 0; s < GW; ++s)
-                            if (r0 + RS * s == j + 1) sxch[0] = v[s];
-                        __syncthreads();
-                        d21 = sxch[0];
+                        if (i == r) sxch[2] = v[s];
                     }
+                    ldl_sync<W>();                         // (also: every warp has read rows j + 1 and r)
+                    const double xa = sxch[0], xb = sxch[1], d21 = sxch[2], d22 = arr;
+                    if (r != pr) ldl_swap<GW, RS, W>(A, rb, perm, pr, r, n, r0, tid);
                     // [l1 l2] = [w1 w2] D^-1, scaled by the off-diagonal like LAPACK's dsytf2
                     const double t = ldl_rcp(d21);
                     const double ak = d * t, akp1 = d22 * t;
                     const double den = t * ldl_rcp(__fma_rn(ak, akp1, -1.0));
 #pragma unroll
                     for (int s = 0; s < GW; ++s) {
-                        if (on[s]) {
-                            A[rb[s] + j] = den * __fma_rn(akp1, v[s], -v2[s]);
-                            A[rb[s] + j + 1] = den * __fma_rn(ak, v2[s], -v[s]);
+                        const int i = r0 + RS * s;
+                        if (act[s] && i > pr) {
+                            const double w1 = (i == r) ? xa : v[s], w2 = (i == r) ? xb : val[s];
+                            A[rb[s] + j] = den * __fma_rn(akp1, w1, -w2);
+                            A[rb[s] + j + 1] = den * __fma_rn(ak, w2, -w1);
                         }
                     }
                     if (tid == 0) {

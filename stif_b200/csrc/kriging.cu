@@ -354,7 +354,11 @@ __device__ __forceinline__ int warp_count_le(const unsigned long long *key, int 
                                              unsigned long long thr)
 {
     int c = 0;
-    for (int e = lane; e < m; e += 32) c += (key[e] <= thr) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < BUF_CAP / 32; ++i) {       // m <= BUF_CAP: fixed trip count, predicated loads
+        const int e = lane + 32 * i;
+        if (e < m) c += (key[e] <= thr) ? 1 : 0;
+    }
     return __reduce_add_sync(FULL, c);
 }
 
@@ -362,10 +366,14 @@ __device__ __forceinline__ int warp_count_le(const unsigned long long *key, int 
 __device__ void select_k(const WarpBuf &B, int &m, int k, int lane)
 {
     unsigned long long lo = ~0ull, hi = 0ull;
-    for (int e = lane; e < m; e += 32) {
-        const unsigned long long v = B.key[e];
-        lo = v < lo ? v : lo;
-        hi = v > hi ? v : hi;
+#pragma unroll
+    for (int i = 0; i < BUF_CAP / 32; ++i) {
+        const int e = lane + 32 * i;
+        if (e < m) {
+            const unsigned long long v = B.key[e];
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
+        }
     }
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long a = __shfl_xor_sync(FULL, lo, off);

@@ -54,3 +54,20 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "liboracle" not in src, f
+
+
+def test_flag_constants_match_header():
+    """The bit values of the ctypes layer are the header's #defines (STIF_KRIG_*, STIF_VARIO_*)."""
+    text = open(HEADER).read()
+    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(STIF_(?:KRIG|VARIO)_[A-Z0-9_]+)\s+(\d+)", text)}
+    assert "STIF_KRIG_TRY_LDL" in defines and "STIF_VARIO_DETERMINISTIC" in defines
+    checked = 0
+    for name, value in defines.items():
+        py = name[len("STIF_"):]
+        if hasattr(_native, py):
+            assert getattr(_native, py) == value, name
+            checked += 1
+    assert checked >= 6
+    # solver flags are distinct bits
+    bits = [defines[n] for n in defines if n.startswith("STIF_KRIG_")]
+    assert len(set(bits)) == len(bits) and all(b & (b - 1) == 0 for b in bits)
